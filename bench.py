@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 NTT engine (contract: see the task statement).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU NTT on host cores
+
+Workload (BASELINE.json configs[1] / metric): forward Merge-NTT, Data64, N = 2^16, batch = 1024
+polynomials PER GPU (weak scaling; 8 GPUs = configs[4], 8192 polynomials), single 60-bit prime
+576460756061519873, X^N-1, in place, through the C ABI (gpuntt_b200_merge_ntt).  A "step" is one
+call on the whole resident batch (512 MiB per GPU, > the 126 MB L2, so no L2 flush is needed).
+
+One JSON line on stdout (rank 0).  `value` = polynomials transformed per second with data resident
+in HBM (CUDA events, max over ranks); `e2e` = the same through gpuntt_b200_merge_ntt_host with
+pinned HOST buffers, H2D + D2H inside the timed region; `roofline` = algorithmic bytes per
+merge_pass_kernel launch / its live CUDA-event duration against the measured HBM copy peak;
+`cpu_baseline` = the reference's own NTTCPU<Data64>::ntt (oracle/_ref) on all host threads over a
+bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LOGN, BATCH, BITS = 16, 1024, 64
+METRIC = "forward-NTT/s Data64 N=2^16 batch=1024"
+UNIT = "NTT/s"
+WORKLOAD = ("C2: Merge-NTT forward Data64 N=2^16 batch=1024 per GPU, single 60-bit prime "
+            "576460756061519873, X^N-1, in place (GPU_NTT_Inplace)")
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- CPU arms
+def cpu_reference_rate(count, threads=None, seed=0):
+    """(NTT/s, threads, kind) of the reference's CPU NTT over `count` polynomials of the workload."""
+    from oracle import oracle as O
+    R = O.ref()
+    if R is not None:
+        threads = threads or R.ref_hardware_threads()
+        secs = R.ref_time_merge_ntt(LOGN, O.X_N_minus, BITS, count, threads, seed)
+        return count / secs, threads, "reference"
+    # oracle/_ref absent: time the C restatement instead (one thread per core, GIL released in ctypes)
+    import concurrent.futures as cf
+    import numpy as np
+    threads = threads or os.cpu_count() or 1
+    P = O.merge_params(LOGN, O.X_N_minus, BITS)
+    x = O.example_input(P.modulus, count << LOGN, seed).reshape(count, -1)
+    L = O.lib()
+
+    def work(rows):
+        for r in rows:
+            L.ora_merge_ntt(r, LOGN, P.modulus, P.fwd, P.poly)
+    parts = [list(x[i::threads]) for i in range(threads)]
+    t0 = time.perf_counter()
+    with cf.ThreadPoolExecutor(threads) as ex:
+        list(ex.map(work, parts))
+    return count / (time.perf_counter() - t0), threads, "port"
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    R = O.ref()
+    threads = (R.ref_hardware_threads() if R is not None else os.cpu_count()) or 1
+    per_step = max(64, 2 * threads)   # bounded sample of the 1024-polynomial batch per step
+    for _ in range(args.warmup):
+        cpu_reference_rate(per_step, threads)
+    total_t, kind = 0.0, "port"
+    for s in range(args.steps):
+        rate, _, kind = cpu_reference_rate(per_step, threads, seed=s)
+        total_t += per_step / rate
+    value = per_step * args.steps / total_t
+    sample = f"{per_step} of the {BATCH} polynomials per step, NTTCPU<Data64>::ntt N=2^16 on {threads} host threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "reference CPU implementation on host cores; step = bounded sample"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev):
+        self.path = f"/tmp/bench_clocks_{os.getpid()}.csv"
+        self.proc = None
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(dev)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples_under_load": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                util = float(p[4])
+                if util < 50:
+                    continue
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+                for nm, v in zip(names, p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except ValueError:
+                continue
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons),
+                       samples_under_load=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_b200_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from gpu_ntt_b200 import capi
+    from gpu_ntt_b200.params import NTTParameters, X_N_minus
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = capi.lib()  # raises if the extension is missing
+
+    P = NTTParameters(LOGN, X_N_minus, BITS)
+    p = P.modulus
+    table = torch.from_numpy(P.gpu_root_of_unity_table_generator(P.forward_root_of_unity_table).view(np.int64)).cuda()
+    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    data = torch.randint(0, p, (BATCH, 1 << LOGN), dtype=torch.int64, device="cuda", generator=gen)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        capi.ntt(data, table, p, LOGN, X_N_minus, stream=stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    warm = max(3, args.warmup)
+    sampler = ClockSampler(local) if rank == 0 else None
+    for _ in range(warm):
+        step()
+    barrier()
+    lib.gpuntt_b200_set_profiling(1)
+    capi.profile_read()
+    launches0 = lib.gpuntt_b200_total_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.gpuntt_b200_total_launch_count() - launches0
+    recs = capi.profile_read()
+    lib.gpuntt_b200_set_profiling(0)
+    # keep the same load running ~1 s more (untimed) so the 100 ms clock sampler sees it
+    t_hold = time.perf_counter()
+    while sampler is not None and time.perf_counter() - t_hold < 1.2:
+        for _ in range(20):
+            step()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler is not None else None
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * BATCH * args.steps / (ms * 1e-3)
+
+    # live roofline of the dominant kernel (merge_pass_kernel; npasses launches per step)
+    pass_ms = [m for k, m in recs if k >= 1]
+    prep_ms = [m for k, m in recs if k == 0]
+    npasses = max(1, len(pass_ms) // max(1, args.steps))
+    alg_bytes_per_launch = 2 * (1 << LOGN) * 8 * BATCH / npasses
+    avg_pass_ms = sum(pass_ms) / max(1, len(pass_ms))
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes_per_launch / (avg_pass_ms * 1e-3) / 1e9 if pass_ms else None
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("merge_pass_kernel_dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    # end to end: pinned host buffers -> H2D -> NTT -> D2H through the host-buffer C-ABI entry point
+    import ctypes as C
+    h_in = torch.empty((BATCH, 1 << LOGN), dtype=torch.int64).pin_memory()
+    h_out = torch.empty_like(h_in).pin_memory()
+    h_in.copy_(data.cpu())
+    h_tab = P.gpu_root_of_unity_table_generator(P.forward_root_of_unity_table)
+    desc = capi.MergeDesc(BITS, 0, capi.FORWARD, LOGN, capi.PerPolynomial, X_N_minus, BATCH, 0,
+                          h_in.data_ptr(), h_out.data_ptr(), None, p, 0, None, None, stream.cuda_stream)
+
+    def e2e_step():
+        capi.check(lib.gpuntt_b200_merge_ntt_host(C.byref(desc), h_tab.ctypes.data, h_tab.size))
+    e2e_step()
+    e2e_steps = max(1, min(args.steps, 10))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()      # synchronises its stream before returning
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    nbytes = BATCH * (1 << LOGN) * 8
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "l2": "inputs (512 MiB per GPU) larger than the 126 MB L2; no flush",
+                   "plan": capi.describe_plan(LOGN, BITS).strip(), "batch_per_gpu": BATCH,
+                   "partition": f"batch slices, {world} x {BATCH} polynomials, no collective"},
+        "clocks": clocks,
+        "e2e": {"value": world * BATCH * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": nbytes + h_tab.nbytes,
+                "d2h_bytes_per_step": nbytes, "steps": e2e_steps,
+                "api": "gpuntt_b200_merge_ntt_host (pinned host in/out, copies + kernels + sync per step)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "merge_pass_kernel<u64,fwd>", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                     "peak_source": peak_src, "launches_per_step": npasses,
+                     "algorithmic_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": avg_pass_ms,
+                     "prep_kernel_avg_ms": (sum(prep_ms) / len(prep_ms)) if prep_ms else None,
+                     "frac_of_8TBps_nominal": (achieved / 8000.0) if achieved else None},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, threads, kind = cpu_reference_rate(args.cpu_sample)
+        out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
+                               "sample": f"{args.cpu_sample} polynomials of the same workload (N=2^16, Data64, seed 0), "
+                                         f"NTTCPU::ntt sharded over {threads} host threads"}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

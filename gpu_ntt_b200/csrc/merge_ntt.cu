@@ -1,0 +1,853 @@
+// gpu_ntt_b200/csrc/merge_ntt.cu -- B200 (sm_100a) Merge-NTT kernels and their host dispatcher.
+//
+// Replaces the reference's ForwardCore / InverseCore / *LowRing kernels and the GPU_NTT /
+// GPU_INTT host functions (src/lib/ntt_merge/ntt.cu:11-3097 in the reference tree) with a
+// different design:
+//   * one generic "pass" kernel: a tile of 2^k elements is staged in XOR-swizzled shared
+//     memory, then processed in register rounds of radix 2^R (R <= 4 for 64-bit, <= 5 for
+//     32-bit data): every thread owns 2^R elements of a round and performs R butterfly stages
+//     on them out of registers, so shared memory is touched once per R stages instead of once
+//     per stage, with one __syncthreads per round;
+//   * Shoup/Harvey lazy butterflies on (w, w') twiddle pairs prepared per call by a small
+//     pre-kernel (modarith.cuh);
+//   * 128-bit global and shared accesses; bank-conflict-free swizzle for every round shape;
+//   * any n_power 1..28: 1 pass (whole polynomial(s) per tile) up to 2^13 (u64) / 2^14 (u32),
+//     2 passes up to 2^22/2^23, 3 passes above; several small polynomials share one tile.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <map>
+#include <string>
+#include <tuple>
+#include <type_traits>
+#include <vector>
+
+#include "gpuntt_b200.h"
+#include "merge_ntt.cuh"
+#include "modarith.cuh"
+
+namespace gpuntt_b200
+{
+
+    // ------------------------------------------------------------------ shared-memory swizzle
+    // 16-byte chunks are XOR-permuted inside each 128-byte row by the row index (the TMA
+    // SWIZZLE_128B pattern), keeping 16-byte vectors intact:
+    //   u64: element bits [1:3] ^= bits [4:6]      u32: element bits [2:4] ^= bits [5:7]
+    template <typename T> __device__ __forceinline__ int swz(int l)
+    {
+        if constexpr (sizeof(T) == 8)
+            return l ^ (((l >> 4) & 7) << 1);
+        else
+            return l ^ (((l >> 5) & 7) << 2);
+    }
+
+    template <typename T> struct Vec16;
+    template <> struct Vec16<uint64_t>
+    {
+        using type = ulonglong2;
+        static constexpr int N = 2;
+    };
+    template <> struct Vec16<uint32_t>
+    {
+        using type = uint4;
+        static constexpr int N = 4;
+    };
+
+    template <typename T> __device__ __forceinline__ Twiddle<T> ld_tw(const Twiddle<T>* p)
+    {
+        if constexpr (sizeof(T) == 8)
+        {
+            ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(p));
+            return Twiddle<T>{v.x, v.y};
+        }
+        else
+        {
+            uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+            return Twiddle<T>{v.x, v.y};
+        }
+    }
+
+    // ------------------------------------------------------------------ one register round
+    // Item `item` of a round with local active bits [lb, lb+R): its 2^R elements are
+    // l_base | (a << lb).  Forward = Cooley-Tukey, highest active bit first; inverse =
+    // Gentleman-Sande, lowest first.  Twiddle for the stage on local bit lb+ab and element a:
+    //   index = (plus << s) + (jrow >> (rb+1)) + (a >> (ab+1)),  rb = lb+ab-c, s = n-1-lo-rb
+    // (the bit-reversed caller table makes these 2^(R-1-ab) twiddles adjacent in memory).
+    // LB0: the round's lowest active bit is local bit 0, i.e. the thread's 2^R elements are adjacent
+    // in memory: they are moved with 16-byte shared-memory accesses (conflict-free under the swizzle).
+    template <typename T, int R, bool INV, bool LB0>
+    __device__ __forceinline__ void do_round(T* sm, int item, int lb, int c, int stage_hi, int jrow,
+                                             int plus, const Twiddle<T>* __restrict__ tw, T p)
+    {
+        constexpr int E = 1 << R;
+        using V = typename Vec16<T>::type;
+        constexpr int VN = Vec16<T>::N;
+        constexpr bool VEC = LB0 && (E >= VN);
+        const T two_p = p + p;
+        if constexpr (LB0) lb = 0;
+        const int l_base = ((item >> lb) << (lb + R)) | (item & ((1 << lb) - 1));
+        T e[E];
+        if constexpr (VEC)
+        {
+#pragma unroll
+            for (int a = 0; a < E; a += VN)
+            {
+                V vv = *reinterpret_cast<const V*>(sm + swz<T>(l_base | a));
+                memcpy(&e[a], &vv, sizeof(V));
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int a = 0; a < E; a++) e[a] = sm[swz<T>(l_base | (a << lb))];
+        }
+
+        // stage_hi = s of the stage acting on local bit lb (the LOWEST active bit); the stage on
+        // bit lb+ab has s = stage_hi - ab.   rb0 = lb - c.
+        const int rb0 = lb - c;
+        if constexpr (!INV)
+        {
+#pragma unroll
+            for (int it = 0; it < R; it++)
+            {
+                const int ab = R - 1 - it;
+                const int s = stage_hi - ab;
+                const Twiddle<T>* t = tw + ((plus << s) + (jrow >> (rb0 + ab + 1)));
+#pragma unroll
+                for (int x = 0; x < (E >> (ab + 1)); x++)
+                {
+                    Twiddle<T> w = ld_tw<T>(t + x);
+#pragma unroll
+                    for (int y = 0; y < (1 << ab); y++)
+                    {
+                        const int a0 = (x << (ab + 1)) | y;
+                        ct_butterfly<T>(e[a0], e[a0 | (1 << ab)], w, p, two_p);
+                    }
+                }
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int ab = 0; ab < R; ab++)
+            {
+                const int s = stage_hi - ab;
+                const Twiddle<T>* t = tw + ((plus << s) + (jrow >> (rb0 + ab + 1)));
+#pragma unroll
+                for (int x = 0; x < (E >> (ab + 1)); x++)
+                {
+                    Twiddle<T> w = ld_tw<T>(t + x);
+#pragma unroll
+                    for (int y = 0; y < (1 << ab); y++)
+                    {
+                        const int a0 = (x << (ab + 1)) | y;
+                        gs_butterfly<T>(e[a0], e[a0 | (1 << ab)], w, p, two_p);
+                    }
+                }
+            }
+        }
+        if constexpr (VEC)
+        {
+#pragma unroll
+            for (int a = 0; a < E; a += VN)
+            {
+                V vv;
+                memcpy(&vv, &e[a], sizeof(V));
+                *reinterpret_cast<V*>(sm + swz<T>(l_base | a)) = vv;
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int a = 0; a < E; a++) sm[swz<T>(l_base | (a << lb))] = e[a];
+        }
+    }
+
+    // ------------------------------------------------------------------ the pass kernel
+    template <typename T, bool INV, bool RNS>
+    __global__ void __launch_bounds__(kThreads) merge_pass_kernel(const PassArgs<T> a)
+    {
+        extern __shared__ __align__(16) unsigned char smem_raw[];
+        T* sm = reinterpret_cast<T*>(smem_raw);
+        using ST = typename std::make_signed<T>::type;
+        using V = typename Vec16<T>::type;
+        constexpr int VN = Vec16<T>::N;
+
+        const PassPlan& pl = a.plan;
+        const int k = pl.tile_log, n = a.n_power, c = pl.c, lo = pl.lo;
+        const int tile_elems = 1 << k;
+        const int tid = threadIdx.x;
+
+        // ---- which tile is this?
+        const long long tile = blockIdx.x;
+        long long gbase;   // global element offset of local index 0
+        int jrow_tile;     // (index within polynomial >> lo) of local row 0
+        long long poly0;   // polynomial of local index 0
+        if (lo > 0)
+        {
+            const int hi = lo + pl.d;
+            const int cc_bits = lo - c, pre_bits = n - hi;
+            const long long cc = tile & ((1LL << cc_bits) - 1);
+            const long long P = (tile >> cc_bits) & ((1LL << pre_bits) - 1);
+            poly0 = tile >> (cc_bits + pre_bits);
+            gbase = (poly0 << n) + (P << hi) + (cc << c);
+            jrow_tile = (int) (P << pl.d);
+        }
+        else
+        {
+            gbase = tile << k;
+            jrow_tile = (int) (gbase & ((1LL << n) - 1));
+            poly0 = gbase >> n;
+        }
+        const int cmask = (1 << c) - 1;
+        const int poly_shift = n - lo; // (l >> c) >> poly_shift = polynomial offset inside the tile
+
+        // ---- global -> shared
+        {
+            const bool fix_signed = (!INV) && pl.first && a.signed_io;
+            const T* gin = reinterpret_cast<const T*>(a.in);
+            const bool vec_ok = ((reinterpret_cast<uintptr_t>(gin) & 15) == 0) && (c == 0 || c >= 2) &&
+                                (k >= 2);
+            for (int l = tid * VN; l < tile_elems; l += kThreads * VN)
+            {
+                const int row = l >> c, col = l & cmask;
+                const long long g = gbase + ((long long) row << lo) + col;
+                T v[VN];
+                if (vec_ok && g + VN <= a.total_elems)
+                {
+                    V vv = *reinterpret_cast<const V*>(gin + g);
+                    memcpy(v, &vv, sizeof(V));
+                }
+                else
+                {
+#pragma unroll
+                    for (int i = 0; i < VN; i++)
+                    {
+                        // (c < 2 only happens for contiguous tiles, where l+i is simply g+i)
+                        v[i] = (g + i < a.total_elems) ? gin[g + i] : T(0);
+                    }
+                }
+                if (fix_signed)
+                {
+                    T p = a.p;
+                    if constexpr (RNS)
+                        p = a.mod_values[3 * (int) ((poly0 + (row >> poly_shift)) % a.mod_count)];
+#pragma unroll
+                    for (int i = 0; i < VN; i++)
+                        if ((ST) v[i] < 0) v[i] += p; // p - |x|  (modular_arith.cuh:372-385 of the reference)
+                }
+                V vv;
+                memcpy(&vv, v, sizeof(V));
+                *reinterpret_cast<V*>(sm + swz<T>(l)) = vv;
+            }
+        }
+
+        // ---- register rounds
+        int lb_fwd[kMaxRounds]; // local low bit of each round
+        {
+            int acc = c + pl.d;
+#pragma unroll
+            for (int r = 0; r < kMaxRounds; r++)
+            {
+                if (r < pl.nrounds) acc -= pl.round_bits[r];
+                lb_fwd[r] = acc;
+            }
+        }
+#pragma unroll 1
+        for (int ri = 0; ri < pl.nrounds; ri++)
+        {
+            const int r = INV ? (pl.nrounds - 1 - ri) : ri;
+            int R = 0, lb = 0;
+#pragma unroll
+            for (int q = 0; q < kMaxRounds; q++)
+                if (q == r)
+                {
+                    R = pl.round_bits[q];
+                    lb = lb_fwd[q];
+                }
+            __syncthreads();
+            const int items = tile_elems >> R;
+            const int stage_hi = n - 1 - lo - (lb - c);
+#pragma unroll 1
+            for (int item = tid; item < items; item += kThreads)
+            {
+                const int l_base = ((item >> lb) << (lb + R)) | (item & ((1 << lb) - 1));
+                const int row = l_base >> c;
+                const int jrow = (jrow_tile | row) & ((1 << poly_shift) - 1);
+                T p = a.p;
+                const Twiddle<T>* tw = reinterpret_cast<const Twiddle<T>*>(a.tw);
+                if constexpr (RNS)
+                {
+                    const int mi = (int) ((poly0 + (row >> poly_shift)) % a.mod_count);
+                    p = a.mod_values[3 * mi];
+                    tw += ((size_t) mi << a.tw_stride_log);
+                }
+                if (lb == 0)
+                    switch (R)
+                    {
+                        case 1: do_round<T, 1, INV, true>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, p); break;
+                        case 2: do_round<T, 2, INV, true>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, p); break;
+                        case 3: do_round<T, 3, INV, true>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, p); break;
+                        case 4: do_round<T, 4, INV, true>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, p); break;
+                        default:
+                            if constexpr (sizeof(T) == 4)
+                                do_round<T, 5, INV, true>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, p);
+                            break;
+                    }
+                else
+                    switch (R)
+                    {
+                        case 1: do_round<T, 1, INV, false>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, p); break;
+                        case 2: do_round<T, 2, INV, false>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, p); break;
+                        case 3: do_round<T, 3, INV, false>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, p); break;
+                        default: do_round<T, 4, INV, false>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, p); break;
+                    }
+            }
+        }
+        __syncthreads();
+
+        // ---- shared -> global
+        {
+            T* gout = a.out;
+            const bool vec_ok = ((reinterpret_cast<uintptr_t>(gout) & 15) == 0) && (c == 0 || c >= 2) &&
+                                (k >= 2);
+            const bool centre = INV && pl.last && a.signed_io;
+            for (int l = tid * VN; l < tile_elems; l += kThreads * VN)
+            {
+                const int row = l >> c, col = l & cmask;
+                const long long g = gbase + ((long long) row << lo) + col;
+                if (g >= a.total_elems) continue;
+                V vv = *reinterpret_cast<const V*>(sm + swz<T>(l));
+                T v[VN];
+                memcpy(v, &vv, sizeof(V));
+                if (pl.last)
+                {
+                    T p = a.p;
+                    Twiddle<T> ni{a.ninv_w, a.ninv_wq};
+                    if constexpr (RNS)
+                    {
+                        const int mi = (int) ((poly0 + (row >> poly_shift)) % a.mod_count);
+                        p = a.mod_values[3 * mi];
+                        if constexpr (INV) ni = reinterpret_cast<const Twiddle<T>*>(a.ninv_tw)[mi];
+                    }
+                    const T two_p = p + p;
+#pragma unroll
+                    for (int i = 0; i < VN; i++)
+                    {
+                        if constexpr (INV)
+                        {
+                            T x = shoup_mul_lazy<T>(v[i], ni, p); // [0,2p)
+                            x = csub(x, p);
+                            if (centre && x > (p >> 1)) x -= p; // modular_arith.cuh:389-405 of the reference
+                            v[i] = x;
+                        }
+                        else
+                            v[i] = canon4(v[i], p, two_p);
+                    }
+                }
+                if (vec_ok && g + VN <= a.total_elems)
+                {
+                    memcpy(&vv, v, sizeof(V));
+                    *reinterpret_cast<V*>(gout + g) = vv;
+                }
+                else
+                {
+#pragma unroll
+                    for (int i = 0; i < VN; i++)
+                        if (g + i < a.total_elems) gout[g + i] = v[i];
+                }
+            }
+        }
+    }
+
+    // ------------------------------------------------------------------ twiddle companion pre-kernel
+    // out[(m << stride_log) + i] = { w, floor(w * 2^BITS / p_m) }  for the caller's table slice m;
+    // after the slices: the same pair for n^-1 of every modulus (RNS inverse only).
+    template <typename T>
+    __global__ void twiddle_prep_kernel(const T* __restrict__ table, Twiddle<T>* __restrict__ out,
+                                        const T* __restrict__ mod_values, T p_single, int slices,
+                                        int stride_log, long long table_len,
+                                        const T* __restrict__ ninv_dev, Twiddle<T>* __restrict__ ninv_out)
+    {
+        const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+        const int m = blockIdx.y;
+        const T p = mod_values ? mod_values[3 * m] : p_single;
+        if (i < table_len)
+        {
+            const size_t idx = ((size_t) m << stride_log) + (size_t) i;
+            const T w = table[idx];
+            out[idx] = Twiddle<T>{w, shoup_companion(w, p)};
+        }
+        if (ninv_dev && i == 0)
+        {
+            const T w = ninv_dev[m];
+            ninv_out[m] = Twiddle<T>{w, shoup_companion(w, p)};
+        }
+    }
+
+    // ------------------------------------------------------------------ launch plan
+    static void split_rounds(PassPlan& ps, int element_bits)
+    {
+        // rounds listed from the highest bits down.  The lowest round of a contiguous 32-bit
+        // tile is radix-32 so that no round starts at local bit 4 (bank conflicts).
+        int d = ps.d, nr = 0;
+        int rounds_low_first[kMaxRounds];
+        if (element_bits == 32 && ps.lo == 0 && d >= 5)
+        {
+            rounds_low_first[nr++] = 5;
+            d -= 5;
+        }
+        while (d > 0)
+        {
+            int r = d >= 4 ? 4 : d;
+            rounds_low_first[nr++] = r;
+            d -= r;
+        }
+        ps.nrounds = nr;
+        for (int i = 0; i < nr; i++) ps.round_bits[i] = rounds_low_first[nr - 1 - i];
+        for (int i = nr; i < kMaxRounds; i++) ps.round_bits[i] = 0;
+    }
+
+    MergePlan make_merge_plan(int n, int element_bits)
+    {
+        MergePlan mp{};
+        const int kmax = (element_bits == 64) ? 13 : 14;   // 64 KiB tiles at most
+        const int cmin = (element_bits == 64) ? 4 : 5;     // 128-byte row segments in strided tiles
+        const int kpref = 12;                              // preferred tile: 4096 elements
+        auto contiguous = [&](int d)
+        {
+            PassPlan ps{};
+            ps.lo = 0;
+            ps.c = 0;
+            ps.d = d;
+            ps.tile_log = d > 11 ? d : 11; // small rings: several polynomials per 2048-element tile
+            if (d <= kpref && d > 0 && n > d) ps.tile_log = kpref;
+            split_rounds(ps, element_bits);
+            return ps;
+        };
+        auto strided = [&](int lo, int d)
+        {
+            PassPlan ps{};
+            ps.lo = lo;
+            ps.d = d;
+            int c = kpref - d;
+            if (c < cmin) c = cmin;
+            if (c > lo) c = lo;
+            ps.c = c;
+            ps.tile_log = d + c;
+            split_rounds(ps, element_bits);
+            return ps;
+        };
+        if (n <= kmax)
+        {
+            mp.npasses = 1;
+            mp.pass[0] = contiguous(n);
+        }
+        else if (n <= 2 * kmax - cmin)
+        {
+            int d1 = n / 2;
+            if (d1 > kmax - cmin) d1 = kmax - cmin; // strided tile = 2^(d1 + c) elements <= 64 KiB
+            int d2 = n - d1;
+            mp.npasses = 2;
+            mp.pass[0] = strided(d2, d1);
+            mp.pass[1] = contiguous(d2);
+        }
+        else
+        {
+            int d1 = n / 3, d2 = n / 3, d3 = n - d1 - d2;
+            mp.npasses = 3;
+            mp.pass[0] = strided(d2 + d3, d1);
+            mp.pass[1] = strided(d3, d2);
+            mp.pass[2] = contiguous(d3);
+        }
+        for (int i = 0; i < mp.npasses; i++)
+        {
+            mp.pass[i].first = 0;
+            mp.pass[i].last = 0;
+        }
+        return mp;
+    }
+
+    // ------------------------------------------------------------------ host side
+    thread_local std::string g_last_error;
+    thread_local int g_last_launches = 0;
+    static std::atomic<unsigned long long> g_total_launches{0};
+
+    // Optional per-launch device timing (bench.py's live roofline): when enabled, every launch is
+    // bracketed by CUDA events on the launching stream; gpuntt_b200_profile_read() resolves them.
+    struct ProfRec
+    {
+        cudaEvent_t e0, e1;
+        int kind; // 0 = twiddle_prep_kernel, 1.. = merge pass number (1-based, execution order)
+    };
+    static std::atomic<int> g_profiling{0};
+    static std::mutex g_prof_mutex;
+    static std::vector<ProfRec> g_prof;
+
+    struct ProfScope
+    {
+        bool on;
+        ProfRec r;
+        cudaStream_t st;
+        ProfScope(int kind, cudaStream_t s) : on(g_profiling.load() != 0), st(s)
+        {
+            if (!on) return;
+            r.kind = kind;
+            cudaEventCreate(&r.e0);
+            cudaEventCreate(&r.e1);
+            cudaEventRecord(r.e0, st);
+        }
+        ~ProfScope()
+        {
+            if (!on) return;
+            cudaEventRecord(r.e1, st);
+            std::lock_guard<std::mutex> lk(g_prof_mutex);
+            g_prof.push_back(r);
+        }
+    };
+
+    static int fail(int code, const std::string& msg)
+    {
+        g_last_error = msg;
+        return code;
+    }
+    static int cuda_fail(cudaError_t e, const char* what)
+    {
+        return fail(GPUNTT_B200_ERR_CUDA,
+                    std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
+    }
+
+    struct Workspace
+    {
+        void* ptr = nullptr;
+        size_t bytes = 0;
+    };
+    static std::mutex g_ws_mutex;
+    static std::map<std::tuple<int, void*, int>, Workspace> g_ws; // (device, stream, slot)
+
+    // slot 0: twiddle companions; slots 1,2: host-convenience staging buffers
+    static cudaError_t get_workspace(void* stream, int slot, size_t bytes, void** out)
+    {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        std::lock_guard<std::mutex> lk(g_ws_mutex);
+        Workspace& w = g_ws[std::make_tuple(dev, stream, slot)];
+        if (w.bytes < bytes)
+        {
+            if (w.ptr)
+            {
+                // in-flight kernels of earlier calls may still read the old buffer
+                e = cudaStreamSynchronize((cudaStream_t) stream);
+                if (e != cudaSuccess) return e;
+                cudaFree(w.ptr);
+                w.ptr = nullptr;
+                w.bytes = 0;
+            }
+            size_t want = bytes < (1u << 20) ? (1u << 20) : bytes;
+            e = cudaMalloc(&w.ptr, want);
+            if (e != cudaSuccess) return e;
+            w.bytes = want;
+        }
+        *out = w.ptr;
+        return cudaSuccess;
+    }
+
+    template <typename K> static cudaError_t allow_smem(K kernel, size_t bytes)
+    {
+        if (bytes <= 48 * 1024) return cudaSuccess;
+        return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    }
+
+    template <typename T, bool INV, bool RNS>
+    static cudaError_t launch_pass(const PassArgs<T>& args, int batch, cudaStream_t st, int pass_no)
+    {
+        ProfScope prof(pass_no, st);
+        const PassPlan& pl = args.plan;
+        const long long total = (long long) batch << args.n_power;
+        long long tiles;
+        if (pl.lo > 0)
+            tiles = total >> pl.tile_log;
+        else
+            tiles = (total + (1LL << pl.tile_log) - 1) >> pl.tile_log;
+        const size_t smem = sizeof(T) << pl.tile_log;
+        auto kern = merge_pass_kernel<T, INV, RNS>;
+        cudaError_t e = allow_smem(kern, smem);
+        if (e != cudaSuccess) return e;
+        kern<<<(unsigned) tiles, kThreads, smem, st>>>(args);
+        g_last_launches++;
+        g_total_launches++;
+        return cudaGetLastError();
+    }
+
+    template <typename T> static int merge_execute_t(const gpuntt_b200_merge_desc* d)
+    {
+        const int n = d->n_power;
+        const bool inv = d->direction == GPUNTT_B200_INVERSE;
+        const bool rns = d->mod_count > 0;
+        const bool plus = d->reduction_poly == GPUNTT_B200_X_N_PLUS;
+        cudaStream_t st = (cudaStream_t) d->stream;
+        const int slices = rns ? d->mod_count : 1;
+        const long long table_len = plus ? (1LL << n) : (1LL << (n - 1));
+        const int stride_log = n; // the reference's RNS tables are spaced (1 << n_power) apart for both ring types
+
+        // scratch: (w, w') pairs for every table entry (+ n^-1 pairs for RNS inverse)
+        const size_t tw_elems = ((size_t) (slices - 1) << stride_log) + (size_t) table_len;
+        const size_t bytes = (tw_elems + (size_t) slices) * sizeof(Twiddle<T>);
+        void* ws = nullptr;
+        cudaError_t e = get_workspace(d->stream, 0, bytes, &ws);
+        if (e != cudaSuccess) return cuda_fail(e, "workspace allocation");
+        Twiddle<T>* tw = reinterpret_cast<Twiddle<T>*>(ws);
+        Twiddle<T>* ninv_tw = tw + tw_elems;
+
+        const T* mod_values = rns ? reinterpret_cast<const T*>(d->modulus_dev) : nullptr;
+        {
+            ProfScope prof(0, st);
+            const int threads = 256;
+            dim3 grid((unsigned) ((table_len + threads - 1) / threads), (unsigned) slices);
+            twiddle_prep_kernel<T><<<grid, threads, 0, st>>>(
+                reinterpret_cast<const T*>(d->root_of_unity_table), tw, mod_values, (T) d->modulus_value,
+                slices, stride_log, table_len,
+                (rns && inv) ? reinterpret_cast<const T*>(d->mod_inverse_dev) : nullptr, ninv_tw);
+            g_last_launches++;
+            g_total_launches++;
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return cuda_fail(e, "twiddle_prep_kernel launch");
+        }
+
+        MergePlan mp = make_merge_plan(n, (int) sizeof(T) * 8);
+        PassArgs<T> args{};
+        args.tw = tw;
+        args.mod_values = mod_values;
+        args.ninv_tw = ninv_tw;
+        args.p = (T) d->modulus_value;
+        if (inv && !rns)
+        {
+            const T p = (T) d->modulus_value, w = (T) d->mod_inverse_value;
+            args.ninv_w = w;
+            if constexpr (sizeof(T) == 8)
+                args.ninv_wq = p ? (T) ((((unsigned __int128) w) << 64) / p) : 0;
+            else
+                args.ninv_wq = p ? (T) ((((uint64_t) w) << 32) / p) : 0;
+        }
+        args.n_power = n;
+        args.mod_count = d->mod_count;
+        args.tw_stride_log = stride_log;
+        args.plus = plus ? 1 : 0;
+        args.signed_io = d->is_signed ? 1 : 0;
+        args.total_elems = (long long) d->batch_size << n;
+
+        for (int i = 0; i < mp.npasses; i++)
+        {
+            const int pi = inv ? (mp.npasses - 1 - i) : i;
+            args.plan = mp.pass[pi];
+            args.plan.first = (i == 0);
+            args.plan.last = (i == mp.npasses - 1);
+            args.in = (i == 0) ? d->in : d->out; // later passes chain through `out` (also out of place)
+            args.out = reinterpret_cast<T*>(d->out);
+            if (inv)
+                e = rns ? launch_pass<T, true, true>(args, d->batch_size, st, i + 1)
+                        : launch_pass<T, true, false>(args, d->batch_size, st, i + 1);
+            else
+                e = rns ? launch_pass<T, false, true>(args, d->batch_size, st, i + 1)
+                        : launch_pass<T, false, false>(args, d->batch_size, st, i + 1);
+            if (e != cudaSuccess) return cuda_fail(e, "merge_pass_kernel launch");
+        }
+        return GPUNTT_B200_OK;
+    }
+
+    static int merge_execute(const gpuntt_b200_merge_desc* d)
+    {
+        g_last_launches = 0;
+        if (!d) return fail(GPUNTT_B200_ERR_ARGUMENT, "null descriptor");
+        if (d->ntt_layout == GPUNTT_B200_PER_COEFFICIENT)
+            return fail(GPUNTT_B200_ERR_UNSUPPORTED,
+                        "NTTLayout::PerCoefficient is not built yet (SURVEY.md 8f rank 2)");
+        if (d->ntt_layout != GPUNTT_B200_PER_POLYNOMIAL)
+            return fail(GPUNTT_B200_ERR_LAYOUT, "Invalid ntt_layout!");
+        if (d->n_power < 1 || d->n_power > 28) return fail(GPUNTT_B200_ERR_N_POWER, "Invalid n_power range!");
+        if (d->element_bits != 32 && d->element_bits != 64)
+            return fail(GPUNTT_B200_ERR_ARGUMENT, "element_bits must be 32 or 64");
+        if (d->batch_size < 0 || d->mod_count < 0) return fail(GPUNTT_B200_ERR_ARGUMENT, "negative batch_size / mod_count");
+        if (d->direction != GPUNTT_B200_FORWARD && d->direction != GPUNTT_B200_INVERSE)
+            return fail(GPUNTT_B200_ERR_ARGUMENT, "direction must be FORWARD or INVERSE");
+        if (d->reduction_poly != GPUNTT_B200_X_N_PLUS && d->reduction_poly != GPUNTT_B200_X_N_MINUS)
+            return fail(GPUNTT_B200_ERR_ARGUMENT, "reduction_poly must be X_N_plus or X_N_minus");
+        if (d->batch_size == 0) return GPUNTT_B200_OK;
+        if (!d->in || !d->out || !d->root_of_unity_table)
+            return fail(GPUNTT_B200_ERR_ARGUMENT, "null data / table pointer");
+        if (d->mod_count > 0 && !d->modulus_dev) return fail(GPUNTT_B200_ERR_ARGUMENT, "RNS form needs modulus_dev");
+        if (d->mod_count > 0 && d->direction == GPUNTT_B200_INVERSE && !d->mod_inverse_dev)
+            return fail(GPUNTT_B200_ERR_ARGUMENT, "RNS inverse needs mod_inverse_dev");
+        if (d->mod_count == 0 && d->modulus_value < 2) return fail(GPUNTT_B200_ERR_ARGUMENT, "modulus_value < 2");
+        if (d->element_bits == 64) return merge_execute_t<uint64_t>(d);
+        return merge_execute_t<uint32_t>(d);
+    }
+
+} // namespace gpuntt_b200
+
+using namespace gpuntt_b200;
+
+extern "C"
+{
+    int gpuntt_b200_merge_ntt(const gpuntt_b200_merge_desc* desc) { return merge_execute(desc); }
+
+    static gpuntt_b200_merge_desc simple_desc(int bits, int dir, const void* in, void* out, const void* table,
+                                              uint64_t p, uint64_t ninv, int n_power, int poly, int batch,
+                                              void* stream)
+    {
+        gpuntt_b200_merge_desc d;
+        memset(&d, 0, sizeof(d));
+        d.element_bits = bits;
+        d.direction = dir;
+        d.n_power = n_power;
+        d.ntt_layout = GPUNTT_B200_PER_POLYNOMIAL;
+        d.reduction_poly = poly;
+        d.batch_size = batch;
+        d.in = in;
+        d.out = out;
+        d.root_of_unity_table = table;
+        d.modulus_value = p;
+        d.mod_inverse_value = ninv;
+        d.stream = stream;
+        return d;
+    }
+
+    int gpuntt_b200_ntt_u64(const uint64_t* in, uint64_t* out, const uint64_t* root_table, uint64_t modulus,
+                            int n_power, int reduction_poly, int batch_size, void* stream)
+    {
+        gpuntt_b200_merge_desc d = simple_desc(64, GPUNTT_B200_FORWARD, in, out, root_table, modulus, 0, n_power,
+                                               reduction_poly, batch_size, stream);
+        return merge_execute(&d);
+    }
+    int gpuntt_b200_intt_u64(const uint64_t* in, uint64_t* out, const uint64_t* inv_root_table, uint64_t modulus,
+                             uint64_t n_inverse, int n_power, int reduction_poly, int batch_size, void* stream)
+    {
+        gpuntt_b200_merge_desc d = simple_desc(64, GPUNTT_B200_INVERSE, in, out, inv_root_table, modulus, n_inverse,
+                                               n_power, reduction_poly, batch_size, stream);
+        return merge_execute(&d);
+    }
+    int gpuntt_b200_ntt_u32(const uint32_t* in, uint32_t* out, const uint32_t* root_table, uint32_t modulus,
+                            int n_power, int reduction_poly, int batch_size, void* stream)
+    {
+        gpuntt_b200_merge_desc d = simple_desc(32, GPUNTT_B200_FORWARD, in, out, root_table, modulus, 0, n_power,
+                                               reduction_poly, batch_size, stream);
+        return merge_execute(&d);
+    }
+    int gpuntt_b200_intt_u32(const uint32_t* in, uint32_t* out, const uint32_t* inv_root_table, uint32_t modulus,
+                             uint32_t n_inverse, int n_power, int reduction_poly, int batch_size, void* stream)
+    {
+        gpuntt_b200_merge_desc d = simple_desc(32, GPUNTT_B200_INVERSE, in, out, inv_root_table, modulus, n_inverse,
+                                               n_power, reduction_poly, batch_size, stream);
+        return merge_execute(&d);
+    }
+
+    int gpuntt_b200_merge_ntt_host(const gpuntt_b200_merge_desc* hd, const void* host_root_table,
+                                   size_t root_table_elems)
+    {
+        g_last_launches = 0;
+        if (!hd || !hd->in || !hd->out || !host_root_table) return fail(GPUNTT_B200_ERR_ARGUMENT, "null pointer");
+        if (hd->mod_count != 0) return fail(GPUNTT_B200_ERR_UNSUPPORTED, "host convenience call is single-modulus only");
+        if (hd->n_power < 1 || hd->n_power > 28) return fail(GPUNTT_B200_ERR_N_POWER, "Invalid n_power range!");
+        if (hd->element_bits != 32 && hd->element_bits != 64)
+            return fail(GPUNTT_B200_ERR_ARGUMENT, "element_bits must be 32 or 64");
+        const size_t esz = hd->element_bits / 8;
+        const size_t data_bytes = ((size_t) hd->batch_size << hd->n_power) * esz;
+        const size_t table_bytes = root_table_elems * esz;
+        cudaStream_t st = (cudaStream_t) hd->stream;
+        void *dbuf = nullptr, *dtab = nullptr;
+        cudaError_t e = get_workspace(hd->stream, 1, data_bytes, &dbuf);
+        if (e != cudaSuccess) return cuda_fail(e, "staging allocation");
+        e = get_workspace(hd->stream, 2, table_bytes, &dtab);
+        if (e != cudaSuccess) return cuda_fail(e, "staging allocation");
+        e = cudaMemcpyAsync(dtab, host_root_table, table_bytes, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return cuda_fail(e, "table H2D");
+        e = cudaMemcpyAsync(dbuf, hd->in, data_bytes, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return cuda_fail(e, "data H2D");
+        gpuntt_b200_merge_desc d = *hd;
+        d.in = dbuf;
+        d.out = dbuf;
+        d.root_of_unity_table = dtab;
+        int rc = merge_execute(&d);
+        if (rc != GPUNTT_B200_OK) return rc;
+        e = cudaMemcpyAsync(hd->out, dbuf, data_bytes, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return cuda_fail(e, "data D2H");
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return cuda_fail(e, "stream synchronize");
+        return GPUNTT_B200_OK;
+    }
+
+    int gpuntt_b200_last_launch_count(void) { return g_last_launches; }
+    unsigned long long gpuntt_b200_total_launch_count(void) { return g_total_launches.load(); }
+    const char* gpuntt_b200_last_error(void) { return g_last_error.c_str(); }
+
+    void gpuntt_b200_release_workspaces(void)
+    {
+        std::lock_guard<std::mutex> lk(g_ws_mutex);
+        for (auto& kv : g_ws)
+            if (kv.second.ptr)
+            {
+                cudaSetDevice(std::get<0>(kv.first));
+                cudaDeviceSynchronize();
+                cudaFree(kv.second.ptr);
+            }
+        g_ws.clear();
+    }
+
+    int gpuntt_b200_describe_plan(int n_power, int element_bits, char* buf, size_t buf_len)
+    {
+        if (n_power < 1 || n_power > 28 || (element_bits != 32 && element_bits != 64)) return -1;
+        MergePlan mp = make_merge_plan(n_power, element_bits);
+        std::string s;
+        char tmp[256];
+        for (int i = 0; i < mp.npasses; i++)
+        {
+            const PassPlan& p = mp.pass[i];
+            snprintf(tmp, sizeof(tmp), "pass%d{tile=2^%d %s lo=%d d=%d c=%d rounds=", i, p.tile_log,
+                     p.lo ? "strided" : "contiguous", p.lo, p.d, p.c);
+            s += tmp;
+            for (int r = 0; r < p.nrounds; r++)
+            {
+                snprintf(tmp, sizeof(tmp), "%s%d", r ? "," : "", p.round_bits[r]);
+                s += tmp;
+            }
+            s += "} ";
+        }
+        if (buf && buf_len)
+        {
+            strncpy(buf, s.c_str(), buf_len - 1);
+            buf[buf_len - 1] = 0;
+        }
+        return mp.npasses;
+    }
+
+    void gpuntt_b200_set_profiling(int on) { g_profiling.store(on ? 1 : 0); }
+
+    int gpuntt_b200_profile_read(float* ms_out, int* kind_out, int max_records)
+    {
+        std::vector<ProfRec> recs;
+        {
+            std::lock_guard<std::mutex> lk(g_prof_mutex);
+            recs.swap(g_prof);
+        }
+        int n = 0;
+        for (auto& r : recs)
+        {
+            float ms = 0.f;
+            cudaEventSynchronize(r.e1);
+            cudaEventElapsedTime(&ms, r.e0, r.e1);
+            if (n < max_records)
+            {
+                if (ms_out) ms_out[n] = ms;
+                if (kind_out) kind_out[n] = r.kind;
+                n++;
+            }
+            cudaEventDestroy(r.e0);
+            cudaEventDestroy(r.e1);
+        }
+        return n;
+    }
+
+    int gpuntt_b200_version(void) { return GPUNTT_B200_VERSION; }
+}

@@ -1,0 +1,145 @@
+/*
+ * gpuntt_b200.h -- C ABI of the B200-native (sm_100a) batched NTT/INTT engine.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Every entry
+ * point replaces one host entry point of Alisah-Ozcan/GPU-NTT (citations are file:line in the
+ * reference tree); the C++17 headers under include/gpuntt/ re-create the reference's template
+ * API (GPU_NTT / GPU_INTT / GPU_NTT_Inplace / GPU_INTT_Inplace, ntt_configuration,
+ * NTTParameters ...) as thin forwarders onto these functions, so reference callers recompile
+ * unchanged; see INTEGRATION.md.
+ *
+ * Conventions (identical to the reference):
+ *  - all data/table/modulus pointers are DEVICE pointers owned by the caller;
+ *  - polynomials are rows of a row-major [batch][N] array, N = 1 << n_power;
+ *  - forward: natural-order coefficients in, bit-reversed-order evaluations out; inverse: the
+ *    opposite, including the multiplication by N^-1 (mod_inverse);
+ *  - root_of_unity_table is the BIT-REVERSED power table the reference's
+ *    NTTParameters::gpu_root_of_unity_table_generator produces (nttparameters.cu:175-189):
+ *    N/2 powers of omega for X^N-1, N powers of psi for X^N+1;
+ *  - RNS form: polynomial b uses modulus[b % mod_count], table slice starting at element
+ *    (b % mod_count) << n_power, mod_inverse[b % mod_count] (ntt.cu:613-619,672-673);
+ *  - calls only enqueue work on `stream` and return; they never synchronise;
+ *  - in == out is allowed (that is all the reference's *_Inplace entry points do).
+ *
+ * Unlike the reference the engine keeps one small device scratch buffer per (device, stream)
+ * for the per-call twiddle companion table; it is allocated on first use,
+ * grown on demand and released by gpuntt_b200_release_workspaces().
+ *
+ * There is no CPU fallback: every function fails with GPUNTT_B200_ERR_CUDA if no usable
+ * sm_100 device/context exists.
+ */
+#ifndef GPUNTT_B200_H
+#define GPUNTT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPUNTT_B200_VERSION 100 /* 0.1.0 */
+
+typedef enum gpuntt_b200_status
+{
+    GPUNTT_B200_OK = 0,
+    GPUNTT_B200_ERR_N_POWER = 1,     /* "Invalid n_power range!"  (ntt.cu:2088-2091) */
+    GPUNTT_B200_ERR_LAYOUT = 2,      /* "Invalid ntt_layout!"     (ntt.cu:2253)      */
+    GPUNTT_B200_ERR_CUDA = 3,        /* a CUDA runtime call / launch failed (GPUNTT_CUDA_CHECK) */
+    GPUNTT_B200_ERR_ARGUMENT = 4,    /* null pointer, negative batch, bad enum ...   */
+    GPUNTT_B200_ERR_UNSUPPORTED = 5  /* valid in the reference but not built yet     */
+} gpuntt_b200_status;
+
+/* enum values equal the reference's (nttparameters.cuh:19-36) */
+enum { GPUNTT_B200_FORWARD = 0, GPUNTT_B200_INVERSE = 1 };
+enum { GPUNTT_B200_PER_POLYNOMIAL = 0, GPUNTT_B200_PER_COEFFICIENT = 1 };
+enum { GPUNTT_B200_X_N_PLUS = 0, GPUNTT_B200_X_N_MINUS = 1 };
+
+/* Same layout as the reference's Modulus<Data64> / Modulus<Data32> (modular_arith.cuh:28-57):
+ * value = p, bit = bit length of p, mu = floor(2^(2*bit+1) / p).  Only `value` is read by this
+ * engine (it derives its own reduction constants); bit/mu are carried for ABI compatibility. */
+typedef struct gpuntt_b200_modulus64 { uint64_t value, bit, mu; } gpuntt_b200_modulus64;
+typedef struct gpuntt_b200_modulus32 { uint32_t value, bit, mu; } gpuntt_b200_modulus32;
+
+/* One Merge-NTT call.  Replaces, depending on the fields,
+ *   GPU_NTT  single modulus (ntt.cu:2076-2256)   GPU_NTT  RNS (ntt.cu:2560-2746)
+ *   GPU_INTT single modulus (ntt.cu:2258-2558)   GPU_INTT RNS (ntt.cu:2748-3058)
+ *   GPU_NTT_Inplace / GPU_INTT_Inplace (ntt.cu:3060-3097): pass in == out.
+ * The ntt_configuration / ntt_rns_configuration fields (ntt.cuh:31-51) map 1:1:
+ *   n_power, ntt_layout, reduction_poly, mod_inverse(_dev), stream; `direction` is the function
+ *   name in the reference (its cfg.ntt_type is ignored there); zero_padding is never read by the
+ *   reference and has no field here. */
+typedef struct gpuntt_b200_merge_desc
+{
+    int element_bits;     /* 32 (Data32/Data32s) or 64 (Data64/Data64s)                       */
+    int is_signed;        /* T = Data32s/Data64s: signed INPUT on forward (reduced into [0,p)
+                             on load, ntt.cu:481-489), centred signed OUTPUT on inverse
+                             (ntt.cu:1178-1186)                                               */
+    int direction;        /* GPUNTT_B200_FORWARD / GPUNTT_B200_INVERSE                        */
+    int n_power;          /* 1..28                                                            */
+    int ntt_layout;       /* GPUNTT_B200_PER_POLYNOMIAL (PER_COEFFICIENT: see status codes)   */
+    int reduction_poly;   /* GPUNTT_B200_X_N_PLUS / GPUNTT_B200_X_N_MINUS                     */
+    int batch_size;       /* number of polynomials                                           */
+    int mod_count;        /* 0: single modulus by value; >= 1: RNS form, arrays on device     */
+    const void* in;       /* device, [batch][N] elements                                      */
+    void* out;            /* device, [batch][N] elements (may equal in)                       */
+    const void* root_of_unity_table; /* device, bit-reversed order (see above)                */
+    uint64_t modulus_value;          /* single-modulus form: p                                */
+    uint64_t mod_inverse_value;      /* single-modulus inverse: N^-1 mod p                    */
+    const void* modulus_dev;         /* RNS: device array of gpuntt_b200_modulus{32,64}       */
+    const void* mod_inverse_dev;     /* RNS inverse: device array of N^-1 mod p_i (elements)  */
+    void* stream;                    /* cudaStream_t                                          */
+} gpuntt_b200_merge_desc;
+
+/* Enqueue one batched Merge-NTT / INTT. Returns a gpuntt_b200_status. */
+int gpuntt_b200_merge_ntt(const gpuntt_b200_merge_desc* desc);
+
+/* Convenience forms of the above for the four hot entry points on unsigned 64/32-bit data with
+ * a single modulus (GPU_NTT / GPU_INTT, ntt.cuh:315-340; in == out gives the *_Inplace forms). */
+int gpuntt_b200_ntt_u64(const uint64_t* in, uint64_t* out, const uint64_t* root_table,
+                        uint64_t modulus, int n_power, int reduction_poly, int batch_size,
+                        void* stream);
+int gpuntt_b200_intt_u64(const uint64_t* in, uint64_t* out, const uint64_t* inv_root_table,
+                         uint64_t modulus, uint64_t n_inverse, int n_power, int reduction_poly,
+                         int batch_size, void* stream);
+int gpuntt_b200_ntt_u32(const uint32_t* in, uint32_t* out, const uint32_t* root_table,
+                        uint32_t modulus, int n_power, int reduction_poly, int batch_size,
+                        void* stream);
+int gpuntt_b200_intt_u32(const uint32_t* in, uint32_t* out, const uint32_t* inv_root_table,
+                         uint32_t modulus, uint32_t n_inverse, int n_power, int reduction_poly,
+                         int batch_size, void* stream);
+
+/* Host-buffer convenience (used by the end-to-end benchmark and the ctypes tests): copies
+ * `in` (host, pinned or pageable) to an internal device buffer, runs the transform and copies the
+ * result back to `out` (host); synchronises `stream` before returning. Single modulus, unsigned. */
+int gpuntt_b200_merge_ntt_host(const gpuntt_b200_merge_desc* desc_with_host_in_out,
+                               const void* host_root_table, size_t root_table_elems);
+
+/* Number of kernel launches the last gpuntt_b200_* call on this thread enqueued (the caller's
+ * evidence for "gpu_launches" in bench.py) and cumulative count since load. */
+int gpuntt_b200_last_launch_count(void);
+unsigned long long gpuntt_b200_total_launch_count(void);
+
+/* Per-launch device timing for the benchmark's live roofline: while enabled, every kernel launch
+ * is bracketed by CUDA events on its stream.  gpuntt_b200_profile_read waits for the recorded
+ * launches, writes up to max_records (duration in ms, kind: 0 = twiddle companion pre-kernel,
+ * k >= 1 = k-th merge pass of a call) and returns how many it wrote; the record list is cleared. */
+void gpuntt_b200_set_profiling(int on);
+int gpuntt_b200_profile_read(float* ms_out, int* kind_out, int max_records);
+
+/* Human-readable message for the last non-OK status returned on this thread. */
+const char* gpuntt_b200_last_error(void);
+
+/* Frees every cached scratch buffer (device-synchronising). */
+void gpuntt_b200_release_workspaces(void);
+
+/* Describes the launch plan chosen for (n_power, element_bits) as text into buf (for DESIGN.md /
+ * profiles); returns the number of kernel launches of the transform itself. */
+int gpuntt_b200_describe_plan(int n_power, int element_bits, char* buf, size_t buf_len);
+
+int gpuntt_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPUNTT_B200_H */

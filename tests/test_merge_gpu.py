@@ -1,0 +1,273 @@
+"""GPU parity tests of the Merge-NTT path: every call goes through the C ABI
+(include/gpuntt_b200.h via gpu_ntt_b200.capi) and is compared bit-exactly with the oracle on the
+same seeded inputs, mirroring the reference's gpu_merge_ntt_examples / gpu_merge_intt_examples
+(example/ntt_merge/test_merge_ntt.cu, test_merge_intt.cu)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from gpu_ntt_b200 import capi  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from tests.gpu_util import to_dev, to_host, to_host_signed  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def run_fwd(x, P, bits, poly, inplace=True):
+    n = P.logn
+    d = to_dev(x, bits)
+    tab = to_dev(P.fwd_br, bits)
+    out = d if inplace else torch.zeros_like(d)
+    capi.ntt(d.view(-1, P.n), tab, P.modulus, n, poly, out=out.view(-1, P.n))
+    torch.cuda.synchronize()
+    if not inplace:
+        assert (to_host(d, bits) == x).all(), "out-of-place call modified its input"
+    return to_host(out, bits)
+
+
+def run_inv(y, P, bits, poly, inplace=True):
+    d = to_dev(y, bits)
+    tab = to_dev(P.inv_br, bits)
+    out = d if inplace else torch.zeros_like(d)
+    capi.intt(d.view(-1, P.n), tab, P.modulus, P.n_inv, P.logn, poly, out=out.view(-1, P.n))
+    torch.cuda.synchronize()
+    return to_host(out, bits)
+
+
+@pytest.mark.parametrize("bits", [64, 32])
+@pytest.mark.parametrize("poly", [O.X_N_minus, O.X_N_plus])
+@pytest.mark.parametrize("logn,batch", [(1, 1), (1, 7), (2, 3), (3, 1000), (4, 1), (5, 33), (7, 5), (9, 9),
+                                        (10, 3), (11, 2), (12, 5), (13, 3), (14, 2), (15, 1), (16, 3), (17, 1)])
+def test_forward_and_inverse_match_oracle(bits, poly, logn, batch):
+    P = O.merge_params(logn, poly, bits)
+    x = O.example_input(P.modulus, batch << logn, seed=logn + batch)
+    want = O.merge_ntt(x, P)
+    got = run_fwd(x, P, bits, poly, inplace=True)
+    assert (got == want).all()
+    got2 = run_fwd(x, P, bits, poly, inplace=False)
+    assert (got2 == want).all()
+    back = run_inv(want, P, bits, poly, inplace=True)
+    assert (back == x).all()
+    back2 = run_inv(want, P, bits, poly, inplace=False)   # the reference's single-modulus out-of-place INTT is
+    assert (back2 == x).all()                            # broken for logn >= 11 (ntt.cu:2367-2390); ours is not
+    winv = O.merge_intt(x, P)
+    assert (run_inv(x, P, bits, poly) == winv).all()
+
+
+@pytest.mark.parametrize("bits,logn", [(64, 18), (64, 20), (32, 19), (64, 23), (32, 24)])
+def test_large_rings(bits, logn):
+    """2- and 3-pass plans (the reference switches kernels at logn 17 and 25, ntt.cuh:637-697)."""
+    P = O.merge_params(logn, O.X_N_minus, bits)
+    x = O.example_input(P.modulus, 1 << logn, seed=1)
+    want = O.merge_ntt(x, P)
+    assert (run_fwd(x, P, bits, O.X_N_minus) == want).all()
+    assert (run_inv(want, P, bits, O.X_N_minus) == x).all()
+
+
+def test_golden_vectors_through_c_abi(golden):
+    """Outputs on the example drivers' seed-0 input equal the hashes recorded from the reference."""
+    for g in golden["merge"]:
+        if g["logn"] > 16:
+            continue
+        bits, poly, logn = g["width"], g["poly"], g["logn"]
+        P = O.merge_params(logn, poly, bits)
+        x = O.example_input(P.modulus, g["batch"] << logn)
+        y = run_fwd(x, P, bits, poly)
+        assert str(O.fold_hash(y)) == g["ntt_hash"], g
+        z = run_inv(x, P, bits, poly)
+        assert str(O.fold_hash(z)) == g["intt_hash"], g
+
+
+@pytest.mark.parametrize("bits", [64, 32])
+@pytest.mark.parametrize("logn", [4, 12, 16])
+def test_signed_variants(bits, logn):
+    """Data32s/Data64s: signed input on forward (test_merge_ntt.cu:184-341), centred output on inverse."""
+    P = O.merge_params(logn, O.X_N_plus, bits)
+    p = P.modulus
+    rng = np.random.RandomState(logn)
+    mag = rng.randint(0, 2**31, size=3 << logn).astype(np.int64) * (1 if bits == 32 else 2**20) % (p // 2)
+    sx = np.where(rng.randint(0, 2, size=mag.size) == 1, -mag, mag).astype(np.int64)
+    want = O.merge_ntt(O.reduce_signed(sx, p), P)
+    d = torch.from_numpy(sx if bits == 64 else sx.astype(np.int32)).cuda()
+    out = torch.zeros_like(d)
+    tab = to_dev(P.fwd_br, bits)
+    capi.merge_ntt(in_ptr=d.data_ptr(), out_ptr=out.data_ptr(), table_ptr=tab.data_ptr(), n_power=logn, batch=3,
+                   element_bits=bits, direction=capi.FORWARD, reduction_poly=O.X_N_plus, modulus=p, is_signed=True,
+                   stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert (to_host(out, bits) == want).all()
+    # inverse with centred signed output
+    itab = to_dev(P.inv_br, bits)
+    back = torch.zeros_like(d)
+    capi.merge_ntt(in_ptr=out.data_ptr(), out_ptr=back.data_ptr(), table_ptr=itab.data_ptr(), n_power=logn, batch=3,
+                   element_bits=bits, direction=capi.INVERSE, reduction_poly=O.X_N_plus, modulus=p,
+                   mod_inverse=P.n_inv, is_signed=True, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert (to_host_signed(back) == O.centered(O.merge_intt(want, P), p)).all()
+    assert (to_host_signed(back) == sx).all()
+
+
+def _is_prime(n):
+    if n < 2:
+        return False
+    for q in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37):
+        if n % q == 0:
+            return n == q
+    d, s = n - 1, 0
+    while d % 2 == 0:
+        d //= 2
+        s += 1
+    for a in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37):
+        x = pow(a, d, n)
+        if x in (1, n - 1):
+            continue
+        for _ in range(s - 1):
+            x = x * x % n
+            if x == n - 1:
+                break
+        else:
+            return False
+    return True
+
+
+def rns_primes(bits, logn, count):
+    m = 1 << (logn + 1)
+    top = (1 << (61 if bits == 64 else 29)) // m
+    out = []
+    k = top
+    while len(out) < count:
+        p = k * m + 1
+        if _is_prime(p):
+            for g in range(2, 200):
+                psi = pow(g, (p - 1) // m, p)
+                if pow(psi, m // 2, p) == p - 1:
+                    out.append((p, psi))
+                    break
+        k -= 1
+    return out
+
+
+@pytest.mark.parametrize("bits", [64, 32])
+@pytest.mark.parametrize("logn,batch,mod_count", [(3, 10, 3), (10, 7, 2), (12, 6, 3), (14, 5, 2), (16, 4, 4)])
+def test_rns_form(bits, logn, batch, mod_count):
+    """RNS overloads: polynomial b uses modulus[b % mod_count], table slice (b % mod_count) << n_power,
+    mod_inverse[b % mod_count] (ntt.cu:613-619, 672-673, 1225-1226).  61-/29-bit primes exercise the top
+    of the supported modulus range."""
+    n = 1 << logn
+    primes = rns_primes(bits, logn, mod_count)
+    np_dt = np.uint64 if bits == 64 else np.uint32
+    fwd_tab = np.zeros(mod_count << logn, dtype=np.uint64)
+    inv_tab = np.zeros(mod_count << logn, dtype=np.uint64)
+    mods = np.zeros((mod_count, 3), dtype=np.uint64)
+    ninvs = np.zeros(mod_count, dtype=np.uint64)
+    params = []
+    for m, (p, psi) in enumerate(primes):
+        fwd = np.array([pow(psi, i, p) for i in range(n)], dtype=np.uint64)
+        ipsi = pow(psi, p - 2, p)
+        inv = np.array([pow(ipsi, i, p) for i in range(n)], dtype=np.uint64)
+        fwd_tab[m << logn:(m + 1) << logn] = O.bitrev_table(fwd)
+        inv_tab[m << logn:(m + 1) << logn] = O.bitrev_table(inv)
+        bit, mu = O.modulus(p, bits)
+        mods[m] = (p, bit, mu)
+        ninvs[m] = pow(n, p - 2, p)
+        P = O.MergeParams(logn, O.X_N_plus, bits, p, 0, psi, int(ninvs[m]), psi, ipsi, n, n)
+        P.fwd, P.inv = fwd, inv
+        params.append(P)
+    rng = np.random.RandomState(5)
+    x = np.zeros((batch, n), dtype=np.uint64)
+    for b in range(batch):
+        p = primes[b % mod_count][0]
+        x[b] = (rng.randint(0, 2**31, size=n).astype(np.uint64) * np.uint64(2**31) +
+                rng.randint(0, 2**31, size=n).astype(np.uint64)) % np.uint64(p)
+    want = np.stack([O.merge_ntt(x[b], params[b % mod_count]) for b in range(batch)])
+    d = to_dev(x, bits)
+    s = torch.cuda.current_stream().cuda_stream
+    mods_d = to_dev(mods.ravel(), bits)
+    ninv_d = to_dev(ninvs, bits)
+    capi.merge_ntt(in_ptr=d.data_ptr(), out_ptr=d.data_ptr(), table_ptr=to_dev(fwd_tab, bits).data_ptr(),
+                   n_power=logn, batch=batch, element_bits=bits, direction=capi.FORWARD,
+                   reduction_poly=O.X_N_plus, mod_count=mod_count, modulus_dev=mods_d.data_ptr(), stream=s)
+    torch.cuda.synchronize()
+    assert (to_host(d, bits) == want).all()
+    capi.merge_ntt(in_ptr=d.data_ptr(), out_ptr=d.data_ptr(), table_ptr=to_dev(inv_tab, bits).data_ptr(),
+                   n_power=logn, batch=batch, element_bits=bits, direction=capi.INVERSE,
+                   reduction_poly=O.X_N_plus, mod_count=mod_count, modulus_dev=mods_d.data_ptr(),
+                   mod_inverse_dev=ninv_d.data_ptr(), stream=s)
+    torch.cuda.synchronize()
+    assert (to_host(d, bits) == x).all()
+
+
+def test_config_c2_full_size():
+    """BASELINE config 2: forward Data64 N=2^16 batch=1024, single prime, in place.  Full-size checks:
+    a sample of polynomials against the oracle + linearity + fwd/inv round trip of every element."""
+    logn, batch, bits = 16, 1024, 64
+    P = O.merge_params(logn, O.X_N_minus, bits)
+    p = P.modulus
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randint(0, p, (batch, P.n), dtype=torch.int64, device="cuda", generator=g)
+    x0 = x.clone()
+    tab, itab = to_dev(P.fwd_br, bits), to_dev(P.inv_br, bits)
+    capi.ntt(x, tab, p, logn, O.X_N_minus)
+    torch.cuda.synchronize()
+    for b in (0, 1, 511, 777, 1023):
+        assert (to_host(x[b], bits) == O.merge_ntt(to_host(x0[b], bits), P)).all()
+    # linearity: NTT(a+b) == NTT(a)+NTT(b) (mod p) for the first 512 pairs
+    a, b2 = x0[:512], x0[512:]
+    s = a + b2
+    s = torch.where(s >= p, s - p, s)
+    capi.ntt(s, tab, p, logn, O.X_N_minus)
+    t = x[:512] + x[512:]
+    t = torch.where(t >= p, t - p, t)
+    assert torch.equal(s, t)
+    # every output canonical, and the inverse restores every input word
+    assert int(x.max()) < p and int(x.min()) >= 0
+    capi.intt(x, itab, p, P.n_inv, logn, O.X_N_minus)
+    assert torch.equal(x, x0)
+
+
+def test_config_c3_round_trip_u32():
+    """BASELINE config 3: Data32 N=2^14 batch=4096 forward+inverse round trip, bit exact."""
+    logn, batch, bits = 14, 4096, 32
+    P = O.merge_params(logn, O.X_N_minus, bits)
+    p = P.modulus
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randint(0, p, (batch, P.n), dtype=torch.int32, device="cuda", generator=g)
+    x0 = x.clone()
+    tab, itab = to_dev(P.fwd_br, bits), to_dev(P.inv_br, bits)
+    capi.ntt(x, tab, p, logn, O.X_N_minus)
+    torch.cuda.synchronize()
+    for b in (0, 2047, 4095):
+        assert (to_host(x[b], bits) == O.merge_ntt(to_host(x0[b], bits), P)).all()
+    assert int(x.max()) < p and int(x.min()) >= 0
+    capi.intt(x, itab, p, P.n_inv, logn, O.X_N_minus)
+    assert torch.equal(x, x0)
+
+
+def test_host_buffer_entry_point():
+    """gpuntt_b200_merge_ntt_host: host in/out, copies inside (the e2e path of bench.py)."""
+    import ctypes as C
+    logn, batch = 12, 8
+    P = O.merge_params(logn, O.X_N_minus, 64)
+    x = O.example_input(P.modulus, batch << logn, seed=9)
+    out = np.zeros_like(x)
+    d = capi.MergeDesc(64, 0, capi.FORWARD, logn, capi.PerPolynomial, O.X_N_minus, batch, 0,
+                       x.ctypes.data, out.ctypes.data, None, P.modulus, 0, None, None, None)
+    capi.check(capi.lib().gpuntt_b200_merge_ntt_host(C.byref(d), P.fwd_br.ctypes.data, P.fwd_br.size))
+    assert (out == O.merge_ntt(x, P)).all()
+    assert capi.lib().gpuntt_b200_last_launch_count() >= 2
+
+
+def test_streams_and_no_sync():
+    """Calls only enqueue on cfg.stream: two streams, two different transforms, results both right."""
+    P = O.merge_params(13, O.X_N_minus, 64)
+    xs = [O.example_input(P.modulus, 4 << 13, seed=s) for s in (1, 2)]
+    tab = to_dev(P.fwd_br, 64)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    ds = [to_dev(x, 64) for x in xs]
+    torch.cuda.synchronize()
+    for st, d in zip(streams, ds):
+        capi.ntt(d.view(-1, P.n), tab, P.modulus, 13, O.X_N_minus, stream=st)
+    torch.cuda.synchronize()
+    for x, d in zip(xs, ds):
+        assert (to_host(d, 64) == O.merge_ntt(x, P)).all()
