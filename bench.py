@@ -202,7 +202,7 @@ def run_b200_arm(args):
     lib.gpuntt_b200_set_profiling(0)
     # keep the same load running ~1 s more (untimed) so the 100 ms clock sampler sees it
     t_hold = time.perf_counter()
-    while sampler is not None and time.perf_counter() - t_hold < 1.2:
+    while sampler is not None and not args.quick and time.perf_counter() - t_hold < 1.2:
         for _ in range(20):
             step()
         torch.cuda.synchronize()
@@ -240,7 +240,7 @@ def run_b200_arm(args):
     def e2e_step():
         capi.check(lib.gpuntt_b200_merge_ntt_host(C.byref(desc), h_tab.ctypes.data, h_tab.size))
     e2e_step()
-    e2e_steps = max(1, min(args.steps, 10))
+    e2e_steps = 1 if args.quick else max(1, min(args.steps, 10))
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -272,7 +272,7 @@ def run_b200_arm(args):
                      "prep_kernel_avg_ms": (sum(prep_ms) / len(prep_ms)) if prep_ms else None,
                      "frac_of_8TBps_nominal": (achieved / 8000.0) if achieved else None},
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.quick:
         rate, threads, kind = cpu_reference_rate(args.cpu_sample)
         out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
                                "sample": f"{args.cpu_sample} polynomials of the same workload (N=2^16, Data64, seed 0), "
@@ -291,6 +291,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="kernel-timed region only (for runs under ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

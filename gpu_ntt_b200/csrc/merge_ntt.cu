@@ -76,15 +76,15 @@ namespace gpuntt_b200
     // (the bit-reversed caller table makes these 2^(R-1-ab) twiddles adjacent in memory).
     // LB0: the round's lowest active bit is local bit 0, i.e. the thread's 2^R elements are adjacent
     // in memory: they are moved with 16-byte shared-memory accesses (conflict-free under the swizzle).
-    template <typename T, int R, bool INV, bool LB0>
+    template <typename T, int R, bool INV, bool LB0, bool FAST>
     __device__ __forceinline__ void do_round(T* sm, int item, int lb, int c, int stage_hi, int jrow,
-                                             int plus, const Twiddle<T>* __restrict__ tw, T p)
+                                             int plus, const Twiddle<T>* __restrict__ tw,
+                                             const Mod<T, FAST>& M)
     {
         constexpr int E = 1 << R;
         using V = typename Vec16<T>::type;
         constexpr int VN = Vec16<T>::N;
         constexpr bool VEC = LB0 && (E >= VN);
-        const T two_p = p + p;
         if constexpr (LB0) lb = 0;
         const int l_base = ((item >> lb) << (lb + R)) | (item & ((1 << lb) - 1));
         T e[E];
@@ -122,7 +122,7 @@ namespace gpuntt_b200
                     for (int y = 0; y < (1 << ab); y++)
                     {
                         const int a0 = (x << (ab + 1)) | y;
-                        ct_butterfly<T>(e[a0], e[a0 | (1 << ab)], w, p, two_p);
+                        M.ct(e[a0], e[a0 | (1 << ab)], w);
                     }
                 }
             }
@@ -142,7 +142,7 @@ namespace gpuntt_b200
                     for (int y = 0; y < (1 << ab); y++)
                     {
                         const int a0 = (x << (ab + 1)) | y;
-                        gs_butterfly<T>(e[a0], e[a0 | (1 << ab)], w, p, two_p);
+                        M.gs(e[a0], e[a0 | (1 << ab)], w);
                     }
                 }
             }
@@ -165,7 +165,7 @@ namespace gpuntt_b200
     }
 
     // ------------------------------------------------------------------ the pass kernel
-    template <typename T, bool INV, bool RNS>
+    template <typename T, bool INV, bool RNS, bool FAST>
     __global__ void __launch_bounds__(kThreads) merge_pass_kernel(const PassArgs<T> a)
     {
         extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -283,25 +283,26 @@ namespace gpuntt_b200
                     p = a.mod_values[3 * mi];
                     tw += ((size_t) mi << a.tw_stride_log);
                 }
+                const Mod<T, FAST> M(p);
                 if (lb == 0)
                     switch (R)
                     {
-                        case 1: do_round<T, 1, INV, true>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, p); break;
-                        case 2: do_round<T, 2, INV, true>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, p); break;
-                        case 3: do_round<T, 3, INV, true>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, p); break;
-                        case 4: do_round<T, 4, INV, true>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, p); break;
+                        case 1: do_round<T, 1, INV, true, FAST>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, M); break;
+                        case 2: do_round<T, 2, INV, true, FAST>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, M); break;
+                        case 3: do_round<T, 3, INV, true, FAST>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, M); break;
+                        case 4: do_round<T, 4, INV, true, FAST>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, M); break;
                         default:
                             if constexpr (sizeof(T) == 4)
-                                do_round<T, 5, INV, true>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, p);
+                                do_round<T, 5, INV, true, FAST>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, M);
                             break;
                     }
                 else
                     switch (R)
                     {
-                        case 1: do_round<T, 1, INV, false>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, p); break;
-                        case 2: do_round<T, 2, INV, false>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, p); break;
-                        case 3: do_round<T, 3, INV, false>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, p); break;
-                        default: do_round<T, 4, INV, false>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, p); break;
+                        case 1: do_round<T, 1, INV, false, FAST>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, M); break;
+                        case 2: do_round<T, 2, INV, false, FAST>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, M); break;
+                        case 3: do_round<T, 3, INV, false, FAST>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, M); break;
+                        default: do_round<T, 4, INV, false, FAST>(sm, item, lb, c, stage_hi, jrow, a.plus, tw, M); break;
                     }
             }
         }
@@ -331,19 +332,18 @@ namespace gpuntt_b200
                         p = a.mod_values[3 * mi];
                         if constexpr (INV) ni = reinterpret_cast<const Twiddle<T>*>(a.ninv_tw)[mi];
                     }
-                    const T two_p = p + p;
+                    const Mod<T, FAST> M(p);
 #pragma unroll
                     for (int i = 0; i < VN; i++)
                     {
                         if constexpr (INV)
                         {
-                            T x = shoup_mul_lazy<T>(v[i], ni, p); // [0,2p)
-                            x = csub(x, p);
+                            T x = M.canon_inv(v[i], ni);
                             if (centre && x > (p >> 1)) x -= p; // modular_arith.cuh:389-405 of the reference
                             v[i] = x;
                         }
                         else
-                            v[i] = canon4(v[i], p, two_p);
+                            v[i] = M.canon_fwd(v[i]);
                     }
                 }
                 if (vec_ok && g + VN <= a.total_elems)
@@ -560,7 +560,7 @@ namespace gpuntt_b200
         return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     }
 
-    template <typename T, bool INV, bool RNS>
+    template <typename T, bool INV, bool RNS, bool FAST>
     static cudaError_t launch_pass(const PassArgs<T>& args, int batch, cudaStream_t st, int pass_no)
     {
         ProfScope prof(pass_no, st);
@@ -572,7 +572,7 @@ namespace gpuntt_b200
         else
             tiles = (total + (1LL << pl.tile_log) - 1) >> pl.tile_log;
         const size_t smem = sizeof(T) << pl.tile_log;
-        auto kern = merge_pass_kernel<T, INV, RNS>;
+        auto kern = merge_pass_kernel<T, INV, RNS, FAST>;
         cudaError_t e = allow_smem(kern, smem);
         if (e != cudaSuccess) return e;
         kern<<<(unsigned) tiles, kThreads, smem, st>>>(args);
@@ -646,12 +646,23 @@ namespace gpuntt_b200
             args.plan.last = (i == mp.npasses - 1);
             args.in = (i == 0) ? d->in : d->out; // later passes chain through `out` (also out of place)
             args.out = reinterpret_cast<T*>(d->out);
-            if (inv)
-                e = rns ? launch_pass<T, true, true>(args, d->batch_size, st, i + 1)
-                        : launch_pass<T, true, false>(args, d->batch_size, st, i + 1);
-            else
-                e = rns ? launch_pass<T, false, true>(args, d->batch_size, st, i + 1)
-                        : launch_pass<T, false, false>(args, d->batch_size, st, i + 1);
+            bool fast = false;
+            if constexpr (sizeof(T) == 8) fast = !rns && (uint64_t) d->modulus_value < kFastModulusLimit;
+            if constexpr (sizeof(T) == 8)
+            {
+                if (fast)
+                    e = inv ? launch_pass<T, true, false, true>(args, d->batch_size, st, i + 1)
+                            : launch_pass<T, false, false, true>(args, d->batch_size, st, i + 1);
+            }
+            if (!fast)
+            {
+                if (inv)
+                    e = rns ? launch_pass<T, true, true, false>(args, d->batch_size, st, i + 1)
+                            : launch_pass<T, true, false, false>(args, d->batch_size, st, i + 1);
+                else
+                    e = rns ? launch_pass<T, false, true, false>(args, d->batch_size, st, i + 1)
+                            : launch_pass<T, false, false, false>(args, d->batch_size, st, i + 1);
+            }
             if (e != cudaSuccess) return cuda_fail(e, "merge_pass_kernel launch");
         }
         return GPUNTT_B200_OK;

@@ -25,3 +25,18 @@ for k, h in hist.items():
     for op, c in h.items(): pp[pipe(op)] += c
     print(f"== {k}: {tot} instrs  " + "  ".join(f"{p}={c/div:.1f}" for p, c in pp.most_common()))
     print("   " + "  ".join(f"{op}:{c/div:.1f}" for op, c in h.most_common(40)))
+
+# estimated pipe cycles per SMSP warp-instruction on B200 (tools/microbench.cu): IMAD.WIDE/IMAD.HI 4, other fma-pipe 2, alu 2
+def cycles(h):
+    f = a = 0
+    for op, c in h.items():
+        pp = pipe(op)
+        if pp == "fma":
+            f += c * (4 if (".WIDE" in op or ".HI" in op) else 2)
+        elif pp == "alu":
+            a += c * 2
+    return f, a
+for k, h in hist.items():
+    if sub not in k: continue
+    f, a = cycles(h)
+    print(f"## {k[:60]}: fma-pipe cycles {f/div:.1f}  alu-pipe cycles {a/div:.1f}  issue {sum(h.values())/div:.1f}")
