@@ -76,6 +76,8 @@ def lib():
         L.gpuntt_b200_describe_plan.restype = i
         L.gpuntt_b200_describe_plan.argtypes = [i, i, C.c_char_p, C.c_size_t]
         L.gpuntt_b200_version.restype = i
+        L.gpuntt_b200_force_generic_path.restype = None
+        L.gpuntt_b200_force_generic_path.argtypes = [i]
         L.gpuntt_b200_set_profiling.restype = None
         L.gpuntt_b200_set_profiling.argtypes = [i]
         L.gpuntt_b200_profile_read.restype = i

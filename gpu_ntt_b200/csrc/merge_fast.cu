@@ -1,0 +1,625 @@
+// gpu_ntt_b200/csrc/merge_fast.cu -- the tuned Merge-NTT path (single modulus, unsigned data).
+//
+// One persistent, warp-specialised kernel per pass ("fast path"):
+//   * 8 consumer warps do nothing but shared-memory <-> register butterfly rounds;
+//   * 1 producer warp moves every coefficient tile with the TMA engine: ONE cp.async.bulk.tensor
+//     (UTMALDG) per 32 KiB tile global -> shared for the next tile while the current one is being
+//     transformed (two tile buffers, mbarrier full/done hand-shake) and one UTMASTG per finished
+//     tile shared -> global; the strided (column) tile of the first pass is a 2-D box
+//     [2^D rows x 128 bytes], the contiguous tile of the last pass a 3-D box
+//     [polynomials x rows x 128 bytes] (out-of-range polynomials are clipped by the hardware);
+//   * tiles land in shared memory in the hardware SWIZZLE_128B layout (16-byte chunk index XOR
+//     row mod 8), which makes every round shape bank-conflict free (16-byte accesses for the
+//     lowest round);
+//   * the twiddles of a pass are turned into (w, w') Shoup pairs ONCE per CTA, straight from the
+//     caller's table, into a slot-major shared-memory layout (lanes read adjacent 16-byte
+//     pairs) -- no scratch memory and no pre-kernel on this path;
+//   * the last pass pins each CTA to one contiguous range of the ring and streams polynomials
+//     through it, so the ~N distinct twiddles of the final stages are fetched once per CTA
+//     instead of once per polynomial.
+// Replaces ForwardCore/InverseCore of the reference (src/lib/ntt_merge/ntt.cu:435-1318) for
+// the plans listed in fast_supported().
+#include <cstdint>
+#include <cstdio>
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "gpuntt_b200.h"
+#include "merge_ntt.cuh"
+#include "modarith.cuh"
+
+namespace gpuntt_b200
+{
+
+    constexpr int kConsumers = 256;
+    constexpr int kFastThreads = kConsumers + 32;
+
+    // ------------------------------------------------------------------ PTX helpers
+    __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+    __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+    {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    }
+    __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+    {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    }
+    __device__ __forceinline__ void mbar_arrive(uint32_t bar)
+    {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+    }
+    __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+    {
+        asm volatile("{\n\t"
+                     ".reg .pred P;\n\t"
+                     "WAIT_%=:\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1;\n\t"
+                     "@P bra DONE_%=;\n\t"
+                     "bra WAIT_%=;\n\t"
+                     "DONE_%=:\n\t"
+                     "}" ::"r"(bar),
+                     "r"(parity)
+                     : "memory");
+    }
+    __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar)
+    {
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                     "l"(map), "r"(c0), "r"(c1), "r"(bar)
+                     : "memory");
+    }
+    __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar)
+    {
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+                     "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+                     : "memory");
+    }
+    __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src)
+    {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0),
+                     "r"(c1), "r"(src)
+                     : "memory");
+    }
+    __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, int c0, int c1, int c2, uint32_t src)
+    {
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(c0),
+                     "r"(c1), "r"(c2), "r"(src)
+                     : "memory");
+    }
+    __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map)
+    {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+    }
+    __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+    __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+    __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+    __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+    __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
+
+    // ------------------------------------------------------------------ compile-time pass shape
+    // STRIDED: tile = 2^D rows (row stride 2^lo elements) x 2^C adjacent columns, K = D + C.
+    // !STRIDED: tile = 2^NPLOG polynomials x 2^KC adjacent elements of the same ring range.
+    // Two register rounds: R1 stages on the high bits, R2 on the low bits (D = R1 + R2).
+    template <typename T_, bool INV_, bool FAST_, bool STRIDED_, int R1_, int R2_, int K_, int NPLOG_> struct Shape
+    {
+        using T = T_;
+        static constexpr bool INV = INV_, FAST = FAST_, STRIDED = STRIDED_;
+        static constexpr int R1 = R1_, R2 = R2_, K = K_, NPLOG = NPLOG_;
+        static constexpr int D = R1 + R2;
+        static constexpr int C = STRIDED ? (K - D) : 0;
+        static constexpr int KC = K - NPLOG;          // contiguous elements per polynomial in a tile
+        static constexpr int KTW = STRIDED ? K : KC;  // local index bits that select twiddles
+        static constexpr int CB = (sizeof(T) == 8) ? 4 : 5; // log2 elements per 128-byte row
+        static constexpr int ROWS = (1 << K) >> CB;
+        static constexpr int TILE_SMEM = ROWS * 128;
+        static constexpr int LB1 = C + R2, LB2 = C;   // lowest local bit of the high / low round
+        static constexpr int G1 = 1 << (KTW - LB1 - R1), G2 = 1 << (KTW - LB2 - R2); // twiddle groups
+        static constexpr int TW1 = ((1 << R1) - 1) * G1, TW2 = ((1 << R2) - 1) * G2;
+        static constexpr int TW_SMEM = (TW1 + TW2) * (int) sizeof(Twiddle<T>);
+        static constexpr int SMEM = 2 * TILE_SMEM + TW_SMEM + 64 + 1024; // + slack to align the tiles to 1 KiB
+        static_assert(LB2 == 0 || LB2 >= CB, "low round must start at bit 0 or on a row boundary");
+        static_assert(LB1 >= CB, "high round must start on a row boundary");
+    };
+
+    template <typename T> struct FastArgs
+    {
+        const T* in;
+        T* out;
+        const T* table; // the caller's bit-reversed root table (w only)
+        T p, ninv_w, ninv_wq;
+        int n, lo, plus, last, batch;
+        long long work; // total tiles of this pass
+    };
+
+    // byte offset of local element l inside a (1 KiB aligned) tile buffer: TMA SWIZZLE_128B
+    template <typename S> __device__ __forceinline__ int tile_off(int l)
+    {
+        const int b = l * (int) sizeof(typename S::T);
+        return b ^ (((b >> 7) & 7) << 4);
+    }
+
+    // ------------------------------------------------------------------ one register round
+    template <typename S, int R, int LB, int G, bool FINAL>
+    __device__ __forceinline__ void fast_round(unsigned char* buf, const Twiddle<typename S::T>* __restrict__ tws,
+                                               const Mod<typename S::T, S::FAST>& M, int ctid,
+                                               const Twiddle<typename S::T>& ninv)
+    {
+        using T = typename S::T;
+        constexpr int E = 1 << R;
+        constexpr int ITEMS = (1 << S::K) >> R;
+        constexpr int VN = 16 / (int) sizeof(T);
+        constexpr int ES = (int) sizeof(T);
+        // Swizzled address of element a of the item: with b = byte offset of (l_base | a << LB),
+        //   addr = b ^ (((b >> 7) & 7) << 4).
+        // LB*ES >= 1 KiB rows apart (LB >= CB + 3): the XOR term comes from l_base only.
+        // CB <= LB < CB + 3: bits 7..9 of b come from a (l_base has zeros there) -> XOR constant per a.
+        // LB == 0: the item is one or more whole 128-byte rows; chunks are 16-byte vectors.
+        static_assert(LB == 0 || LB >= S::CB, "round must start at bit 0 or on a row boundary");
+#pragma unroll 1
+        for (int item = ctid; item < ITEMS; item += kConsumers)
+        {
+            const int l_base = ((item >> LB) << (LB + R)) | (item & ((1 << LB) - 1));
+            const int group = (l_base >> (LB + R)) & (G - 1);
+            const int b0 = l_base * ES;
+            T e[E];
+            auto addr = [&](int a) -> unsigned char*
+            {
+                // a is a compile-time constant after unrolling
+                const int b = b0 + ((a << LB) * ES);         // no carries: the a-bits of l_base are zero
+                if constexpr (LB >= S::CB + 3)
+                    return buf + ((b0 ^ (((b0 >> 7) & 7) << 4)) + ((a << LB) * ES));
+                else
+                    return buf + (b ^ (((b >> 7) & 7) << 4));
+            };
+            if constexpr (LB == 0)
+            {
+#pragma unroll
+                for (int a = 0; a < E; a += VN)
+                {
+                    if constexpr (sizeof(T) == 8)
+                    {
+                        ulonglong2 v = *reinterpret_cast<const ulonglong2*>(addr(a));
+                        e[a] = v.x;
+                        e[a + 1] = v.y;
+                    }
+                    else
+                    {
+                        uint4 v = *reinterpret_cast<const uint4*>(addr(a));
+                        e[a] = v.x;
+                        e[a + 1] = v.y;
+                        e[a + 2] = v.z;
+                        e[a + 3] = v.w;
+                    }
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int a = 0; a < E; a++) e[a] = *reinterpret_cast<const T*>(addr(a));
+            }
+
+            const Twiddle<T>* tg = tws + group;
+            if constexpr (!S::INV)
+            {
+#pragma unroll
+                for (int it = 0; it < R; it++)
+                {
+                    const int ab = R - 1 - it;
+#pragma unroll
+                    for (int x = 0; x < (E >> (ab + 1)); x++)
+                    {
+                        const Twiddle<T> w = tg[((E >> (ab + 1)) - 1 + x) * G];
+#pragma unroll
+                        for (int y = 0; y < (1 << ab); y++)
+                        {
+                            const int a0 = (x << (ab + 1)) | y;
+                            M.ct(e[a0], e[a0 | (1 << ab)], w);
+                        }
+                    }
+                }
+                if constexpr (FINAL)
+                {
+#pragma unroll
+                    for (int a = 0; a < E; a++) e[a] = M.canon_fwd(e[a]);
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int ab = 0; ab < R; ab++)
+                {
+#pragma unroll
+                    for (int x = 0; x < (E >> (ab + 1)); x++)
+                    {
+                        const Twiddle<T> w = tg[((E >> (ab + 1)) - 1 + x) * G];
+#pragma unroll
+                        for (int y = 0; y < (1 << ab); y++)
+                        {
+                            const int a0 = (x << (ab + 1)) | y;
+                            M.gs(e[a0], e[a0 | (1 << ab)], w);
+                        }
+                    }
+                }
+                if constexpr (FINAL)
+                {
+#pragma unroll
+                    for (int a = 0; a < E; a++) e[a] = M.canon_inv(e[a], ninv);
+                }
+            }
+
+            if constexpr (LB == 0)
+            {
+#pragma unroll
+                for (int a = 0; a < E; a += VN)
+                {
+                    if constexpr (sizeof(T) == 8)
+                        *reinterpret_cast<ulonglong2*>(addr(a)) = make_ulonglong2(e[a], e[a + 1]);
+                    else
+                        *reinterpret_cast<uint4*>(addr(a)) = make_uint4(e[a], e[a + 1], e[a + 2], e[a + 3]);
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int a = 0; a < E; a++) *reinterpret_cast<T*>(addr(a)) = e[a];
+            }
+        }
+    }
+
+    // ------------------------------------------------------------------ the persistent pass kernel
+    // Work item w of a pass:
+    //   STRIDED:   w = poly * 2^(lo-C) + column chunk            (any CTA, any order)
+    //   !STRIDED:  w = range * tiles_per_range + polynomial group (range-major, so a CTA's
+    //              contiguous share of the work stays inside one or two ranges)
+    template <typename S>
+    __global__ void __launch_bounds__(kFastThreads, 2)
+        fast_pass_kernel(const FastArgs<typename S::T> a, const __grid_constant__ CUtensorMap map_in,
+                         const __grid_constant__ CUtensorMap map_out)
+    {
+        using T = typename S::T;
+        extern __shared__ __align__(128) unsigned char smem_raw[];
+        unsigned char* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+        unsigned char* bufs = smem;                                                    // 2 tile buffers
+        Twiddle<T>* tw1 = reinterpret_cast<Twiddle<T>*>(smem + 2 * S::TILE_SMEM);       // high round, slot-major
+        Twiddle<T>* tw2 = tw1 + S::TW1;                                                 // low round
+        uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * S::TILE_SMEM + S::TW_SMEM); // full[2], done[2]
+
+        const int tid = threadIdx.x;
+        const int n = a.n;
+        const long long w_begin = a.work * blockIdx.x / gridDim.x;
+        const long long w_end = a.work * (blockIdx.x + 1) / gridDim.x;
+        const int tiles_per_range = S::STRIDED ? 1 : ((a.batch + (1 << S::NPLOG) - 1) >> S::NPLOG);
+
+        if (tid == kConsumers)
+        {
+            tma_prefetch_desc(&map_in);
+            tma_prefetch_desc(&map_out);
+        }
+        if (tid == 0)
+        {
+            mbar_init(smem_u32(&bars[0]), 1);
+            mbar_init(smem_u32(&bars[1]), 1);
+            mbar_init(smem_u32(&bars[2]), kConsumers);
+            mbar_init(smem_u32(&bars[3]), kConsumers);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            fence_async();
+        }
+        const Mod<T, S::FAST> M(a.p);
+        const Twiddle<T> ninv{a.ninv_w, a.ninv_wq};
+        uint32_t uses0 = 0, uses1 = 0; // how often each buffer has been filled so far (phase tracking)
+
+        long long w = w_begin;
+        while (w < w_end)
+        {
+            // ---- segment: a run of tiles sharing one twiddle set
+            long long seg_end = w_end;
+            int range = 0;
+            if constexpr (!S::STRIDED)
+            {
+                range = (int) (w / tiles_per_range);
+                const long long re = (long long) (range + 1) * tiles_per_range;
+                if (re < seg_end) seg_end = re;
+            }
+            const int ntiles = (int) (seg_end - w);
+
+            __syncthreads(); // everybody is done with the previous segment's twiddles and buffers
+            {
+                // (w, w') pairs for both rounds, slot-major: entry (slot, group) at slot*G + group
+                const int j0 = S::STRIDED ? 0 : (range << S::KC); // index (>> lo) of the tile's first row
+                for (int i = tid; i < S::TW1 + S::TW2; i += kFastThreads)
+                {
+                    const bool hi = i < S::TW1;
+                    const int ii = hi ? i : i - S::TW1;
+                    const int R = hi ? S::R1 : S::R2, LB = hi ? S::LB1 : S::LB2, G = hi ? S::G1 : S::G2;
+                    const int slot = ii / G, group = ii % G;
+                    // slot -> (ab, x): slot = 2^(R-1-ab) - 1 + x
+                    const int lvl = 31 - __clz(slot + 1); // = R-1-ab
+                    const int ab = R - 1 - lvl, x = slot + 1 - (1 << lvl);
+                    const int rb0 = LB - S::C;
+                    const int s = n - 1 - a.lo - (rb0 + ab);
+                    const int J = j0 | (group << (LB + R - S::C));
+                    const long long idx = ((long long) a.plus << s) + (J >> (rb0 + ab + 1)) + x;
+                    const T wv = a.table[idx];
+                    (hi ? tw1 : tw2)[ii] = Twiddle<T>{wv, shoup_companion(wv, a.p)};
+                }
+            }
+            __syncthreads();
+
+            if (tid >= kConsumers)
+            {
+                // =================== producer warp ===================
+                const int lane = tid - kConsumers;
+                // TMA coordinates of work item ww (innermost first)
+                auto issue_load = [&](long long ww, int b)
+                {
+                    if (lane == 0)
+                    {
+                        const uint32_t bar = smem_u32(&bars[b]);
+                        const uint32_t dst = smem_u32(bufs + b * S::TILE_SMEM);
+                        mbar_expect_tx(bar, S::TILE_SMEM); // out-of-range rows are zero-filled and still counted
+                        if constexpr (S::STRIDED)
+                        {
+                            const int ccb = a.lo - S::C;
+                            const long long poly = ww >> ccb, cc = ww & ((1LL << ccb) - 1);
+                            tma_load_2d(dst, &map_in, (int) (cc << S::C), (int) (poly << S::D), bar);
+                        }
+                        else
+                        {
+                            const long long grp = ww % tiles_per_range;
+                            tma_load_3d(dst, &map_in, 0, range << (S::KC - S::CB), (int) (grp << S::NPLOG), bar);
+                        }
+                    }
+                };
+                for (int i = 0; i < 2 && i < ntiles; i++) issue_load(w + i, (int) ((uses0 + uses1 + i) & 1));
+                // tile t of the CTA's whole stream uses buffer (t & 1); uses0 + uses1 = tiles so far
+                for (int i = 0; i < ntiles; i++)
+                {
+                    const uint32_t t = uses0 + uses1;
+                    const int b = t & 1;
+                    const uint32_t k = b ? uses1 : uses0;
+                    mbar_wait(smem_u32(&bars[2 + b]), k & 1); // consumers finished this tile
+                    if (lane == 0)
+                    {
+                        const uint32_t src = smem_u32(bufs + b * S::TILE_SMEM);
+                        const long long ww = w + i;
+                        if constexpr (S::STRIDED)
+                        {
+                            const int ccb = a.lo - S::C;
+                            const long long poly = ww >> ccb, cc = ww & ((1LL << ccb) - 1);
+                            tma_store_2d(&map_out, (int) (cc << S::C), (int) (poly << S::D), src);
+                        }
+                        else
+                        {
+                            const long long grp = ww % tiles_per_range;
+                            tma_store_3d(&map_out, 0, range << (S::KC - S::CB), (int) (grp << S::NPLOG), src);
+                        }
+                        bulk_commit();
+                        bulk_wait_read0(); // this buffer may be overwritten again
+                    }
+                    __syncwarp();
+                    if (b) uses1++; else uses0++;
+                    if (i + 2 < ntiles) issue_load(w + i + 2, b);
+                }
+                if (lane == 0) bulk_wait0();
+            }
+            else
+            {
+                // =================== consumer warps ===================
+                for (int i = 0; i < ntiles; i++)
+                {
+                    const uint32_t t = uses0 + uses1;
+                    const int b = t & 1;
+                    const uint32_t k = b ? uses1 : uses0;
+                    unsigned char* buf = bufs + b * S::TILE_SMEM;
+                    mbar_wait(smem_u32(&bars[b]), k & 1); // tile landed
+                    if constexpr (!S::INV)
+                    {
+                        fast_round<S, S::R1, S::LB1, S::G1, false>(buf, tw1, M, tid, ninv);
+                        consumer_sync();
+                        if (a.last)
+                            fast_round<S, S::R2, S::LB2, S::G2, true>(buf, tw2, M, tid, ninv);
+                        else
+                            fast_round<S, S::R2, S::LB2, S::G2, false>(buf, tw2, M, tid, ninv);
+                    }
+                    else
+                    {
+                        fast_round<S, S::R2, S::LB2, S::G2, false>(buf, tw2, M, tid, ninv);
+                        consumer_sync();
+                        if (a.last)
+                            fast_round<S, S::R1, S::LB1, S::G1, true>(buf, tw1, M, tid, ninv);
+                        else
+                            fast_round<S, S::R1, S::LB1, S::G1, false>(buf, tw1, M, tid, ninv);
+                    }
+                    fence_async(); // make the generic-proxy writes visible to the bulk store
+                    mbar_arrive(smem_u32(&bars[2 + b]));
+                    if (b) uses1++; else uses0++;
+                }
+            }
+            // the producer's counters advance identically
+            if (tid >= kConsumers)
+            {
+                // (already advanced inside the loop)
+            }
+            w = seg_end;
+        }
+    }
+
+    // ------------------------------------------------------------------ host side
+    static PFN_cuTensorMapEncodeTiled get_encode()
+    {
+        static PFN_cuTensorMapEncodeTiled fn = nullptr;
+        static bool tried = false;
+        if (!tried)
+        {
+            tried = true;
+            void* p = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+                q == cudaDriverEntryPointSuccess)
+                fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+        }
+        return fn;
+    }
+
+    // Tensor map of the [batch][N] array for one pass shape.
+    //   STRIDED: 2-D view {2^lo (adjacent elements of a matrix row), batch * 2^D rows}; box {2^C, 2^D}
+    //   else:    3-D view {2^CB (one 128-byte row), N / 2^CB rows, batch}; box {2^CB, 2^(KC-CB), 2^NPLOG}
+    template <typename S> static bool make_map(CUtensorMap* map, const void* base, int n, int lo, int batch)
+    {
+        using T = typename S::T;
+        PFN_cuTensorMapEncodeTiled enc = get_encode();
+        if (!enc) return false;
+        const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32;
+        cuuint64_t gdim[3], gstride[2];
+        cuuint32_t box[3], estr[3] = {1, 1, 1};
+        int rank;
+        if constexpr (S::STRIDED)
+        {
+            rank = 2;
+            gdim[0] = 1ull << lo;
+            gdim[1] = (cuuint64_t) batch << (n - lo);
+            gstride[0] = (cuuint64_t) sizeof(T) << lo;
+            box[0] = 1u << S::C;
+            box[1] = 1u << S::D;
+        }
+        else
+        {
+            rank = 3;
+            gdim[0] = 1ull << S::CB;
+            gdim[1] = 1ull << (n - S::CB);
+            gdim[2] = (cuuint64_t) batch;
+            gstride[0] = 128;
+            gstride[1] = (cuuint64_t) sizeof(T) << n;
+            box[0] = 1u << S::CB;
+            box[1] = 1u << (S::KC - S::CB);
+            box[2] = 1u << S::NPLOG;
+        }
+        CUresult r = enc(map, dt, (cuuint32_t) rank, const_cast<void*>(base), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        return r == CUDA_SUCCESS;
+    }
+
+    // returns cudaErrorNotSupported when the tensor maps cannot be built (caller falls back)
+    template <typename S> static cudaError_t launch_fast(const FastArgs<typename S::T>& args, cudaStream_t st)
+    {
+        static int blocks_per_sm = -1, sms = 0; // per process; devices on one box are identical
+        auto kern = fast_pass_kernel<S>;
+        if (blocks_per_sm < 0)
+        {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM);
+            if (e != cudaSuccess) return e;
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            int bps = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kFastThreads, S::SMEM);
+            if (e != cudaSuccess) return e;
+            blocks_per_sm = bps > 0 ? bps : 1;
+        }
+        alignas(64) CUtensorMap map_in, map_out;
+        if (!make_map<S>(&map_in, args.in, args.n, args.lo, args.batch)) return cudaErrorNotSupported;
+        if (args.in == args.out)
+            map_out = map_in;
+        else if (!make_map<S>(&map_out, args.out, args.n, args.lo, args.batch))
+            return cudaErrorNotSupported;
+        long long grid = (long long) sms * blocks_per_sm;
+        if (grid > args.work) grid = args.work;
+        kern<<<(unsigned) grid, kFastThreads, S::SMEM, st>>>(args, map_in, map_out);
+        return cudaGetLastError();
+    }
+
+    // which (n_power, element width) the fast path covers: two passes of two rounds each
+    bool fast_supported(int n_power, int element_bits)
+    {
+        if (element_bits == 64) return n_power == 16;
+        return false;
+    }
+
+    // Returns cudaSuccess and sets *launched to the number of kernels, or *launched = 0 if this
+    // transform is not covered (the caller then uses the generic path).
+    template <typename T>
+    cudaError_t fast_merge(const T* in, T* out, const T* table, T p, T ninv, int n_power, int plus, bool inverse,
+                           int batch, cudaStream_t st, int* launched, void (*prof_begin)(int, cudaStream_t),
+                           void (*prof_end)(cudaStream_t))
+    {
+        *launched = 0;
+        if (!fast_supported(n_power, (int) sizeof(T) * 8)) return cudaSuccess;
+        if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return cudaSuccess;
+        if constexpr (sizeof(T) == 8)
+        {
+            const bool fast_arith = (uint64_t) p < kFastModulusLimit;
+            FastArgs<T> a{};
+            a.table = table;
+            a.p = p;
+            a.ninv_w = ninv;
+            a.ninv_wq = inverse ? shoup_companion(ninv, p) : 0;
+            a.n = n_power;
+            a.plus = plus;
+            a.batch = batch;
+            cudaError_t e = cudaSuccess;
+            // n = 16: strided pass (8 stages, 256 rows x 16 columns) + contiguous pass (8 stages,
+            // 2 polynomials x 2048 adjacent elements)
+            using Sf = Shape<T, false, true, true, 4, 4, 12, 0>;
+            using Cf = Shape<T, false, true, false, 4, 4, 12, 1>;
+            using Si = Shape<T, true, true, true, 4, 4, 12, 0>;
+            using Ci = Shape<T, true, true, false, 4, 4, 12, 1>;
+            using Sfx = Shape<T, false, false, true, 4, 4, 12, 0>;
+            using Cfx = Shape<T, false, false, false, 4, 4, 12, 1>;
+            using Six = Shape<T, true, false, true, 4, 4, 12, 0>;
+            using Cix = Shape<T, true, false, false, 4, 4, 12, 1>;
+            const int d2 = 8;
+            auto strided_args = [&](bool first, bool last)
+            {
+                FastArgs<T> s = a;
+                s.in = first ? in : out;
+                s.out = out;
+                s.lo = d2;
+                s.last = last;
+                s.work = (long long) batch << (d2 - Sf::C);
+                return s;
+            };
+            auto contig_args = [&](bool first, bool last)
+            {
+                FastArgs<T> s = a;
+                s.in = first ? in : out;
+                s.out = out;
+                s.lo = 0;
+                s.last = last;
+                const long long tpr = (batch + (1 << Cf::NPLOG) - 1) >> Cf::NPLOG;
+                s.work = tpr << (n_power - Cf::KC);
+                return s;
+            };
+            if (!inverse)
+            {
+                prof_begin(1, st);
+                e = fast_arith ? launch_fast<Sf>(strided_args(true, false), st) : launch_fast<Sfx>(strided_args(true, false), st);
+                prof_end(st);
+                if (e == cudaErrorNotSupported) return cudaSuccess; // no tensor maps: generic path
+                if (e != cudaSuccess) return e;
+                prof_begin(2, st);
+                e = fast_arith ? launch_fast<Cf>(contig_args(false, true), st) : launch_fast<Cfx>(contig_args(false, true), st);
+                prof_end(st);
+            }
+            else
+            {
+                prof_begin(1, st);
+                e = fast_arith ? launch_fast<Ci>(contig_args(true, false), st) : launch_fast<Cix>(contig_args(true, false), st);
+                prof_end(st);
+                if (e == cudaErrorNotSupported) return cudaSuccess;
+                if (e != cudaSuccess) return e;
+                prof_begin(2, st);
+                e = fast_arith ? launch_fast<Si>(strided_args(false, true), st) : launch_fast<Six>(strided_args(false, true), st);
+                prof_end(st);
+            }
+            if (e != cudaSuccess) return e;
+            *launched = 2;
+        }
+        return cudaSuccess;
+    }
+
+    template cudaError_t fast_merge<uint64_t>(const uint64_t*, uint64_t*, const uint64_t*, uint64_t, uint64_t, int, int, bool,
+                                              int, cudaStream_t, int*, void (*)(int, cudaStream_t), void (*)(cudaStream_t));
+    template cudaError_t fast_merge<uint32_t>(const uint32_t*, uint32_t*, const uint32_t*, uint32_t, uint32_t, int, int, bool,
+                                              int, cudaStream_t, int*, void (*)(int, cudaStream_t), void (*)(cudaStream_t));
+
+} // namespace gpuntt_b200

@@ -482,6 +482,7 @@ namespace gpuntt_b200
         int kind; // 0 = twiddle_prep_kernel, 1.. = merge pass number (1-based, execution order)
     };
     static std::atomic<int> g_profiling{0};
+    static std::atomic<int> g_force_generic{0};
     static std::mutex g_prof_mutex;
     static std::vector<ProfRec> g_prof;
 
@@ -506,6 +507,25 @@ namespace gpuntt_b200
             g_prof.push_back(r);
         }
     };
+
+    static thread_local ProfScope* g_cur_prof = nullptr;
+    static void prof_begin(int kind, cudaStream_t st)
+    {
+        g_cur_prof = new ProfScope(kind, st);
+        g_last_launches++;
+        g_total_launches++;
+    }
+    static void prof_end(cudaStream_t)
+    {
+        delete g_cur_prof;
+        g_cur_prof = nullptr;
+    }
+
+    // merge_fast.cu
+    template <typename T>
+    cudaError_t fast_merge(const T* in, T* out, const T* table, T p, T ninv, int n_power, int plus, bool inverse,
+                           int batch, cudaStream_t st, int* launched, void (*prof_begin)(int, cudaStream_t),
+                           void (*prof_end)(cudaStream_t));
 
     static int fail(int code, const std::string& msg)
     {
@@ -588,6 +608,16 @@ namespace gpuntt_b200
         const bool rns = d->mod_count > 0;
         const bool plus = d->reduction_poly == GPUNTT_B200_X_N_PLUS;
         cudaStream_t st = (cudaStream_t) d->stream;
+        if (!rns && !d->is_signed && !g_force_generic.load())
+        {
+            int launched = 0;
+            cudaError_t fe = fast_merge<T>(reinterpret_cast<const T*>(d->in), reinterpret_cast<T*>(d->out),
+                                           reinterpret_cast<const T*>(d->root_of_unity_table), (T) d->modulus_value,
+                                           (T) d->mod_inverse_value, n, plus ? 1 : 0, inv, d->batch_size, st, &launched,
+                                           prof_begin, prof_end);
+            if (fe != cudaSuccess) return cuda_fail(fe, "fast_pass_kernel launch");
+            if (launched > 0) return GPUNTT_B200_OK;
+        }
         const int slices = rns ? d->mod_count : 1;
         const long long table_len = plus ? (1LL << n) : (1LL << (n - 1));
         const int stride_log = n; // the reference's RNS tables are spaced (1 << n_power) apart for both ring types
@@ -834,6 +864,7 @@ extern "C"
     }
 
     void gpuntt_b200_set_profiling(int on) { g_profiling.store(on ? 1 : 0); }
+    void gpuntt_b200_force_generic_path(int on) { g_force_generic.store(on ? 1 : 0); }
 
     int gpuntt_b200_profile_read(float* ms_out, int* kind_out, int max_records)
     {

@@ -127,6 +127,10 @@ unsigned long long gpuntt_b200_total_launch_count(void);
 void gpuntt_b200_set_profiling(int on);
 int gpuntt_b200_profile_read(float* ms_out, int* kind_out, int max_records);
 
+/* Testing aid: when on, the tuned persistent kernels (merge_fast.cu) are bypassed and every call
+ * takes the generic pass kernel, so both implementations can be checked against the oracle. */
+void gpuntt_b200_force_generic_path(int on);
+
 /* Human-readable message for the last non-OK status returned on this thread. */
 const char* gpuntt_b200_last_error(void);
 

@@ -271,3 +271,45 @@ def test_streams_and_no_sync():
     torch.cuda.synchronize()
     for x, d in zip(xs, ds):
         assert (to_host(d, 64) == O.merge_ntt(x, P)).all()
+
+
+@pytest.mark.parametrize("poly", [O.X_N_minus, O.X_N_plus])
+@pytest.mark.parametrize("batch", [1, 2, 5, 64, 301])
+def test_fast_path_and_generic_path_agree_with_oracle(poly, batch):
+    """logn=16 Data64 takes the persistent TMA kernels (merge_fast.cu); the same call with the fast path
+    disabled takes the generic pass kernel.  Both must equal the oracle bit for bit (odd batches leave a
+    half-empty last tile; 301 polynomials make every CTA cross a range boundary)."""
+    logn, bits = 16, 64
+    P = O.merge_params(logn, poly, bits)
+    x = O.example_input(P.modulus, batch << logn, seed=batch)
+    idx = sorted(set([0, batch - 1, batch // 2]))
+    want = {b: O.merge_ntt(x.reshape(batch, -1)[b], P) for b in idx}
+    for force in (0, 1):
+        capi.lib().gpuntt_b200_force_generic_path(force)
+        try:
+            y = run_fwd(x, P, bits, poly, inplace=(force == 0)).reshape(batch, -1)
+            for b in idx:
+                assert (y[b] == want[b]).all(), (force, b)
+            back = run_inv(y.ravel(), P, bits, poly, inplace=(force == 1))
+            assert (back == x).all(), force
+        finally:
+            capi.lib().gpuntt_b200_force_generic_path(0)
+
+
+def test_fast_path_large_modulus_uses_exact_arithmetic():
+    """A 61-bit prime is above the fast-arithmetic limit: the persistent kernels run with exact quotients."""
+    logn = 16
+    (p, psi), = rns_primes(64, logn, 1)
+    assert p.bit_length() == 61
+    n = 1 << logn
+    omega = psi * psi % p
+    fwd = np.array([pow(omega, i, p) for i in range(n // 2)], dtype=np.uint64)
+    inv = np.array([pow(pow(omega, p - 2, p), i, p) for i in range(n // 2)], dtype=np.uint64)
+    P = O.MergeParams(logn, O.X_N_minus, 64, p, omega, psi, pow(n, p - 2, p), omega, pow(omega, p - 2, p), n // 2, n)
+    P.fwd, P.inv, P.fwd_br, P.inv_br = fwd, inv, O.bitrev_table(fwd), O.bitrev_table(inv)
+    rng = np.random.RandomState(3)
+    x = (rng.randint(0, 2**31, size=2 * n).astype(np.uint64) * np.uint64(2**31) +
+         rng.randint(0, 2**31, size=2 * n).astype(np.uint64)) % np.uint64(p)
+    y = run_fwd(x, P, 64, O.X_N_minus)
+    assert (y == O.merge_ntt(x, P)).all()
+    assert (run_inv(y, P, 64, O.X_N_minus) == x).all()
