@@ -126,7 +126,7 @@ namespace gpuntt_b200
         T* out;
         const T* table; // the caller's bit-reversed root table (w only)
         T p, ninv_w, ninv_wq;
-        int n, lo, plus, last, batch;
+        int n, lo, plus, first, last, batch;
         long long work; // total tiles of this pass
     };
 
@@ -138,7 +138,9 @@ namespace gpuntt_b200
     }
 
     // ------------------------------------------------------------------ one register round
-    template <typename S, int R, int LB, int G, bool FINAL>
+    // TRIV: the twiddle in slot 0 of every stage is 1 (first round of an X^N-1 transform: table[0] = omega^0),
+    // so those butterflies skip the multiply (15 of the 32 butterflies of a radix-16 round).
+    template <typename S, int R, int LB, int G, bool FINAL, bool TRIV = false>
     __device__ __forceinline__ void fast_round(unsigned char* buf, const Twiddle<typename S::T>* __restrict__ tws,
                                                const Mod<typename S::T, S::FAST>& M, int ctid,
                                                const Twiddle<typename S::T>& ninv)
@@ -207,6 +209,15 @@ namespace gpuntt_b200
 #pragma unroll
                     for (int x = 0; x < (E >> (ab + 1)); x++)
                     {
+                        if constexpr (TRIV && S::FAST)
+                        {
+                            if (x == 0)
+                            {
+#pragma unroll
+                                for (int y = 0; y < (1 << ab); y++) M.ct_one(e[y], e[y | (1 << ab)]);
+                                continue;
+                            }
+                        }
                         const Twiddle<T> w = tg[((E >> (ab + 1)) - 1 + x) * G];
 #pragma unroll
                         for (int y = 0; y < (1 << ab); y++)
@@ -305,6 +316,9 @@ namespace gpuntt_b200
         }
         const Mod<T, S::FAST> M(a.p);
         const Twiddle<T> ninv{a.ninv_w, a.ninv_wq};
+        // first pass of a cyclic transform: slot 0 of every stage of the high round is table[0]; when that is 1
+        // (it is omega^0 in the reference's tables) those butterflies need no multiply
+        const bool triv = S::STRIDED && !S::INV && !a.plus && a.first && (a.lo + S::D == a.n) && a.table[0] == T(1);
         uint32_t uses0 = 0, uses1 = 0; // how often each buffer has been filled so far (phase tracking)
 
         long long w = w_begin;
@@ -413,7 +427,15 @@ namespace gpuntt_b200
                     mbar_wait(smem_u32(&bars[b]), k & 1); // tile landed
                     if constexpr (!S::INV)
                     {
-                        fast_round<S, S::R1, S::LB1, S::G1, false>(buf, tw1, M, tid, ninv);
+                        if constexpr (S::STRIDED && S::FAST && S::G1 == 1)
+                        {
+                            if (triv)
+                                fast_round<S, S::R1, S::LB1, S::G1, false, true>(buf, tw1, M, tid, ninv);
+                            else
+                                fast_round<S, S::R1, S::LB1, S::G1, false>(buf, tw1, M, tid, ninv);
+                        }
+                        else
+                            fast_round<S, S::R1, S::LB1, S::G1, false>(buf, tw1, M, tid, ninv);
                         consumer_sync();
                         if (a.last)
                             fast_round<S, S::R2, S::LB2, S::G2, true>(buf, tw2, M, tid, ninv);
@@ -574,6 +596,7 @@ namespace gpuntt_b200
                 s.in = first ? in : out;
                 s.out = out;
                 s.lo = d2;
+                s.first = first;
                 s.last = last;
                 s.work = (long long) batch << (d2 - Sf::C);
                 return s;
@@ -584,6 +607,7 @@ namespace gpuntt_b200
                 s.in = first ? in : out;
                 s.out = out;
                 s.lo = 0;
+                s.first = first;
                 s.last = last;
                 const long long tpr = (batch + (1 << Cf::NPLOG) - 1) >> Cf::NPLOG;
                 s.work = tpr << (n_power - Cf::KC);

@@ -87,13 +87,18 @@ namespace gpuntt_b200
         __device__ __forceinline__ T canon_inv(T x, const Twiddle<T>& ninv) const { return csub(mul(x, ninv), p); }
     };
 
-    // ------------------------------------------------------------------ fast policy (u64, p < 2^60.9)
+    // ------------------------------------------------------------------ fast policy (u64, p < 2^60.5)
+    // Everything below is shaped by what tools/arith_bench.cu measured on B200: all integer multiplies
+    // issue on the "fmaheavy" pipe (IMAD 64 lanes/clk/SM, IMAD.WIDE / IMAD.HI 32), additions on the alu
+    // pipe at 128 lanes/clk/SM, and ptxas likes to move carry additions onto the multiplier pipe
+    // (IMAD.X) -- so the multiply is one PTX block whose partial sums ride in IMAD / IMAD.WIDE addends,
+    // and the range correction is a predicated subtract keyed on the high word only.
     template <> struct Mod<uint64_t, true>
     {
         using T = uint64_t;
-        T p, four_p;
+        T p, four_p, six_p;
         uint32_t n0, n1, f0, f1; // -p mod 2^64 ; 4p
-        __device__ __forceinline__ explicit Mod(T p_) : p(p_), four_p(4 * p_)
+        __device__ __forceinline__ explicit Mod(T p_) : p(p_), four_p(4 * p_), six_p(6 * p_)
         {
             const T np = 0 - p_;
             n0 = (uint32_t) np;
@@ -102,7 +107,8 @@ namespace gpuntt_b200
             f1 = (uint32_t) (four_p >> 32);
         }
 
-        // r = w*y - q~*p in [0,4p): 3 IMAD.WIDE + 2 IMAD.HI + 4 IMAD, no subtract
+        // r = w*y - q~*p in [0,4p) for ANY 64-bit y;  q~ = a1*y1 + hi32(a1*y0) + hi32(a0*y1) in {Q-2..Q}.
+        // 3 IMAD.WIDE + 2 IMAD.HI + 4 IMAD; the only additions are the carry of the two cross terms.
         __device__ __forceinline__ T mul(T y, const Twiddle<T>& tw) const
         {
             const uint32_t y0 = (uint32_t) y, y1 = (uint32_t) (y >> 32);
@@ -110,46 +116,65 @@ namespace gpuntt_b200
             const uint32_t a0 = (uint32_t) tw.wq, a1 = (uint32_t) (tw.wq >> 32);
             uint32_t r0, r1;
             asm("{\n\t"
-                ".reg .u32 h1, h2, q0, q1, t0, t1;\n\t"
-                ".reg .u64 q, r;\n\t"
-                "mul.hi.u32 h1, %6, %3;\n\t"  // hi(a1*y0)
-                "mul.hi.u32 h2, %7, %2;\n\t"  // hi(a0*y1)
-                "mul.wide.u32 q, %6, %2;\n\t" // a1*y1
+                ".reg .u32 q0, q1, u, h1, h2, z;\n\t"
+                ".reg .u64 q, A, B, H;\n\t"
+                "mul.hi.u32 h1, %6, %2;\n\t"      // hi(a1*y0)
+                "mul.hi.u32 h2, %7, %3;\n\t"      // hi(a0*y1)
+                "mov.u32 z, 0;\n\t"
+                "add.cc.u32 h1, h1, h2;\n\t"
+                "addc.u32 h2, z, z;\n\t"
+                "mov.b64 H, {h1, h2};\n\t"
+                "mad.wide.u32 q, %6, %3, H;\n\t"  // a1*y1 + cross terms
                 "mov.b64 {q0, q1}, q;\n\t"
-                "add.cc.u32 q0, q0, h1;\n\t"
-                "addc.u32 q1, q1, 0;\n\t"
-                "add.cc.u32 q0, q0, h2;\n\t"
-                "addc.u32 q1, q1, 0;\n\t"
-                "mul.wide.u32 r, %4, %3;\n\t" // w0*y0
-                "mov.b64 {t0, t1}, r;\n\t"
-                "mad.lo.u32 t1, %5, %3, t1;\n\t" // w1*y0
-                "mad.lo.u32 t1, %4, %2, t1;\n\t" // w0*y1
-                "mov.b64 r, {t0, t1};\n\t"
-                "mad.wide.u32 r, q0, %8, r;\n\t" // q0*n0
-                "mov.b64 {t0, t1}, r;\n\t"
-                "mad.lo.u32 t1, q1, %8, t1;\n\t" // q1*n0
-                "mad.lo.u32 %1, q0, %9, t1;\n\t" // q0*n1
-                "mov.u32 %0, t0;\n\t"
+                "mul.wide.u32 A, %4, %2;\n\t"     // w0*y0
+                "mul.lo.u32 u, %5, %2;\n\t"       // w1*y0
+                "mad.lo.u32 u, %4, %3, u;\n\t"    // w0*y1
+                "mad.lo.u32 u, q1, %8, u;\n\t"    // q1*n0
+                "mad.lo.u32 u, q0, %9, u;\n\t"    // q0*n1
+                "mad.wide.u32 B, q0, %8, A;\n\t"  // q0*n0 + w0*y0
+                "mov.b64 {%0, %1}, B;\n\t"
+                "add.u32 %1, %1, u;\n\t"
                 "}"
                 : "=r"(r0), "=r"(r1)
-                : "r"(y1), "r"(y0), "r"(w0), "r"(w1), "r"(a1), "r"(a0), "r"(n0), "r"(n1));
+                : "r"(y0), "r"(y1), "r"(w0), "r"(w1), "r"(a1), "r"(a0), "r"(n0), "r"(n1));
             return ((T) r1 << 32) | r0;
         }
-        // In/out: [0, 8p + 2^32).  The range test looks at the high word only: x1 > hi32(4p)
-        // implies x >= 4p; otherwise x < 4p + 2^32.
+        // x >= 4p + 2^32 is impossible afterwards: hi32(x) > hi32(4p) implies x >= 4p.
+        __device__ __forceinline__ T csub_hi(T x) const
+        {
+            uint32_t x0 = (uint32_t) x, x1 = (uint32_t) (x >> 32);
+            asm("{\n\t"
+                ".reg .pred P;\n\t"
+                "setp.gt.u32 P, %1, %3;\n\t"
+                "@P sub.cc.u32 %0, %0, %2;\n\t"
+                "@P subc.u32 %1, %1, %3;\n\t"
+                "}"
+                : "+r"(x0), "+r"(x1)
+                : "r"(f0), "r"(f1));
+            return ((T) x1 << 32) | x0;
+        }
+        // Forward values live in [0, 8p + 2^32).
         __device__ __forceinline__ void ct(T& X, T& Y, const Twiddle<T>& tw) const
         {
-            const T x = ((uint32_t) (X >> 32) > f1) ? X - four_p : X;
+            const T x = csub_hi(X);
             const T t = mul(Y, tw);
             X = x + t;
             Y = x - t + four_p;
         }
-        // In/out: [0,4p)  (exact range test: a high-word-only test would double the slack per stage)
+        // butterfly with twiddle 1 (first stages of X^N-1 transforms): no multiply, Y only range-reduced
+        __device__ __forceinline__ void ct_one(T& X, T& Y) const
+        {
+            const T x = csub_hi(X);
+            const T t = csub(csub_hi(Y), four_p); // [0, 8p + 2^32) -> [0, 4p), same range as a product
+            X = x + t;
+            Y = x - t + four_p;
+        }
+        // Inverse values live in [0, 4p + 17 * 2^32): the high-word test leaves 2^32 of slack per stage.
         __device__ __forceinline__ void gs(T& X, T& Y, const Twiddle<T>& tw) const
         {
             const T s = X + Y;
-            const T d = X - Y + four_p;
-            X = csub(s, four_p);
+            const T d = X - Y + six_p;
+            X = csub_hi(s);
             Y = mul(d, tw);
         }
         __device__ __forceinline__ T canon_fwd(T x) const
@@ -163,7 +188,7 @@ namespace gpuntt_b200
         }
     };
 
-    // largest modulus the fast policy accepts: 8p + 2^32 < 2^64 with margin
-    constexpr uint64_t kFastModulusLimit = (1ull << 60) + (1ull << 59);
+    // largest modulus the fast policy accepts: forward needs 8p + 2^33 < 2^64, inverse 10p + 2^37 < 2^64
+    constexpr uint64_t kFastModulusLimit = (1ull << 60) + (1ull << 58);
 
 } // namespace gpuntt_b200
