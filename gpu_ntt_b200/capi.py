@@ -32,6 +32,21 @@ class MergeDesc(C.Structure):
         ("in_", C.c_void_p), ("out", C.c_void_p), ("root_of_unity_table", C.c_void_p),
         ("modulus_value", C.c_uint64), ("mod_inverse_value", C.c_uint64),
         ("modulus_dev", C.c_void_p), ("mod_inverse_dev", C.c_void_p), ("stream", C.c_void_p),
+        ("modulus_order_dev", C.c_void_p), ("poly_order_dev", C.c_void_p),
+    ]
+
+
+FOURSTEP_REFERENCE, FOURSTEP_FUSED = 0, 1
+
+
+class FourStepDesc(C.Structure):
+    """struct gpuntt_b200_4step_desc"""
+    _fields_ = [
+        ("element_bits", C.c_int), ("direction", C.c_int), ("n_power", C.c_int), ("batch_size", C.c_int),
+        ("mod_count", C.c_int), ("io_contract", C.c_int),
+        ("in_", C.c_void_p), ("out", C.c_void_p), ("n1_table", C.c_void_p), ("n2_table", C.c_void_p),
+        ("w_table", C.c_void_p), ("modulus_value", C.c_uint64), ("mod_inverse_value", C.c_uint64),
+        ("modulus_dev", C.c_void_p), ("mod_inverse_dev", C.c_void_p), ("stream", C.c_void_p),
     ]
 
 
@@ -67,6 +82,12 @@ def lib():
         L.gpuntt_b200_ntt_u32.argtypes = [vp, vp, vp, u32, i, i, i, vp]
         L.gpuntt_b200_intt_u32.restype = i
         L.gpuntt_b200_intt_u32.argtypes = [vp, vp, vp, u32, u32, i, i, i, vp]
+        L.gpuntt_b200_4step_ntt.restype = i
+        L.gpuntt_b200_4step_ntt.argtypes = [C.POINTER(FourStepDesc)]
+        L.gpuntt_b200_4step_shape.restype = i
+        L.gpuntt_b200_4step_shape.argtypes = [i, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.gpuntt_b200_transpose.restype = i
+        L.gpuntt_b200_transpose.argtypes = [i, vp, vp, i, i, i, i, vp]
         L.gpuntt_b200_merge_ntt_host.restype = i
         L.gpuntt_b200_merge_ntt_host.argtypes = [C.POINTER(MergeDesc), vp, C.c_size_t]
         L.gpuntt_b200_last_launch_count.restype = i
@@ -100,11 +121,12 @@ def describe_plan(n_power: int, element_bits: int) -> str:
 def merge_ntt(*, in_ptr: int, out_ptr: int, table_ptr: int, n_power: int, batch: int, element_bits: int = 64,
               direction: int = FORWARD, reduction_poly: int = X_N_minus, layout: int = PerPolynomial,
               modulus: int = 0, mod_inverse: int = 0, is_signed: bool = False, mod_count: int = 0,
-              modulus_dev: int = 0, mod_inverse_dev: int = 0, stream: int = 0) -> None:
+              modulus_dev: int = 0, mod_inverse_dev: int = 0, stream: int = 0, modulus_order_dev: int = 0,
+              poly_order_dev: int = 0) -> None:
     """gpuntt_b200_merge_ntt with keyword arguments; pointers are integers (device addresses)."""
     d = MergeDesc(element_bits, int(is_signed), direction, n_power, layout, reduction_poly, batch, mod_count,
                   in_ptr, out_ptr, table_ptr, modulus, mod_inverse, modulus_dev or None, mod_inverse_dev or None,
-                  stream or None)
+                  stream or None, modulus_order_dev or None, poly_order_dev or None)
     check(lib().gpuntt_b200_merge_ntt(C.byref(d)))
 
 
@@ -134,6 +156,32 @@ def intt(x, inv_table, modulus: int, n_inv: int, n_power: int, reduction_poly: i
     merge_ntt(in_ptr=x.data_ptr(), out_ptr=out.data_ptr(), table_ptr=inv_table.data_ptr(), n_power=n_power,
               batch=x.numel() >> n_power, element_bits=bits, direction=INVERSE, reduction_poly=reduction_poly,
               modulus=modulus, mod_inverse=n_inv, stream=_stream_ptr(stream))
+    return out
+
+
+def fourstep_shape(n_power: int):
+    """(n1, n2) of the reference's matrix_dimention()."""
+    a, b = C.c_int(0), C.c_int(0)
+    check(lib().gpuntt_b200_4step_shape(n_power, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def fourstep_ntt(x, n1_table, n2_table, w_table, modulus: int, n_power: int, *, direction: int = FORWARD,
+                 mod_inverse: int = 0, io_contract: int = FOURSTEP_FUSED, out=None, stream=None, mod_count: int = 0,
+                 modulus_dev: int = 0, mod_inverse_dev: int = 0):
+    """GPU_4STEP_NTT (io_contract=FOURSTEP_REFERENCE) / the fused natural-order form on torch CUDA tensors."""
+    out = x if out is None else out
+    d = FourStepDesc(x.element_size() * 8, direction, n_power, x.numel() >> n_power, mod_count, io_contract,
+                     x.data_ptr(), out.data_ptr(), n1_table.data_ptr(), n2_table.data_ptr(), w_table.data_ptr(),
+                     modulus, mod_inverse, modulus_dev or None, mod_inverse_dev or None, _stream_ptr(stream))
+    check(lib().gpuntt_b200_4step_ntt(C.byref(d)))
+    return out
+
+
+def transpose(x, out, row: int, col: int, n_power: int, stream=None):
+    """GPU_Transpose: out[b][c * row + r] = x[b][r * col + c]."""
+    check(lib().gpuntt_b200_transpose(x.element_size() * 8, x.data_ptr(), out.data_ptr(), row, col, n_power,
+                                      x.numel() >> n_power, _stream_ptr(stream)))
     return out
 
 

@@ -1,0 +1,276 @@
+// gpu_ntt_b200/csrc/fourstep.inl -- 4-step (large ring) transforms and the batched transpose, included by
+// merge_ntt.cu inside namespace gpuntt_b200.
+//
+// Replaces GPU_4STEP_NTT / GPU_Transpose and their 15 kernels (src/lib/ntt_4step/ntt_4step.cu:36-3232 of the
+// reference).  The reference runs transpose -> n1-point column kernels -> W product fused into the first row
+// kernel -> row kernels -> transpose (5 HBM round trips + the W read).  Here the n1 x n2 matrix view is never
+// transposed in memory for the arithmetic:
+//   forward  = the strided pass of the merge engine over the TOP log2(n1) index bits with the n1 table (these
+//              are exactly the first log2(n1) stages of a size-N Cooley-Tukey transform) with the W product
+//              applied as the pass is stored, then an ordinary batched size-n2 Merge-NTT over the batch*n1
+//              rows -- which is the 2^16 fast path for logN >= 23;
+//   inverse  = batched size-n1 Merge-INTT over the batch*n2 contiguous rows (no n^-1), then strided
+//              Gentleman-Sande passes over the top log2(n2) index bits with the n2 table, the W^-1 product
+//              applied as the first of them loads (transposed index) and n^-1 as the last one stores.
+// Only the I/O contracts that ask for it pay a transpose (see gpuntt_b200_4step_desc::io_contract).
+
+// matrix_dimention() of the reference (nttparameters.cu:305-354), index logn - 12
+static const int k4StepN1[] = {32, 32, 32, 64, 128, 32, 32, 32, 32, 64, 128, 128, 256};
+static const int k4StepN2[] = {128, 256, 512, 512, 512, 4096, 8192, 16384, 32768, 32768, 32768, 65536, 65536};
+
+static bool fourstep_shape(int n_power, int* n1, int* n2)
+{
+    if (n_power < 12 || n_power > 24) return false;
+    if (n1) *n1 = k4StepN1[n_power - 12];
+    if (n2) *n2 = k4StepN2[n_power - 12];
+    return true;
+}
+static int ilog2i(int v)
+{
+    int l = 0;
+    while ((1 << l) < v) l++;
+    return l;
+}
+
+// out[x * row + y] = in[y * col + x] for every polynomial (GPU_Transpose, ntt_4step.cu:36-66): `in` is a
+// row x col row-major matrix per polynomial, `out` its col x row transpose.  32 x 32 tiles through padded
+// shared memory, both sides coalesced.
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in, T* __restrict__ out, int row, int col,
+                                                        long long poly_elems)
+{
+    __shared__ T tile[32][33];
+    const T* src = in + (size_t) blockIdx.z * poly_elems;
+    T* dst = out + (size_t) blockIdx.z * poly_elems;
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5; // 32 x 8
+#pragma unroll
+    for (int r = ty; r < 32; r += 8)
+        if (y0 + r < row && x0 + tx < col) tile[r][tx] = src[(size_t) (y0 + r) * col + (x0 + tx)];
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8)
+        if (x0 + r < col && y0 + tx < row) dst[(size_t) (x0 + r) * row + (y0 + tx)] = tile[tx][r];
+}
+
+template <typename T>
+static cudaError_t launch_transpose(const T* in, T* out, int row, int col, long long poly_elems, int batch, cudaStream_t st, int kind)
+{
+    ProfScope prof(kind, st);
+    cudaError_t e = cudaSuccess;
+    for (int b0 = 0; b0 < batch && e == cudaSuccess; b0 += 65535) // gridDim.z limit
+    {
+        const int nb = batch - b0 < 65535 ? batch - b0 : 65535;
+        dim3 grid((unsigned) ((col + 31) / 32), (unsigned) ((row + 31) / 32), (unsigned) nb);
+        transpose_kernel<T><<<grid, 256, 0, st>>>(in + (size_t) b0 * poly_elems, out + (size_t) b0 * poly_elems, row, col, poly_elems);
+        g_last_launches++;
+        g_total_launches++;
+        e = cudaGetLastError();
+    }
+    return e;
+}
+
+static int transpose_execute(int element_bits, const void* in, void* out, int row, int col, int n_power, int batch_size, void* stream)
+{
+    g_last_launches = 0;
+    if (element_bits != 32 && element_bits != 64) return fail(GPUNTT_B200_ERR_ARGUMENT, "element_bits must be 32 or 64");
+    if (row <= 0 || col <= 0 || batch_size < 0 || n_power < 0 || n_power > 40) return fail(GPUNTT_B200_ERR_ARGUMENT, "bad transpose shape");
+    if (batch_size == 0) return GPUNTT_B200_OK;
+    if (!in || !out || in == out) return fail(GPUNTT_B200_ERR_ARGUMENT, "transpose needs distinct non-null buffers");
+    const long long poly = 1LL << n_power; // the reference strides polynomials by 1 << n_power (ntt_4step.cu:44)
+    cudaError_t e = element_bits == 64
+                        ? launch_transpose<uint64_t>((const uint64_t*) in, (uint64_t*) out, row, col, poly, batch_size, (cudaStream_t) stream, 9)
+                        : launch_transpose<uint32_t>((const uint32_t*) in, (uint32_t*) out, row, col, poly, batch_size, (cudaStream_t) stream, 9);
+    if (e != cudaSuccess) return cuda_fail(e, "transpose_kernel launch");
+    return GPUNTT_B200_OK;
+}
+
+template <typename T> static int fourstep_execute_t(const gpuntt_b200_4step_desc* d)
+{
+    const int n = d->n_power;
+    int n1 = 0, n2 = 0;
+    fourstep_shape(n, &n1, &n2);
+    const int lg1 = ilog2i(n1), lg2 = ilog2i(n2);
+    const bool inv = d->direction == GPUNTT_B200_INVERSE;
+    const bool rns = d->mod_count > 0;
+    const bool fused = d->io_contract == GPUNTT_B200_4STEP_FUSED;
+    const int bits = (int) sizeof(T) * 8;
+    const int batch = d->batch_size;
+    const long long N = 1LL << n;
+    cudaStream_t st = (cudaStream_t) d->stream;
+    const T* in = reinterpret_cast<const T*>(d->in);
+    T* out = reinterpret_cast<T*>(d->out);
+    if ((long long) batch * n2 > 0x7fffffffLL) return fail(GPUNTT_B200_ERR_ARGUMENT, "batch_size * n2 exceeds 2^31 - 1 rows");
+
+    // scratch for the contracts that cannot run in `out` alone
+    T* ws = nullptr;
+    if (fused || inv)
+    {
+        void* w = nullptr;
+        cudaError_t e = get_workspace(d->stream, 5, (size_t) batch * (size_t) N * sizeof(T), &w);
+        if (e != cudaSuccess) return cuda_fail(e, "4-step workspace allocation");
+        ws = reinterpret_cast<T*>(w);
+    }
+
+    auto base_call = [&](CoreCall<T>& cc)
+    {
+        cc.mod_count = d->mod_count;
+        cc.plus = 0; // the 4-step tables always follow the X^N-1 index rule (ntt_4step_cpu.cu:111-191)
+        cc.inverse = inv;
+        cc.p = (T) d->modulus_value;
+        cc.ninv = (T) d->mod_inverse_value;
+        cc.mod_values = rns ? reinterpret_cast<const T*>(d->modulus_dev) : nullptr;
+        cc.ninv_dev = rns ? reinterpret_cast<const T*>(d->mod_inverse_dev) : nullptr;
+        cc.shared_tables = 1; // the reference's RNS 4-step kernels index one table for every modulus (ntt_4step.cu:150-229)
+        cc.st = st;
+    };
+    // batched size-2^m Merge transform over `rows` contiguous rows of `buf` (in place unless src given)
+    auto row_transforms = [&](const T* src, T* buf, int m, long long rows, const void* table, int mod_shift, bool unit_ninv) -> int
+    {
+        if (!rns)
+        {
+            gpuntt_b200_merge_desc md;
+            memset(&md, 0, sizeof(md));
+            md.element_bits = bits;
+            md.direction = d->direction;
+            md.n_power = m;
+            md.ntt_layout = GPUNTT_B200_PER_POLYNOMIAL;
+            md.reduction_poly = GPUNTT_B200_X_N_MINUS;
+            md.batch_size = (int) rows;
+            md.in = src;
+            md.out = buf;
+            md.root_of_unity_table = table;
+            md.modulus_value = d->modulus_value;
+            md.mod_inverse_value = unit_ninv ? 1 : d->mod_inverse_value;
+            md.stream = d->stream;
+            return merge_execute_t<T>(&md);
+        }
+        CoreCall<T> cc;
+        base_call(cc);
+        cc.in = src;
+        cc.out = buf;
+        cc.table = reinterpret_cast<const T*>(table);
+        cc.table_len = 1LL << (m - 1);
+        cc.n_power = m;
+        cc.batch = (int) rows;
+        cc.mod_shift = mod_shift;
+        cc.unit_ninv = unit_ninv;
+        cc.ws_slot = 0;
+        const MergePlan mp = make_merge_plan(m, bits);
+        cc.npasses = mp.npasses;
+        for (int i = 0; i < mp.npasses; i++) cc.pass[i] = mp.pass[inv ? (mp.npasses - 1 - i) : i];
+        return run_core<T>(cc);
+    };
+
+    int rc = GPUNTT_B200_OK;
+    cudaError_t e = cudaSuccess;
+    if (!inv)
+    {
+        // natural-order matrix M (n1 x n2) in `src`; the reference contract hands us M^T
+        const T* src = in;
+        T* work = fused ? ws : out;
+        if (!fused)
+        {
+            e = launch_transpose<T>(in, out, n2, n1, N, batch, st, 9);
+            if (e != cudaSuccess) return cuda_fail(e, "transpose_kernel launch");
+            src = out;
+        }
+        {
+            // column transforms: stages on index bits [lg2, n), then W[offset] as the pass is stored
+            CoreCall<T> cc;
+            base_call(cc);
+            cc.in = src;
+            cc.out = work;
+            cc.table = reinterpret_cast<const T*>(d->n1_table);
+            cc.table_len = n1 >> 1;
+            cc.n_power = n;
+            cc.batch = batch;
+            cc.w_table = reinterpret_cast<const T*>(d->w_table);
+            cc.w_mode = 1;
+            cc.ws_slot = 3;
+            cc.npasses = 1;
+            cc.pass[0] = make_strided_pass(lg2, lg1, bits);
+            rc = run_core<T>(cc);
+            if (rc != GPUNTT_B200_OK) return rc;
+        }
+        rc = row_transforms(work, work, lg2, (long long) batch * n1, d->n2_table, lg1, false);
+        if (rc != GPUNTT_B200_OK) return rc;
+        if (fused)
+        {
+            e = launch_transpose<T>(work, out, n1, n2, N, batch, st, 9);
+            if (e != cudaSuccess) return cuda_fail(e, "transpose_kernel launch");
+        }
+    }
+    else
+    {
+        // T = n2 rows of n1 (the reference contract passes it; the fused contract passes its transpose)
+        const T* src = in;
+        if (fused)
+        {
+            e = launch_transpose<T>(in, ws, n2, n1, N, batch, st, 9);
+            if (e != cudaSuccess) return cuda_fail(e, "transpose_kernel launch");
+            src = ws;
+        }
+        rc = row_transforms(src, ws, lg1, (long long) batch * n2, d->n1_table, lg2, true);
+        if (rc != GPUNTT_B200_OK) return rc;
+        {
+            CoreCall<T> cc;
+            base_call(cc);
+            cc.in = ws;
+            cc.out = fused ? out : ws;
+            cc.table = reinterpret_cast<const T*>(d->n2_table);
+            cc.table_len = n2 >> 1;
+            cc.n_power = n;
+            cc.batch = batch;
+            cc.w_table = reinterpret_cast<const T*>(d->w_table);
+            cc.w_mode = 2;
+            cc.w_lo = lg1;
+            cc.w_hi = lg2;
+            cc.ws_slot = 3;
+            if (lg2 <= 9)
+            {
+                cc.npasses = 1;
+                cc.pass[0] = make_strided_pass(lg1, lg2, bits);
+            }
+            else
+            {
+                const int da = lg2 / 2;
+                cc.npasses = 2;
+                cc.pass[0] = make_strided_pass(lg1, da, bits);
+                cc.pass[1] = make_strided_pass(lg1 + da, lg2 - da, bits);
+            }
+            rc = run_core<T>(cc);
+            if (rc != GPUNTT_B200_OK) return rc;
+        }
+        if (!fused)
+        {
+            e = launch_transpose<T>(ws, out, n2, n1, N, batch, st, 9);
+            if (e != cudaSuccess) return cuda_fail(e, "transpose_kernel launch");
+        }
+    }
+    return GPUNTT_B200_OK;
+}
+
+static int fourstep_execute(const gpuntt_b200_4step_desc* d)
+{
+    g_last_launches = 0;
+    if (!d) return fail(GPUNTT_B200_ERR_ARGUMENT, "null descriptor");
+    if (d->element_bits != 32 && d->element_bits != 64) return fail(GPUNTT_B200_ERR_ARGUMENT, "element_bits must be 32 or 64");
+    if (!fourstep_shape(d->n_power, nullptr, nullptr))
+        return fail(GPUNTT_B200_ERR_N_POWER, "4-step transforms exist for n_power 12..24 (the reference prints and returns, ntt_4step.cu:2529-2532)");
+    if (d->direction != GPUNTT_B200_FORWARD && d->direction != GPUNTT_B200_INVERSE)
+        return fail(GPUNTT_B200_ERR_ARGUMENT, "direction must be FORWARD or INVERSE");
+    if (d->io_contract != GPUNTT_B200_4STEP_REFERENCE && d->io_contract != GPUNTT_B200_4STEP_FUSED)
+        return fail(GPUNTT_B200_ERR_ARGUMENT, "unknown io_contract");
+    if (d->batch_size < 0 || d->mod_count < 0) return fail(GPUNTT_B200_ERR_ARGUMENT, "negative batch_size / mod_count");
+    if (d->batch_size == 0) return GPUNTT_B200_OK;
+    if (!d->in || !d->out || !d->n1_table || !d->n2_table || !d->w_table) return fail(GPUNTT_B200_ERR_ARGUMENT, "null data / table pointer");
+    if (d->io_contract == GPUNTT_B200_4STEP_REFERENCE && d->in == d->out)
+        return fail(GPUNTT_B200_ERR_ARGUMENT, "the reference 4-step contract is out of place (device_in != device_out)");
+    if (d->mod_count > 0 && !d->modulus_dev) return fail(GPUNTT_B200_ERR_ARGUMENT, "RNS form needs modulus_dev");
+    if (d->mod_count > 0 && d->direction == GPUNTT_B200_INVERSE && !d->mod_inverse_dev)
+        return fail(GPUNTT_B200_ERR_ARGUMENT, "RNS inverse needs mod_inverse_dev");
+    if (d->mod_count == 0 && d->modulus_value < 5) return fail(GPUNTT_B200_ERR_ARGUMENT, "modulus_value too small");
+    if (d->element_bits == 64) return fourstep_execute_t<uint64_t>(d);
+    return fourstep_execute_t<uint32_t>(d);
+}

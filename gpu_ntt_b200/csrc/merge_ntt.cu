@@ -181,9 +181,9 @@ namespace gpuntt_b200
 
         // ---- which tile is this?
         const long long tile = blockIdx.x;
-        long long gbase;   // global element offset of local index 0
+        long long obase;   // offset inside polynomial poly0 of local index 0
         int jrow_tile;     // (index within polynomial >> lo) of local row 0
-        long long poly0;   // polynomial of local index 0
+        long long poly0;   // polynomial (transform number) of local index 0
         if (lo > 0)
         {
             const int hi = lo + pl.d;
@@ -191,51 +191,84 @@ namespace gpuntt_b200
             const long long cc = tile & ((1LL << cc_bits) - 1);
             const long long P = (tile >> cc_bits) & ((1LL << pre_bits) - 1);
             poly0 = tile >> (cc_bits + pre_bits);
-            gbase = (poly0 << n) + (P << hi) + (cc << c);
+            obase = (P << hi) + (cc << c);
             jrow_tile = (int) (P << pl.d);
         }
         else
         {
-            gbase = tile << k;
-            jrow_tile = (int) (gbase & ((1LL << n) - 1));
-            poly0 = gbase >> n;
+            const long long g0 = tile << k;
+            obase = g0 & ((1LL << n) - 1);
+            jrow_tile = (int) obase;
+            poly0 = g0 >> n;
         }
         const int cmask = (1 << c) - 1;
         const int poly_shift = n - lo; // (l >> c) >> poly_shift = polynomial offset inside the tile
+        const long long nmask = (1LL << n) - 1;
+        // transform number b -> modulus index / polynomial slot (the *_Ordered entry points of the reference)
+        auto slice_index = [&](long long b) -> int { return (int) ((b >> a.mod_shift) % a.mod_count); };
+        auto mod_index = [&](long long b) -> int
+        {
+            const int mi = slice_index(b);
+            return a.mod_order ? a.mod_order[mi] : mi;
+        };
+        // global element index of local element (row, col); false when the transform does not exist (ragged last tile)
+        auto locate = [&](int row, int col, long long& g, long long& off, long long& b) -> bool
+        {
+            const long long o = obase + ((long long) row << lo) + col;
+            b = poly0 + (o >> n);
+            off = o & nmask;
+            if (b >= a.batch) return false;
+            const long long slot = a.poly_order ? (long long) a.poly_order[b] : b;
+            g = (slot << n) + off;
+            return true;
+        };
+        auto w_index = [&](long long off) -> long long
+        {
+            return a.w_mode == 2 ? (((off & ((1LL << a.w_lo) - 1)) << a.w_hi) | (off >> a.w_lo)) : off;
+        };
 
         // ---- global -> shared
+        // per-element fix-ups on the way in: signed input (first forward pass), 4-step inverse twiddle matrix
+        const bool fix_signed = (!INV) && pl.first && a.signed_io;
+        const bool w_in = (a.w_mode == 2) && pl.first;
+        auto fix_in = [&](T x, long long b, long long off) -> T
         {
-            const bool fix_signed = (!INV) && pl.first && a.signed_io;
+            if (!fix_signed && !w_in) return x;
+            T p = a.p, bit = a.bar_bit, mu = a.bar_mu;
+            const T* w = a.w_table;
+            if constexpr (RNS)
+            {
+                const int mi = mod_index(b);
+                p = a.mod_values[3 * mi];
+                bit = a.mod_values[3 * mi + 1];
+                mu = a.mod_values[3 * mi + 2];
+                if (w_in && !a.shared_tables) w += ((size_t) mi << n);
+            }
+            if (fix_signed && (ST) x < 0) x += p; // p - |x|  (modular_arith.cuh:372-385 of the reference)
+            if (w_in) x = barrett_mul(x, w[w_index(off)], p, bit, mu);
+            return x;
+        };
+        {
             const T* gin = reinterpret_cast<const T*>(a.in);
-            const bool vec_ok = ((reinterpret_cast<uintptr_t>(gin) & 15) == 0) && (c == 0 || c >= 2) &&
-                                (k >= 2);
+            const bool vec_ok = ((reinterpret_cast<uintptr_t>(gin) & 15) == 0) && (c == 0 || c >= 2) && (k >= 2) &&
+                                ((1 << n) >= VN);
             for (int l = tid * VN; l < tile_elems; l += kThreads * VN)
             {
                 const int row = l >> c, col = l & cmask;
-                const long long g = gbase + ((long long) row << lo) + col;
+                long long g, off, b;
                 T v[VN];
-                if (vec_ok && g + VN <= a.total_elems)
+                if (vec_ok && locate(row, col, g, off, b))
                 {
                     V vv = *reinterpret_cast<const V*>(gin + g);
                     memcpy(v, &vv, sizeof(V));
+#pragma unroll
+                    for (int i = 0; i < VN; i++) v[i] = fix_in(v[i], b, off + i);
                 }
                 else
                 {
 #pragma unroll
-                    for (int i = 0; i < VN; i++)
-                    {
-                        // (c < 2 only happens for contiguous tiles, where l+i is simply g+i)
-                        v[i] = (g + i < a.total_elems) ? gin[g + i] : T(0);
-                    }
-                }
-                if (fix_signed)
-                {
-                    T p = a.p;
-                    if constexpr (RNS)
-                        p = a.mod_values[3 * (int) ((poly0 + (row >> poly_shift)) % a.mod_count)];
-#pragma unroll
-                    for (int i = 0; i < VN; i++)
-                        if ((ST) v[i] < 0) v[i] += p; // p - |x|  (modular_arith.cuh:372-385 of the reference)
+                    for (int i = 0; i < VN; i++) // (c < 2 only happens for contiguous tiles, where element l+i is column col+i)
+                        v[i] = locate(row, col + i, g, off, b) ? fix_in(gin[g], b, off) : T(0);
                 }
                 V vv;
                 memcpy(&vv, v, sizeof(V));
@@ -279,9 +312,9 @@ namespace gpuntt_b200
                 const Twiddle<T>* tw = reinterpret_cast<const Twiddle<T>*>(a.tw);
                 if constexpr (RNS)
                 {
-                    const int mi = (int) ((poly0 + (row >> poly_shift)) % a.mod_count);
-                    p = a.mod_values[3 * mi];
-                    tw += ((size_t) mi << a.tw_stride_log);
+                    const long long b = poly0 + (row >> poly_shift);
+                    p = a.mod_values[3 * mod_index(b)];
+                    tw += ((size_t) slice_index(b) << a.tw_stride_log);
                 }
                 const Mod<T, FAST> M(p);
                 if (lb == 0)
@@ -311,43 +344,50 @@ namespace gpuntt_b200
         // ---- shared -> global
         {
             T* gout = a.out;
-            const bool vec_ok = ((reinterpret_cast<uintptr_t>(gout) & 15) == 0) && (c == 0 || c >= 2) &&
-                                (k >= 2);
+            const bool vec_ok = ((reinterpret_cast<uintptr_t>(gout) & 15) == 0) && (c == 0 || c >= 2) && (k >= 2) &&
+                                ((1 << n) >= VN);
             const bool centre = INV && pl.last && a.signed_io;
+            // last pass: canonical form, n^-1 and centred output (inverse), 4-step twiddle matrix (forward)
+            auto fix_out = [&](T x, long long b, long long off) -> T
+            {
+                if (!pl.last) return x;
+                T p = a.p, bit = a.bar_bit, mu = a.bar_mu;
+                Twiddle<T> ni{a.ninv_w, a.ninv_wq};
+                const T* w = a.w_table;
+                if constexpr (RNS)
+                {
+                    const int mi = mod_index(b);
+                    p = a.mod_values[3 * mi];
+                    bit = a.mod_values[3 * mi + 1];
+                    mu = a.mod_values[3 * mi + 2];
+                    if constexpr (INV) ni = reinterpret_cast<const Twiddle<T>*>(a.ninv_tw)[slice_index(b)];
+                    if (a.w_mode == 1 && !a.shared_tables) w += ((size_t) mi << n);
+                }
+                const Mod<T, FAST> M(p);
+                if constexpr (INV)
+                {
+                    x = M.canon_inv(x, ni);
+                    if (centre && x > (p >> 1)) x -= p; // modular_arith.cuh:389-405 of the reference
+                }
+                else
+                {
+                    x = M.canon_fwd(x);
+                    if (a.w_mode == 1) x = barrett_mul(x, w[off], p, bit, mu);
+                }
+                return x;
+            };
             for (int l = tid * VN; l < tile_elems; l += kThreads * VN)
             {
                 const int row = l >> c, col = l & cmask;
-                const long long g = gbase + ((long long) row << lo) + col;
-                if (g >= a.total_elems) continue;
+                long long g, off, b;
                 V vv = *reinterpret_cast<const V*>(sm + swz<T>(l));
                 T v[VN];
                 memcpy(v, &vv, sizeof(V));
-                if (pl.last)
+                if (vec_ok)
                 {
-                    T p = a.p;
-                    Twiddle<T> ni{a.ninv_w, a.ninv_wq};
-                    if constexpr (RNS)
-                    {
-                        const int mi = (int) ((poly0 + (row >> poly_shift)) % a.mod_count);
-                        p = a.mod_values[3 * mi];
-                        if constexpr (INV) ni = reinterpret_cast<const Twiddle<T>*>(a.ninv_tw)[mi];
-                    }
-                    const Mod<T, FAST> M(p);
+                    if (!locate(row, col, g, off, b)) continue;
 #pragma unroll
-                    for (int i = 0; i < VN; i++)
-                    {
-                        if constexpr (INV)
-                        {
-                            T x = M.canon_inv(v[i], ni);
-                            if (centre && x > (p >> 1)) x -= p; // modular_arith.cuh:389-405 of the reference
-                            v[i] = x;
-                        }
-                        else
-                            v[i] = M.canon_fwd(v[i]);
-                    }
-                }
-                if (vec_ok && g + VN <= a.total_elems)
-                {
+                    for (int i = 0; i < VN; i++) v[i] = fix_out(v[i], b, off + i);
                     memcpy(&vv, v, sizeof(V));
                     *reinterpret_cast<V*>(gout + g) = vv;
                 }
@@ -355,7 +395,7 @@ namespace gpuntt_b200
                 {
 #pragma unroll
                     for (int i = 0; i < VN; i++)
-                        if (g + i < a.total_elems) gout[g + i] = v[i];
+                        if (locate(row, col + i, g, off, b)) gout[g] = fix_out(v[i], b, off);
                 }
             }
         }
@@ -366,22 +406,26 @@ namespace gpuntt_b200
     // after the slices: the same pair for n^-1 of every modulus (RNS inverse only).
     template <typename T>
     __global__ void twiddle_prep_kernel(const T* __restrict__ table, Twiddle<T>* __restrict__ out,
-                                        const T* __restrict__ mod_values, T p_single, int slices,
-                                        int stride_log, long long table_len,
-                                        const T* __restrict__ ninv_dev, Twiddle<T>* __restrict__ ninv_out)
+                                        const T* __restrict__ mod_values, T p_single, int slices, int in_stride_log,
+                                        int out_stride_log, int shared_tables, long long table_len,
+                                        const T* __restrict__ ninv_dev, Twiddle<T>* __restrict__ ninv_out,
+                                        const int* __restrict__ mod_order, int unit_ninv)
     {
+        // output slice m serves the transforms with b % mod_count == m; with mod_order their modulus, table
+        // slice and n^-1 are entry mod_order[m] of the caller's arrays (ntt.cu:3117-3118 of the reference)
         const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
         const int m = blockIdx.y;
-        const T p = mod_values ? mod_values[3 * m] : p_single;
+        const int mi = mod_order ? mod_order[m] : m;
+        const T p = mod_values ? mod_values[3 * mi] : p_single;
         if (i < table_len)
         {
-            const size_t idx = ((size_t) m << stride_log) + (size_t) i;
-            const T w = table[idx];
-            out[idx] = Twiddle<T>{w, shoup_companion(w, p)};
+            const size_t src = shared_tables ? (size_t) i : (((size_t) mi << in_stride_log) + (size_t) i);
+            const T w = table[src];
+            out[((size_t) m << out_stride_log) + (size_t) i] = Twiddle<T>{w, shoup_companion(w, p)};
         }
-        if (ninv_dev && i == 0)
+        if ((ninv_dev || unit_ninv) && i == 0)
         {
-            const T w = ninv_dev[m];
+            const T w = unit_ninv ? T(1) : ninv_dev[mi];
             ninv_out[m] = Twiddle<T>{w, shoup_companion(w, p)};
         }
     }
@@ -407,6 +451,23 @@ namespace gpuntt_b200
         ps.nrounds = nr;
         for (int i = 0; i < nr; i++) ps.round_bits[i] = rounds_low_first[nr - 1 - i];
         for (int i = nr; i < kMaxRounds; i++) ps.round_bits[i] = 0;
+    }
+
+    PassPlan make_strided_pass(int lo, int d, int element_bits)
+    {
+        const int kmax = (element_bits == 64) ? 13 : 14;
+        const int cmin = (element_bits == 64) ? 4 : 5;
+        PassPlan ps{};
+        ps.lo = lo;
+        ps.d = d;
+        int c = 12 - d;
+        if (c < cmin) c = cmin;
+        if (c > lo) c = lo;
+        if (d + c > kmax) c = kmax - d;
+        ps.c = c;
+        ps.tile_log = d + c;
+        split_rounds(ps, element_bits);
+        return ps;
     }
 
     MergePlan make_merge_plan(int n, int element_bits)
@@ -601,6 +662,129 @@ namespace gpuntt_b200
         return cudaGetLastError();
     }
 
+    // ------------------------------------------------------------------ pass sequencer
+    // One "core call": a list of passes (already in execution order) over one [batch][2^n_power] array with one
+    // root table.  merge_execute_t builds it from make_merge_plan; the 4-step driver builds its own lists.
+    template <typename T> struct CoreCall
+    {
+        const void* in = nullptr;
+        T* out = nullptr;
+        const T* table = nullptr; // caller's bit-reversed root table (plain residues)
+        long long table_len = 0;  // entries per modulus slice
+        int stride_log = 0;       // log2 of the slice stride in `table` (RNS); ignored when shared_tables
+        int shared_tables = 0;
+        int n_power = 0, batch = 0, mod_count = 0, plus = 0, signed_io = 0;
+        bool inverse = false;
+        T p = 0, ninv = 0;                 // single modulus
+        const T* mod_values = nullptr;     // RNS: device Modulus<T>[mod_count]
+        const T* ninv_dev = nullptr;       // RNS inverse: device n^-1 per modulus
+        const int* mod_order = nullptr;
+        const int* poly_order = nullptr;
+        int mod_shift = 0;
+        bool unit_ninv = false;            // inverse without the final n^-1 (4-step column phase)
+        const T* w_table = nullptr;
+        int w_mode = 0, w_lo = 0, w_hi = 0;
+        cudaStream_t st = nullptr;
+        int ws_slot = 0;                   // workspace slot for the (w, w') table
+        int npasses = 0;
+        PassPlan pass[4];
+        bool mark_first = true, mark_last = true; // pass[0] reads caller input / pass[npasses-1] writes final results
+    };
+
+    template <typename T> static void barrett_constants(T p, T& bit, T& mu)
+    {
+        bit = 0;
+        for (T v = p; v; v >>= 1) bit++;
+        if constexpr (sizeof(T) == 8)
+            mu = p ? (T) ((((unsigned __int128) 1) << (2 * bit + 1)) / p) : 0;
+        else
+            mu = p ? (T) ((((uint64_t) 1) << (2 * bit + 1)) / p) : 0;
+    }
+
+    template <typename T> static int run_core(const CoreCall<T>& cc)
+    {
+        const bool rns = cc.mod_count > 0;
+        const int slices = rns ? cc.mod_count : 1;
+        const int tw_stride_log = cc.shared_tables ? 0 : cc.stride_log;
+        // companion slices are always laid out (1 << lg) apart, lg = ceil(log2(table_len))
+        int lg = 0;
+        while ((1LL << lg) < cc.table_len) lg++;
+        const int out_stride_log = cc.shared_tables ? lg : cc.stride_log;
+        const size_t tw_elems = ((size_t) (slices - 1) << out_stride_log) + (size_t) cc.table_len;
+        const size_t bytes = (tw_elems + (size_t) slices) * sizeof(Twiddle<T>);
+        void* ws = nullptr;
+        cudaError_t e = get_workspace((void*) cc.st, cc.ws_slot, bytes, &ws);
+        if (e != cudaSuccess) return cuda_fail(e, "workspace allocation");
+        Twiddle<T>* tw = reinterpret_cast<Twiddle<T>*>(ws);
+        Twiddle<T>* ninv_tw = tw + tw_elems;
+        {
+            ProfScope prof(0, cc.st);
+            const int threads = 256;
+            dim3 grid((unsigned) ((cc.table_len + threads - 1) / threads), (unsigned) slices);
+            twiddle_prep_kernel<T><<<grid, threads, 0, cc.st>>>(cc.table, tw, cc.mod_values, cc.p, slices, tw_stride_log, out_stride_log,
+                                                                cc.shared_tables, cc.table_len,
+                                                                (rns && cc.inverse && !cc.unit_ninv) ? cc.ninv_dev : nullptr, ninv_tw,
+                                                                cc.mod_order, (rns && cc.inverse && cc.unit_ninv) ? 1 : 0);
+            g_last_launches++;
+            g_total_launches++;
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return cuda_fail(e, "twiddle_prep_kernel launch");
+        }
+        PassArgs<T> args{};
+        args.tw = tw;
+        args.mod_values = cc.mod_values;
+        args.ninv_tw = ninv_tw;
+        args.p = cc.p;
+        if (cc.inverse && !rns)
+        {
+            args.ninv_w = cc.unit_ninv ? T(1) : cc.ninv;
+            args.ninv_wq = cc.p ? shoup_companion(args.ninv_w, cc.p) : 0;
+        }
+        args.n_power = cc.n_power;
+        args.mod_count = cc.mod_count;
+        args.tw_stride_log = out_stride_log;
+        args.plus = cc.plus;
+        args.signed_io = cc.signed_io;
+        args.total_elems = (long long) cc.batch << cc.n_power;
+        args.mod_order = cc.mod_order;
+        args.poly_order = cc.poly_order;
+        args.batch = cc.batch;
+        args.mod_shift = cc.mod_shift;
+        args.shared_tables = cc.shared_tables;
+        args.w_table = cc.w_table;
+        args.w_mode = cc.w_mode;
+        args.w_lo = cc.w_lo;
+        args.w_hi = cc.w_hi;
+        if (!rns) barrett_constants<T>(cc.p, args.bar_bit, args.bar_mu);
+        bool fast = false;
+        if constexpr (sizeof(T) == 8) fast = !rns && (uint64_t) cc.p < kFastModulusLimit;
+        for (int i = 0; i < cc.npasses; i++)
+        {
+            args.plan = cc.pass[i];
+            args.plan.first = (i == 0) && cc.mark_first;
+            args.plan.last = (i == cc.npasses - 1) && cc.mark_last;
+            args.in = (i == 0) ? cc.in : cc.out; // later passes chain through `out` (also out of place)
+            args.out = cc.out;
+            if constexpr (sizeof(T) == 8)
+            {
+                if (fast)
+                    e = cc.inverse ? launch_pass<T, true, false, true>(args, cc.batch, cc.st, i + 1)
+                                   : launch_pass<T, false, false, true>(args, cc.batch, cc.st, i + 1);
+            }
+            if (!fast)
+            {
+                if (cc.inverse)
+                    e = rns ? launch_pass<T, true, true, false>(args, cc.batch, cc.st, i + 1)
+                            : launch_pass<T, true, false, false>(args, cc.batch, cc.st, i + 1);
+                else
+                    e = rns ? launch_pass<T, false, true, false>(args, cc.batch, cc.st, i + 1)
+                            : launch_pass<T, false, false, false>(args, cc.batch, cc.st, i + 1);
+            }
+            if (e != cudaSuccess) return cuda_fail(e, "merge_pass_kernel launch");
+        }
+        return GPUNTT_B200_OK;
+    }
+
     template <typename T> static int merge_execute_t(const gpuntt_b200_merge_desc* d)
     {
         const int n = d->n_power;
@@ -618,84 +802,30 @@ namespace gpuntt_b200
             if (fe != cudaSuccess) return cuda_fail(fe, "fast_pass_kernel launch");
             if (launched > 0) return GPUNTT_B200_OK;
         }
-        const int slices = rns ? d->mod_count : 1;
-        const long long table_len = plus ? (1LL << n) : (1LL << (n - 1));
-        const int stride_log = n; // the reference's RNS tables are spaced (1 << n_power) apart for both ring types
-
-        // scratch: (w, w') pairs for every table entry (+ n^-1 pairs for RNS inverse)
-        const size_t tw_elems = ((size_t) (slices - 1) << stride_log) + (size_t) table_len;
-        const size_t bytes = (tw_elems + (size_t) slices) * sizeof(Twiddle<T>);
-        void* ws = nullptr;
-        cudaError_t e = get_workspace(d->stream, 0, bytes, &ws);
-        if (e != cudaSuccess) return cuda_fail(e, "workspace allocation");
-        Twiddle<T>* tw = reinterpret_cast<Twiddle<T>*>(ws);
-        Twiddle<T>* ninv_tw = tw + tw_elems;
-
-        const T* mod_values = rns ? reinterpret_cast<const T*>(d->modulus_dev) : nullptr;
-        {
-            ProfScope prof(0, st);
-            const int threads = 256;
-            dim3 grid((unsigned) ((table_len + threads - 1) / threads), (unsigned) slices);
-            twiddle_prep_kernel<T><<<grid, threads, 0, st>>>(
-                reinterpret_cast<const T*>(d->root_of_unity_table), tw, mod_values, (T) d->modulus_value,
-                slices, stride_log, table_len,
-                (rns && inv) ? reinterpret_cast<const T*>(d->mod_inverse_dev) : nullptr, ninv_tw);
-            g_last_launches++;
-            g_total_launches++;
-            e = cudaGetLastError();
-            if (e != cudaSuccess) return cuda_fail(e, "twiddle_prep_kernel launch");
-        }
-
-        MergePlan mp = make_merge_plan(n, (int) sizeof(T) * 8);
-        PassArgs<T> args{};
-        args.tw = tw;
-        args.mod_values = mod_values;
-        args.ninv_tw = ninv_tw;
-        args.p = (T) d->modulus_value;
-        if (inv && !rns)
-        {
-            const T p = (T) d->modulus_value, w = (T) d->mod_inverse_value;
-            args.ninv_w = w;
-            if constexpr (sizeof(T) == 8)
-                args.ninv_wq = p ? (T) ((((unsigned __int128) w) << 64) / p) : 0;
-            else
-                args.ninv_wq = p ? (T) ((((uint64_t) w) << 32) / p) : 0;
-        }
-        args.n_power = n;
-        args.mod_count = d->mod_count;
-        args.tw_stride_log = stride_log;
-        args.plus = plus ? 1 : 0;
-        args.signed_io = d->is_signed ? 1 : 0;
-        args.total_elems = (long long) d->batch_size << n;
-
-        for (int i = 0; i < mp.npasses; i++)
-        {
-            const int pi = inv ? (mp.npasses - 1 - i) : i;
-            args.plan = mp.pass[pi];
-            args.plan.first = (i == 0);
-            args.plan.last = (i == mp.npasses - 1);
-            args.in = (i == 0) ? d->in : d->out; // later passes chain through `out` (also out of place)
-            args.out = reinterpret_cast<T*>(d->out);
-            bool fast = false;
-            if constexpr (sizeof(T) == 8) fast = !rns && (uint64_t) d->modulus_value < kFastModulusLimit;
-            if constexpr (sizeof(T) == 8)
-            {
-                if (fast)
-                    e = inv ? launch_pass<T, true, false, true>(args, d->batch_size, st, i + 1)
-                            : launch_pass<T, false, false, true>(args, d->batch_size, st, i + 1);
-            }
-            if (!fast)
-            {
-                if (inv)
-                    e = rns ? launch_pass<T, true, true, false>(args, d->batch_size, st, i + 1)
-                            : launch_pass<T, true, false, false>(args, d->batch_size, st, i + 1);
-                else
-                    e = rns ? launch_pass<T, false, true, false>(args, d->batch_size, st, i + 1)
-                            : launch_pass<T, false, false, false>(args, d->batch_size, st, i + 1);
-            }
-            if (e != cudaSuccess) return cuda_fail(e, "merge_pass_kernel launch");
-        }
-        return GPUNTT_B200_OK;
+        CoreCall<T> cc;
+        cc.in = d->in;
+        cc.out = reinterpret_cast<T*>(d->out);
+        cc.table = reinterpret_cast<const T*>(d->root_of_unity_table);
+        cc.table_len = plus ? (1LL << n) : (1LL << (n - 1));
+        cc.stride_log = n; // the reference's RNS tables are spaced (1 << n_power) apart for both ring types
+        cc.n_power = n;
+        cc.batch = d->batch_size;
+        cc.mod_count = d->mod_count;
+        cc.plus = plus ? 1 : 0;
+        cc.signed_io = d->is_signed ? 1 : 0;
+        cc.inverse = inv;
+        cc.p = (T) d->modulus_value;
+        cc.ninv = (T) d->mod_inverse_value;
+        cc.mod_values = rns ? reinterpret_cast<const T*>(d->modulus_dev) : nullptr;
+        cc.ninv_dev = rns ? reinterpret_cast<const T*>(d->mod_inverse_dev) : nullptr;
+        cc.mod_order = rns ? d->modulus_order_dev : nullptr;
+        cc.poly_order = rns ? d->poly_order_dev : nullptr;
+        cc.st = st;
+        cc.ws_slot = 0;
+        const MergePlan mp = make_merge_plan(n, (int) sizeof(T) * 8);
+        cc.npasses = mp.npasses;
+        for (int i = 0; i < mp.npasses; i++) cc.pass[i] = mp.pass[inv ? (mp.npasses - 1 - i) : i];
+        return run_core<T>(cc);
     }
 
     static int merge_execute(const gpuntt_b200_merge_desc* d)
@@ -726,12 +856,21 @@ namespace gpuntt_b200
         return merge_execute_t<uint32_t>(d);
     }
 
+#include "fourstep.inl"
+
 } // namespace gpuntt_b200
 
 using namespace gpuntt_b200;
 
 extern "C"
 {
+    int gpuntt_b200_4step_ntt(const gpuntt_b200_4step_desc* desc) { return fourstep_execute(desc); }
+    int gpuntt_b200_4step_shape(int n_power, int* n1, int* n2) { return fourstep_shape(n_power, n1, n2) ? GPUNTT_B200_OK : GPUNTT_B200_ERR_N_POWER; }
+    int gpuntt_b200_transpose(int element_bits, const void* in, void* out, int row, int col, int n_power, int batch_size, void* stream)
+    {
+        return transpose_execute(element_bits, in, out, row, col, n_power, batch_size, stream);
+    }
+
     int gpuntt_b200_merge_ntt(const gpuntt_b200_merge_desc* desc) { return merge_execute(desc); }
 
     static gpuntt_b200_merge_desc simple_desc(int bits, int dir, const void* in, void* out, const void* table,

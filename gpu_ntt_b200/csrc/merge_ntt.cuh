@@ -39,6 +39,8 @@ namespace gpuntt_b200
 
     // element_bits = 32 or 64
     MergePlan make_merge_plan(int n_power, int element_bits);
+    // one strided pass over index bits [lo, lo+d) (d + column bits <= 13 / 14)
+    PassPlan make_strided_pass(int lo, int d, int element_bits);
 
     template <typename T> struct PassArgs
     {
@@ -55,6 +57,18 @@ namespace gpuntt_b200
         int plus;            // reduction polynomial X^N+1 (table index m+i) vs X^N-1 (index i)
         int signed_io;       // first forward pass: signed input; last inverse pass: centred output
         long long total_elems; // batch << n_power
+        // RNS indirection (GPU_NTT_Modulus_Ordered / GPU_NTT_Poly_Ordered of the reference): device arrays or null
+        const int* mod_order;  // modulus / table slice of polynomial b = mod_order[b % mod_count]
+        const int* poly_order; // the b-th transform lives in polynomial slot poly_order[b]
+        int batch;
+        int mod_shift;         // RNS: transform b belongs to modulus group (b >> mod_shift) % mod_count (4-step row phases)
+        int shared_tables;     // RNS: every modulus reads the same (un-offset) table (the reference's 4-step convention)
+        // 4-step twiddle matrix, plain residues (no Shoup companion): multiplied with a Barrett reduction
+        //   w_mode 1: at store, by w_table[offset in polynomial]            (forward: after the column transforms)
+        //   w_mode 2: at load,  by w_table[(offset & (2^w_lo - 1)) << w_hi | offset >> w_lo]   (inverse: transposed index)
+        const T* w_table;
+        int w_mode, w_lo, w_hi;
+        T bar_bit, bar_mu;     // single modulus: Modulus<T>::bit / mu  (RNS: read from mod_values[3*m + 1], [3*m + 2])
         PassPlan plan;
     };
 

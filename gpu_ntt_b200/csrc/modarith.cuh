@@ -188,6 +188,31 @@ namespace gpuntt_b200
         }
     };
 
+    // ------------------------------------------------------------------ plain Barrett product
+    // a * b mod p for canonical a, b with the reference's Modulus constants (bit = bit length of p,
+    // mu = floor(2^(2 bit + 1) / p), modular_arith.cuh:28-57): q = ((z >> (bit-2)) * mu) >> (bit+3) is at most
+    // 2 short of floor(z / p).  Used where a twiddle arrives without a Shoup companion (4-step W matrix).
+    __device__ __forceinline__ uint64_t barrett_mul(uint64_t a, uint64_t b, uint64_t p, uint64_t bit, uint64_t mu)
+    {
+        const uint64_t hi = __umul64hi(a, b), lo = a * b;
+        const int s1 = (int) bit - 2;
+        const uint64_t t = (lo >> s1) | (hi << (64 - s1)); // bit >= 3 here; z < 2^(2 bit) so t < 2^(bit+2)
+        const uint64_t ph = __umul64hi(t, mu), pl = t * mu;
+        const int s2 = (int) bit + 3;
+        const uint64_t q = s2 >= 64 ? (ph >> (s2 - 64)) : ((pl >> s2) | (ph << (64 - s2)));
+        uint64_t r = lo - q * p;
+        r = csub(r, p + p);
+        return csub(r, p);
+    }
+    __device__ __forceinline__ uint32_t barrett_mul(uint32_t a, uint32_t b, uint32_t p, uint32_t bit, uint32_t mu)
+    {
+        const uint64_t z = (uint64_t) a * b;
+        const uint64_t q = ((z >> (bit - 2)) * mu) >> (bit + 3);
+        uint32_t r = (uint32_t) (z - q * p);
+        r = csub(r, p + p);
+        return csub(r, p);
+    }
+
     // largest modulus the fast policy accepts: forward needs 8p + 2^33 < 2^64, inverse 10p + 2^37 < 2^64
     constexpr uint64_t kFastModulusLimit = (1ull << 60) + (1ull << 58);
 

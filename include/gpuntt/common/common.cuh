@@ -1,0 +1,51 @@
+// include/gpuntt/common/common.cuh -- error convention and small host helpers.
+// Same names and behaviour as the reference's common.cuh (src/include/gpuntt/common/common.cuh:17-56).
+#ifndef GPUNTT_B200_COMMON_CUH
+#define GPUNTT_B200_COMMON_CUH
+
+#include <cuda_runtime.h>
+
+#include <exception>
+#include <string>
+
+namespace gpuntt
+{
+    // what(): "CUDA Error in <file> at line <n>: <cudaGetErrorString>"  (common.cuh:20-40 of the reference)
+    class CudaException : public std::exception
+    {
+      public:
+        CudaException(const std::string& file, int line, cudaError_t error)
+            : text_("CUDA Error in " + file + " at line " + std::to_string(line) + ": " + cudaGetErrorString(error)), error_(error)
+        {
+        }
+        // engine-side failures arrive as text from the C ABI (gpuntt_b200_last_error)
+        CudaException(const std::string& file, int line, const std::string& message)
+            : text_("CUDA Error in " + file + " at line " + std::to_string(line) + ": " + message), error_(cudaErrorUnknown)
+        {
+        }
+        const char* what() const noexcept override { return text_.c_str(); }
+        cudaError_t code() const noexcept { return error_; }
+
+      private:
+        std::string text_;
+        cudaError_t error_;
+    };
+
+#define GPUNTT_CUDA_CHECK(err)                                                                                         \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        cudaError_t gpuntt_error_ = (err);                                                                             \
+        if (gpuntt_error_ != cudaSuccess) throw ::gpuntt::CudaException(__FILE__, __LINE__, gpuntt_error_);            \
+    } while (0)
+
+    // throws std::invalid_argument(errorMessage) when the condition is false (common.cu:5-11)
+    void customAssert(bool condition, const std::string& errorMessage);
+
+    // selects device 0 and prints its name (common.cu:13-22)
+    void CudaDevice();
+
+    // elementwise comparison; prints the first mismatch (common.cu:24-47)
+    template <typename T> bool check_result(T* input1, T* input2, int size);
+
+} // namespace gpuntt
+#endif // GPUNTT_B200_COMMON_CUH

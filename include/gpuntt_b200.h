@@ -89,10 +89,61 @@ typedef struct gpuntt_b200_merge_desc
     const void* modulus_dev;         /* RNS: device array of gpuntt_b200_modulus{32,64}       */
     const void* mod_inverse_dev;     /* RNS inverse: device array of N^-1 mod p_i (elements)  */
     void* stream;                    /* cudaStream_t                                          */
+    /* RNS indirection (GPU_NTT_Modulus_Ordered / GPU_NTT_Poly_Ordered, ntt.cu:3600-3776, 4281-4458); both may
+     * be NULL.  modulus_order_dev: device int[mod_count], polynomial b uses modulus / table slice
+     * order[b % mod_count].  poly_order_dev: device int[batch_size], the b-th transform reads and writes
+     * the polynomial slot order[b] (of `in` and of `out`) with modulus index b % mod_count.             */
+    const int* modulus_order_dev;
+    const int* poly_order_dev;
 } gpuntt_b200_merge_desc;
 
 /* Enqueue one batched Merge-NTT / INTT. Returns a gpuntt_b200_status. */
 int gpuntt_b200_merge_ntt(const gpuntt_b200_merge_desc* desc);
+
+/* One 4-step (large ring, n_power 12..24) transform.  Replaces GPU_4STEP_NTT single modulus / RNS
+ * (ntt_4step.cu:2767-3232 / 2293-2765) and ntt4step_(rns_)configuration (ntt_4step.cuh:19-33).  N = n1 * n2 with
+ * the reference's shapes (gpuntt_b200_4step_shape); tables exactly as NTTParameters4Step produces them and
+ * its examples upload them (test_4step_ntt.cu:90-110): n1_table / n2_table = bit-reversed n1/2- and
+ * n2/2-entry power tables, w_table = the natural-layout N-entry twiddle matrix (forward:
+ * W_root_of_unity_table, inverse: W_inverse_root_of_unity_table and the inverse small tables).
+ * io_contract:
+ *   GPUNTT_B200_4STEP_REFERENCE  the reference's: forward takes the n2 x n1 matrix GPU_Transpose(x, row=n1,
+ *        col=n2) made and leaves the n1 x n2 matrix R whose transpose is NTT_4STEP_CPU::ntt(x); inverse
+ *        takes NTT_4STEP_CPU::intt_first_transpose(y) and leaves the n1 x n2 matrix whose transpose is
+ *        NTT_4STEP_CPU::intt(y).  Out of place.
+ *   GPUNTT_B200_4STEP_FUSED      natural x in, NTT_4STEP_CPU::ntt(x) out / y in, NTT_4STEP_CPU::intt(y) out;
+ *        in == out allowed.
+ * RNS form (mod_count >= 1): polynomial b uses modulus_dev[b % mod_count]; like the reference's kernels all
+ * moduli index the SAME tables (ntt_4step.cu:150-229), which is only meaningful for mod_count == 1 or moduli
+ * sharing their roots.  The fused contract and every inverse use an engine-owned scratch buffer of
+ * batch_size * N elements (cached per device and stream, see gpuntt_b200_release_workspaces). */
+enum { GPUNTT_B200_4STEP_REFERENCE = 0, GPUNTT_B200_4STEP_FUSED = 1 };
+typedef struct gpuntt_b200_4step_desc
+{
+    int element_bits;   /* 32 or 64 */
+    int direction;      /* GPUNTT_B200_FORWARD / GPUNTT_B200_INVERSE (cfg.ntt_type) */
+    int n_power;        /* 12..24 */
+    int batch_size;
+    int mod_count;      /* 0: single modulus by value; >= 1: RNS form */
+    int io_contract;    /* GPUNTT_B200_4STEP_REFERENCE / GPUNTT_B200_4STEP_FUSED */
+    const void* in;     /* device, [batch][N] */
+    void* out;          /* device, [batch][N] */
+    const void* n1_table;
+    const void* n2_table;
+    const void* w_table;
+    uint64_t modulus_value;
+    uint64_t mod_inverse_value;  /* inverse: N^-1 mod p */
+    const void* modulus_dev;     /* RNS: device array of gpuntt_b200_modulus{32,64} (bit and mu ARE read here) */
+    const void* mod_inverse_dev; /* RNS inverse: device array of N^-1 mod p_i */
+    void* stream;
+} gpuntt_b200_4step_desc;
+int gpuntt_b200_4step_ntt(const gpuntt_b200_4step_desc* desc);
+/* n1, n2 of the reference's matrix_dimention() (nttparameters.cu:305-354); GPUNTT_B200_ERR_N_POWER outside 12..24 */
+int gpuntt_b200_4step_shape(int n_power, int* n1, int* n2);
+/* GPU_Transpose (ntt_4step.cu:36-66): out[x * row + y] = in[y * col + x] for each of batch_size polynomials
+ * spaced (1 << n_power) elements apart.  Unlike the reference it takes a stream. */
+int gpuntt_b200_transpose(int element_bits, const void* in, void* out, int row, int col, int n_power, int batch_size,
+                          void* stream);
 
 /* Convenience forms of the above for the four hot entry points on unsigned 64/32-bit data with
  * a single modulus (GPU_NTT / GPU_INTT, ntt.cuh:315-340; in == out gives the *_Inplace forms). */

@@ -1,0 +1,153 @@
+"""GPU parity tests of the 4-step path through the C ABI (gpuntt_b200_4step_ntt / gpuntt_b200_transpose),
+bit-exact against the oracle's restatement of NTT_4STEP_CPU (oracle/ntt_oracle.c, pinned to the reference by
+tests/golden/golden.json), mirroring the reference's gpu_4step_ntt_examples / gpu_4step_intt_examples
+(example/ntt_4step/test_4step_ntt.cu:147-166, test_4step_intt.cu:82-84,155-166)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from gpu_ntt_b200 import capi  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from tests.gpu_util import to_dev, to_host  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def tables(P, bits, inverse):
+    t1, t2, W = (P.t1_inv, P.t2_inv, P.W_inv) if inverse else (P.t1, P.t2, P.W)
+    # the examples upload bit-reversed small tables and the natural-layout W (test_4step_ntt.cu:90-110)
+    return to_dev(O.bitrev_table(t1), bits), to_dev(O.bitrev_table(t2), bits), to_dev(W, bits)
+
+
+def transposed(a, rows, cols):
+    """per-polynomial rows x cols -> cols x rows"""
+    return np.ascontiguousarray(a.reshape(-1, rows, cols).transpose(0, 2, 1)).reshape(a.shape)
+
+
+@pytest.mark.parametrize("bits", [64, 32])
+@pytest.mark.parametrize("logn,batch", [(12, 3), (13, 1), (14, 2), (15, 1), (16, 2), (17, 1), (18, 1), (20, 1)])
+def test_4step_fused_and_reference_contracts(bits, logn, batch):
+    P = O.fourstep_params(logn, O.X_N_minus, bits)
+    assert capi.fourstep_shape(logn) == (P.n1, P.n2)
+    n = P.n
+    x = O.example_input(P.modulus, batch * n, seed=logn).reshape(batch, n)
+    want = O.fourstep_ntt(x, P)
+    t1, t2, W = tables(P, bits, False)
+
+    # fused contract: natural in, NTT_4STEP_CPU::ntt order out; out of place and in place
+    d = to_dev(x, bits)
+    out = torch.zeros_like(d)
+    capi.fourstep_ntt(d.view(batch, n), t1, t2, W, P.modulus, logn, out=out.view(batch, n))
+    torch.cuda.synchronize()
+    assert (to_host(out, bits) == want).all()
+    assert (to_host(d, bits) == x).all(), "out-of-place call modified its input"
+    capi.fourstep_ntt(d.view(batch, n), t1, t2, W, P.modulus, logn)
+    torch.cuda.synchronize()
+    assert (to_host(d, bits) == want).all()
+
+    # the reference's call sequence: GPU_Transpose, GPU_4STEP_NTT, GPU_Transpose (test_4step_ntt.cu:147-154)
+    a = to_dev(x, bits)
+    tmp = torch.zeros_like(a)
+    capi.transpose(a.view(batch, n), tmp.view(batch, n), P.n1, P.n2, logn)
+    torch.cuda.synchronize()
+    assert (to_host(tmp, bits) == transposed(x, P.n1, P.n2)).all()
+    capi.fourstep_ntt(tmp.view(batch, n), t1, t2, W, P.modulus, logn, io_contract=capi.FOURSTEP_REFERENCE,
+                      out=a.view(batch, n))
+    capi.transpose(a.view(batch, n), tmp.view(batch, n), P.n1, P.n2, logn)
+    torch.cuda.synchronize()
+    assert (to_host(tmp, bits) == want).all()
+
+    # inverse, fused: NTT order in, natural out
+    it1, it2, iW = tables(P, bits, True)
+    y = to_dev(want, bits)
+    capi.fourstep_ntt(y.view(batch, n), it1, it2, iW, P.modulus, logn, direction=capi.INVERSE, mod_inverse=P.n_inv)
+    torch.cuda.synchronize()
+    assert (to_host(y, bits) == x).all()
+    z = O.example_input(P.modulus, batch * n, seed=99 + logn).reshape(batch, n)
+    winv = O.fourstep_intt(z, P)
+    zd = to_dev(z, bits)
+    zo = torch.zeros_like(zd)
+    capi.fourstep_ntt(zd.view(batch, n), it1, it2, iW, P.modulus, logn, direction=capi.INVERSE, mod_inverse=P.n_inv,
+                      out=zo.view(batch, n))
+    torch.cuda.synchronize()
+    assert (to_host(zo, bits) == winv).all()
+
+    # inverse, the reference's sequence: host intt_first_transpose, GPU_4STEP_NTT(INVERSE), GPU_Transpose
+    # (test_4step_intt.cu:82-84, 155-159)
+    pre = to_dev(O.fourstep_intt_first_transpose(z, P), bits)
+    r = torch.zeros_like(pre)
+    capi.fourstep_ntt(pre.view(batch, n), it1, it2, iW, P.modulus, logn, direction=capi.INVERSE, mod_inverse=P.n_inv,
+                      io_contract=capi.FOURSTEP_REFERENCE, out=r.view(batch, n))
+    capi.transpose(r.view(batch, n), pre.view(batch, n), P.n1, P.n2, logn)
+    torch.cuda.synchronize()
+    assert (to_host(pre, bits) == winv).all()
+
+
+def test_4step_golden_hashes(golden):
+    """Outputs hash-identical to what the reference's NTT_4STEP_CPU produced when the fixtures were made."""
+    for g in golden["fourstep"]:
+        if g["logn"] > 20:
+            continue
+        bits, logn = g["width"], g["logn"]
+        P = O.fourstep_params(logn, O.X_N_minus, bits, inverse_tables=False)
+        x = O.example_input(P.modulus, P.n)
+        assert str(O.fold_hash(x)) == g["in_hash"]
+        t1, t2, W = tables(P, bits, False)
+        d = to_dev(x, bits)
+        capi.fourstep_ntt(d.view(1, P.n), t1, t2, W, P.modulus, logn)
+        torch.cuda.synchronize()
+        y = to_host(d, bits)
+        assert [str(int(v)) for v in y[:4]] == g["ntt_head"] and str(O.fold_hash(y)) == g["ntt_hash"]
+
+
+def test_4step_rns_overload_single_modulus_group():
+    """GPU_4STEP_NTT RNS overload as the reference's example drives it: mod_count = 1 (test_4step_ntt.cu:147-154)."""
+    bits, logn, batch = 64, 14, 3
+    P = O.fourstep_params(logn, O.X_N_minus, bits)
+    x = O.example_input(P.modulus, batch * P.n, seed=3).reshape(batch, P.n)
+    want = O.fourstep_ntt(x, P)
+    t1, t2, W = tables(P, bits, False)
+    bit, mu = O.modulus(P.modulus, bits)
+    mods = to_dev(np.array([P.modulus, bit, mu], dtype=np.uint64), bits)
+    d = to_dev(x, bits)
+    capi.fourstep_ntt(d.view(batch, P.n), t1, t2, W, 0, logn, mod_count=1, modulus_dev=mods.data_ptr())
+    torch.cuda.synchronize()
+    assert (to_host(d, bits) == want).all()
+    it1, it2, iW = tables(P, bits, True)
+    ninv = to_dev(np.array([P.n_inv], dtype=np.uint64), bits)
+    capi.fourstep_ntt(d.view(batch, P.n), it1, it2, iW, 0, logn, direction=capi.INVERSE, mod_count=1,
+                      modulus_dev=mods.data_ptr(), mod_inverse_dev=ninv.data_ptr())
+    torch.cuda.synchronize()
+    assert (to_host(d, bits) == x).all()
+
+
+def test_4step_c4_full_size_properties():
+    """BASELINE config C4 (Data64, N = 2^24): the oracle needs ~4 s per polynomial, so one polynomial is checked
+    against it and the rest through size-independent properties: round trip, linearity."""
+    bits, logn, batch = 64, 24, 3
+    P = O.fourstep_params(logn, O.X_N_minus, bits)
+    p = P.modulus
+    t1, t2, W = tables(P, bits, False)
+    it1, it2, iW = tables(P, bits, True)
+    x = O.example_input(p, batch * P.n, seed=0).reshape(batch, P.n)
+    x[2] = (x[0] + x[1]) % np.uint64(p)
+    d = to_dev(x, bits)
+    capi.fourstep_ntt(d.view(batch, P.n), t1, t2, W, p, logn)
+    torch.cuda.synchronize()
+    y = to_host(d, bits).reshape(batch, P.n)
+    assert (y[0] == O.fourstep_ntt(x[0], P)).all()
+    assert O.fold_hash(y[0]) == 10069984314045308296      # SURVEY.md 8(c) KAT captured from the reference
+    assert (y[2] == (y[0] + y[1]) % np.uint64(p)).all()   # linearity
+    capi.fourstep_ntt(d.view(batch, P.n), it1, it2, iW, p, logn, direction=capi.INVERSE, mod_inverse=P.n_inv)
+    torch.cuda.synchronize()
+    assert (to_host(d, bits).reshape(batch, P.n) == x).all()
+
+
+def test_4step_errors():
+    t = torch.zeros(1 << 12, dtype=torch.int64, device="cuda")
+    with pytest.raises(capi.GpuNttError) as ei:
+        capi.fourstep_ntt(t.view(1, -1), t, t, t, 17, 11)
+    assert ei.value.status == capi.ERR_N_POWER
+    with pytest.raises(capi.GpuNttError):
+        capi.fourstep_ntt(t.view(1, -1), t, t, t, 576460752303415297, 12, io_contract=capi.FOURSTEP_REFERENCE)  # in == out

@@ -313,3 +313,81 @@ def test_fast_path_large_modulus_uses_exact_arithmetic():
     y = run_fwd(x, P, 64, O.X_N_minus)
     assert (y == O.merge_ntt(x, P)).all()
     assert (run_inv(y, P, 64, O.X_N_minus) == x).all()
+
+
+@pytest.mark.parametrize("bits", [64, 32])
+@pytest.mark.parametrize("logn,batch,mod_count", [(10, 6, 2), (12, 8, 4), (16, 5, 3)])
+def test_rns_ordered_entry_points(bits, logn, batch, mod_count):
+    """GPU_NTT_Modulus_Ordered: polynomial b uses modulus / table slice / n^-1 number order[b % mod_count]
+    (ntt.cu:3117-3118); GPU_NTT_Poly_Ordered: the b-th transform runs in polynomial slot order[b] with modulus
+    b % mod_count (ntt.cu:3796-3798)."""
+    n = 1 << logn
+    total_primes = mod_count + 2
+    primes = rns_primes(bits, logn, total_primes)
+    fwd_tab = np.zeros(total_primes << logn, dtype=np.uint64)
+    inv_tab = np.zeros(total_primes << logn, dtype=np.uint64)
+    mods = np.zeros((total_primes, 3), dtype=np.uint64)
+    ninvs = np.zeros(total_primes, dtype=np.uint64)
+    params = []
+    for m, (p, psi) in enumerate(primes):
+        fwd = np.array([pow(psi, i, p) for i in range(n)], dtype=np.uint64)
+        ipsi = pow(psi, p - 2, p)
+        inv = np.array([pow(ipsi, i, p) for i in range(n)], dtype=np.uint64)
+        fwd_tab[m << logn:(m + 1) << logn] = O.bitrev_table(fwd)
+        inv_tab[m << logn:(m + 1) << logn] = O.bitrev_table(inv)
+        bit, mu = O.modulus(p, bits)
+        mods[m] = (p, bit, mu)
+        ninvs[m] = pow(n, p - 2, p)
+        P = O.MergeParams(logn, O.X_N_plus, bits, p, 0, psi, int(ninvs[m]), psi, ipsi, n, n)
+        P.fwd, P.inv = fwd, inv
+        params.append(P)
+    rng = np.random.RandomState(11)
+    s = torch.cuda.current_stream().cuda_stream
+    mods_d, ninv_d = to_dev(mods.ravel(), bits), to_dev(ninvs, bits)
+    ftab, itab = to_dev(fwd_tab, bits), to_dev(inv_tab, bits)
+
+    def rand_poly(p):
+        return (rng.randint(0, 2**31, size=n).astype(np.uint64) * np.uint64(2**31) +
+                rng.randint(0, 2**31, size=n).astype(np.uint64)) % np.uint64(p)
+
+    # --- modulus ordered
+    order = rng.permutation(total_primes)[:mod_count].astype(np.int32)
+    x = np.stack([rand_poly(primes[order[b % mod_count]][0]) for b in range(batch)])
+    want = np.stack([O.merge_ntt(x[b], params[order[b % mod_count]]) for b in range(batch)])
+    order_d = torch.from_numpy(order).cuda()
+    d = to_dev(x, bits)
+    out = torch.zeros_like(d)
+    capi.merge_ntt(in_ptr=d.data_ptr(), out_ptr=out.data_ptr(), table_ptr=ftab.data_ptr(), n_power=logn, batch=batch,
+                   element_bits=bits, direction=capi.FORWARD, reduction_poly=O.X_N_plus, mod_count=mod_count,
+                   modulus_dev=mods_d.data_ptr(), stream=s, modulus_order_dev=order_d.data_ptr())
+    torch.cuda.synchronize()
+    assert (to_host(out, bits) == want).all()
+    capi.merge_ntt(in_ptr=out.data_ptr(), out_ptr=out.data_ptr(), table_ptr=itab.data_ptr(), n_power=logn, batch=batch,
+                   element_bits=bits, direction=capi.INVERSE, reduction_poly=O.X_N_plus, mod_count=mod_count,
+                   modulus_dev=mods_d.data_ptr(), mod_inverse_dev=ninv_d.data_ptr(), stream=s,
+                   modulus_order_dev=order_d.data_ptr())
+    torch.cuda.synchronize()
+    assert (to_host(out, bits) == x).all()
+
+    # --- poly ordered: `slots` polynomial slots, `batch` of them transformed in the order given
+    slots = batch + 3
+    porder = rng.permutation(slots)[:batch].astype(np.int32)
+    buf = np.stack([rand_poly(primes[0][0] if True else 0) for _ in range(slots)])
+    for b in range(batch):
+        buf[porder[b]] = rand_poly(primes[b % mod_count][0])
+    want = buf.copy()
+    for b in range(batch):
+        want[porder[b]] = O.merge_ntt(buf[porder[b]], params[b % mod_count])
+    porder_d = torch.from_numpy(porder).cuda()
+    d = to_dev(buf, bits)
+    capi.merge_ntt(in_ptr=d.data_ptr(), out_ptr=d.data_ptr(), table_ptr=ftab.data_ptr(), n_power=logn, batch=batch,
+                   element_bits=bits, direction=capi.FORWARD, reduction_poly=O.X_N_plus, mod_count=mod_count,
+                   modulus_dev=mods_d.data_ptr(), stream=s, poly_order_dev=porder_d.data_ptr())
+    torch.cuda.synchronize()
+    assert (to_host(d, bits).reshape(slots, n) == want).all()
+    capi.merge_ntt(in_ptr=d.data_ptr(), out_ptr=d.data_ptr(), table_ptr=itab.data_ptr(), n_power=logn, batch=batch,
+                   element_bits=bits, direction=capi.INVERSE, reduction_poly=O.X_N_plus, mod_count=mod_count,
+                   modulus_dev=mods_d.data_ptr(), mod_inverse_dev=ninv_d.data_ptr(), stream=s,
+                   poly_order_dev=porder_d.data_ptr())
+    torch.cuda.synchronize()
+    assert (to_host(d, bits).reshape(slots, n) == buf).all()
