@@ -205,10 +205,15 @@ namespace gpuntt_b200
         const int poly_shift = n - lo; // (l >> c) >> poly_shift = polynomial offset inside the tile
         const long long nmask = (1LL << n) - 1;
         // transform number b -> modulus index / polynomial slot (the *_Ordered entry points of the reference)
-        auto slice_index = [&](long long b) -> int { return (int) ((b >> a.mod_shift) % a.mod_count); };
-        auto mod_index = [&](long long b) -> int
+        // (transform number, offset in polynomial) -> twiddle slice / modulus index
+        auto slice_index = [&](long long b, long long off) -> int
         {
-            const int mi = slice_index(b);
+            if (a.col_log > 0) return (int) ((off & ((1LL << a.col_log) - 1)) % a.mod_count); // PerCoefficient: by column
+            return (int) ((b >> a.mod_shift) % a.mod_count);
+        };
+        auto mod_index = [&](long long b, long long off) -> int
+        {
+            const int mi = slice_index(b, off);
             return a.mod_order ? a.mod_order[mi] : mi;
         };
         // global element index of local element (row, col); false when the transform does not exist (ragged last tile)
@@ -238,7 +243,7 @@ namespace gpuntt_b200
             const T* w = a.w_table;
             if constexpr (RNS)
             {
-                const int mi = mod_index(b);
+                const int mi = mod_index(b, off);
                 p = a.mod_values[3 * mi];
                 bit = a.mod_values[3 * mi + 1];
                 mu = a.mod_values[3 * mi + 2];
@@ -267,8 +272,8 @@ namespace gpuntt_b200
                 else
                 {
 #pragma unroll
-                    for (int i = 0; i < VN; i++) // (c < 2 only happens for contiguous tiles, where element l+i is column col+i)
-                        v[i] = locate(row, col + i, g, off, b) ? fix_in(gin[g], b, off) : T(0);
+                    for (int i = 0; i < VN; i++)
+                        v[i] = locate((l + i) >> c, (l + i) & cmask, g, off, b) ? fix_in(gin[g], b, off) : T(0);
                 }
                 V vv;
                 memcpy(&vv, v, sizeof(V));
@@ -313,8 +318,9 @@ namespace gpuntt_b200
                 if constexpr (RNS)
                 {
                     const long long b = poly0 + (row >> poly_shift);
-                    p = a.mod_values[3 * mod_index(b)];
-                    tw += ((size_t) slice_index(b) << a.tw_stride_log);
+                    const long long off = obase + (l_base & cmask); // only its column bits matter here
+                    p = a.mod_values[3 * mod_index(b, off)];
+                    tw += ((size_t) slice_index(b, off) << a.tw_stride_log);
                 }
                 const Mod<T, FAST> M(p);
                 if (lb == 0)
@@ -356,11 +362,11 @@ namespace gpuntt_b200
                 const T* w = a.w_table;
                 if constexpr (RNS)
                 {
-                    const int mi = mod_index(b);
+                    const int mi = mod_index(b, off);
                     p = a.mod_values[3 * mi];
                     bit = a.mod_values[3 * mi + 1];
                     mu = a.mod_values[3 * mi + 2];
-                    if constexpr (INV) ni = reinterpret_cast<const Twiddle<T>*>(a.ninv_tw)[slice_index(b)];
+                    if constexpr (INV) ni = reinterpret_cast<const Twiddle<T>*>(a.ninv_tw)[slice_index(b, off)];
                     if (a.w_mode == 1 && !a.shared_tables) w += ((size_t) mi << n);
                 }
                 const Mod<T, FAST> M(p);
@@ -395,7 +401,7 @@ namespace gpuntt_b200
                 {
 #pragma unroll
                     for (int i = 0; i < VN; i++)
-                        if (locate(row, col + i, g, off, b)) gout[g] = fix_out(v[i], b, off);
+                        if (locate((l + i) >> c, (l + i) & cmask, g, off, b)) gout[g] = fix_out(v[i], b, off);
                 }
             }
         }
@@ -681,6 +687,7 @@ namespace gpuntt_b200
         const int* mod_order = nullptr;
         const int* poly_order = nullptr;
         int mod_shift = 0;
+        int col_log = 0;                   // PerCoefficient: columns of one [2^n][2^col_log] matrix
         bool unit_ninv = false;            // inverse without the final n^-1 (4-step column phase)
         const T* w_table = nullptr;
         int w_mode = 0, w_lo = 0, w_hi = 0;
@@ -750,6 +757,7 @@ namespace gpuntt_b200
         args.poly_order = cc.poly_order;
         args.batch = cc.batch;
         args.mod_shift = cc.mod_shift;
+        args.col_log = cc.col_log;
         args.shared_tables = cc.shared_tables;
         args.w_table = cc.w_table;
         args.w_mode = cc.w_mode;
@@ -792,7 +800,7 @@ namespace gpuntt_b200
         const bool rns = d->mod_count > 0;
         const bool plus = d->reduction_poly == GPUNTT_B200_X_N_PLUS;
         cudaStream_t st = (cudaStream_t) d->stream;
-        if (!rns && !d->is_signed && !g_force_generic.load())
+        if (!rns && !d->is_signed && !g_force_generic.load() && d->ntt_layout == GPUNTT_B200_PER_POLYNOMIAL)
         {
             int launched = 0;
             cudaError_t fe = fast_merge<T>(reinterpret_cast<const T*>(d->in), reinterpret_cast<T*>(d->out),
@@ -802,14 +810,21 @@ namespace gpuntt_b200
             if (fe != cudaSuccess) return cuda_fail(fe, "fast_pass_kernel launch");
             if (launched > 0) return GPUNTT_B200_OK;
         }
+        // NTTLayout::PerCoefficient (ForwardCoreTranspose / InverseCoreTranspose, ntt.cu:1554-2074): the buffer is one
+        // [2^n_power][batch] row-major matrix and every COLUMN is a transform.  That is a single strided pass over
+        // the top n_power index bits of one array of 2^(n_power + log2 batch) elements -- no transposition anywhere.
+        int col_log = 0;
+        if (d->ntt_layout == GPUNTT_B200_PER_COEFFICIENT)
+            while ((1 << col_log) < d->batch_size) col_log++;
         CoreCall<T> cc;
         cc.in = d->in;
         cc.out = reinterpret_cast<T*>(d->out);
         cc.table = reinterpret_cast<const T*>(d->root_of_unity_table);
         cc.table_len = plus ? (1LL << n) : (1LL << (n - 1));
         cc.stride_log = n; // the reference's RNS tables are spaced (1 << n_power) apart for both ring types
-        cc.n_power = n;
-        cc.batch = d->batch_size;
+        cc.n_power = n + col_log;
+        cc.batch = col_log > 0 ? 1 : d->batch_size;
+        cc.col_log = col_log;
         cc.mod_count = d->mod_count;
         cc.plus = plus ? 1 : 0;
         cc.signed_io = d->is_signed ? 1 : 0;
@@ -822,6 +837,12 @@ namespace gpuntt_b200
         cc.poly_order = rns ? d->poly_order_dev : nullptr;
         cc.st = st;
         cc.ws_slot = 0;
+        if (col_log > 0)
+        {
+            cc.npasses = 1;
+            cc.pass[0] = make_strided_pass(col_log, n, (int) sizeof(T) * 8);
+            return run_core<T>(cc);
+        }
         const MergePlan mp = make_merge_plan(n, (int) sizeof(T) * 8);
         cc.npasses = mp.npasses;
         for (int i = 0; i < mp.npasses; i++) cc.pass[i] = mp.pass[inv ? (mp.npasses - 1 - i) : i];
@@ -832,12 +853,19 @@ namespace gpuntt_b200
     {
         g_last_launches = 0;
         if (!d) return fail(GPUNTT_B200_ERR_ARGUMENT, "null descriptor");
-        if (d->ntt_layout == GPUNTT_B200_PER_COEFFICIENT)
-            return fail(GPUNTT_B200_ERR_UNSUPPORTED,
-                        "NTTLayout::PerCoefficient is not built yet (SURVEY.md 8f rank 2)");
-        if (d->ntt_layout != GPUNTT_B200_PER_POLYNOMIAL)
+        if (d->ntt_layout != GPUNTT_B200_PER_POLYNOMIAL && d->ntt_layout != GPUNTT_B200_PER_COEFFICIENT)
             return fail(GPUNTT_B200_ERR_LAYOUT, "Invalid ntt_layout!");
         if (d->n_power < 1 || d->n_power > 28) return fail(GPUNTT_B200_ERR_N_POWER, "Invalid n_power range!");
+        if (d->ntt_layout == GPUNTT_B200_PER_COEFFICIENT)
+        {
+            // the reference's limits for this layout (ntt.cu:2230-2233): n_power 1..9; its launch arithmetic also
+            // assumes a power-of-two batch (log2(batch_size), ntt.cu:2235) -- anything else is rejected here
+            if (d->n_power > 9) return fail(GPUNTT_B200_ERR_N_POWER, "Invalid n_power range!");
+            if (d->batch_size & (d->batch_size - 1))
+                return fail(GPUNTT_B200_ERR_ARGUMENT, "NTTLayout::PerCoefficient needs a power-of-two batch_size");
+            if (d->poly_order_dev || d->modulus_order_dev)
+                return fail(GPUNTT_B200_ERR_ARGUMENT, "order arrays do not apply to NTTLayout::PerCoefficient");
+        }
         if (d->element_bits != 32 && d->element_bits != 64)
             return fail(GPUNTT_B200_ERR_ARGUMENT, "element_bits must be 32 or 64");
         if (d->batch_size < 0 || d->mod_count < 0) return fail(GPUNTT_B200_ERR_ARGUMENT, "negative batch_size / mod_count");

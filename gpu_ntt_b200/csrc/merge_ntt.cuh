@@ -62,6 +62,8 @@ namespace gpuntt_b200
         const int* poly_order; // the b-th transform lives in polynomial slot poly_order[b]
         int batch;
         int mod_shift;         // RNS: transform b belongs to modulus group (b >> mod_shift) % mod_count (4-step row phases)
+        int col_log;           // NTTLayout::PerCoefficient: > 0 = the array is ONE [2^n][2^col_log] matrix transformed along
+                               // its columns; the modulus group of an element is (column % mod_count)
         int shared_tables;     // RNS: every modulus reads the same (un-offset) table (the reference's 4-step convention)
         // 4-step twiddle matrix, plain residues (no Shoup companion): multiplied with a Barrett reduction
         //   w_mode 1: at store, by w_table[offset in polynomial]            (forward: after the column transforms)

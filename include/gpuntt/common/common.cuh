@@ -5,7 +5,11 @@
 
 #include <cuda_runtime.h>
 
+#include <cassert>
+#include <cstdint>
 #include <exception>
+#include <iostream> // the reference header pulls these in and its callers rely on it (common.cuh:10-15)
+#include <stdexcept>
 #include <string>
 
 namespace gpuntt

@@ -9,9 +9,16 @@
 #ifndef GPUNTT_B200_MODULAR_ARITH_CUH
 #define GPUNTT_B200_MODULAR_ARITH_CUH
 
+#include <math.h>
+
+#include <cinttypes>
 #include <cstdint>
+#include <string>
 #include <type_traits>
+#include <vector>
+
 #include <cuda_runtime.h>
+#include <device_launch_parameters.h>
 
 // global-namespace aliases, as in the reference (modular_arith.cuh:18-26)
 typedef std::int32_t Data32s;

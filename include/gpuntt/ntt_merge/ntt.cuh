@@ -17,7 +17,9 @@
 
 #include <cuda_runtime.h>
 
+#include <functional>
 #include <type_traits>
+#include <unordered_map>
 
 #include "gpuntt/ntt_merge/ntt_cpu.cuh"
 

@@ -391,3 +391,66 @@ def test_rns_ordered_entry_points(bits, logn, batch, mod_count):
                    poly_order_dev=porder_d.data_ptr())
     torch.cuda.synchronize()
     assert (to_host(d, bits).reshape(slots, n) == buf).all()
+
+
+@pytest.mark.parametrize("bits", [64, 32])
+@pytest.mark.parametrize("poly", [O.X_N_plus, O.X_N_minus])
+@pytest.mark.parametrize("logh,w", [(9, 1024), (7, 64), (5, 2), (3, 8), (1, 4), (9, 1), (8, 16)])
+def test_per_coefficient_layout(bits, poly, logh, w):
+    """NTTLayout::PerCoefficient: the buffer is an H x W row-major matrix and every column is a transform of
+    length H = 2^n_power, batch_size = W (example/ntt_merge/test_merge_ntt.cu:343-474: compared with PerPolynomial
+    on the transposed matrix; H = 512 x W = 1024 there, H = 128 in test_merge_intt.cu)."""
+    h = 1 << logh
+    P = O.merge_params(logh, poly, bits)
+    x = O.example_input(P.modulus, h * w, seed=logh * 7 + w).reshape(h, w)
+    want = O.merge_ntt(np.ascontiguousarray(x.T), P).reshape(w, h).T      # column j of the result = NTT(column j)
+    s = torch.cuda.current_stream().cuda_stream
+    d = to_dev(x, bits)
+    tab, itab = to_dev(P.fwd_br, bits), to_dev(P.inv_br, bits)
+    capi.merge_ntt(in_ptr=d.data_ptr(), out_ptr=d.data_ptr(), table_ptr=tab.data_ptr(), n_power=logh, batch=w,
+                   element_bits=bits, direction=capi.FORWARD, reduction_poly=poly, layout=capi.PerCoefficient,
+                   modulus=P.modulus, stream=s)
+    torch.cuda.synchronize()
+    assert (to_host(d, bits).reshape(h, w) == want).all()
+    out = torch.zeros_like(d)
+    capi.merge_ntt(in_ptr=d.data_ptr(), out_ptr=out.data_ptr(), table_ptr=itab.data_ptr(), n_power=logh, batch=w,
+                   element_bits=bits, direction=capi.INVERSE, reduction_poly=poly, layout=capi.PerCoefficient,
+                   modulus=P.modulus, mod_inverse=P.n_inv, stream=s)
+    torch.cuda.synchronize()
+    assert (to_host(out, bits).reshape(h, w) == x).all()
+
+
+def test_per_coefficient_rns_and_limits():
+    """RNS PerCoefficient: column j uses modulus[j % mod_count] (ntt.cu:1737-1741); n_power > 9 is rejected like the
+    reference (ntt.cu:2230-2233)."""
+    bits, logh, w, mod_count = 64, 6, 8, 2
+    h = 1 << logh
+    primes = rns_primes(bits, logh, mod_count)
+    fwd_tab = np.zeros(mod_count << logh, dtype=np.uint64)
+    mods = np.zeros((mod_count, 3), dtype=np.uint64)
+    params = []
+    for m, (p, psi) in enumerate(primes):
+        fwd = np.array([pow(psi, i, p) for i in range(h)], dtype=np.uint64)
+        fwd_tab[m << logh:(m + 1) << logh] = O.bitrev_table(fwd)
+        bit, mu = O.modulus(p, bits)
+        mods[m] = (p, bit, mu)
+        P = O.MergeParams(logh, O.X_N_plus, bits, p, 0, psi, pow(h, p - 2, p), psi, pow(psi, p - 2, p), h, h)
+        P.fwd = fwd
+        params.append(P)
+    rng = np.random.RandomState(3)
+    x = np.zeros((h, w), dtype=np.uint64)
+    for j in range(w):
+        x[:, j] = rng.randint(0, 2**31, size=h).astype(np.uint64) % np.uint64(primes[j % mod_count][0])
+    want = np.stack([O.merge_ntt(np.ascontiguousarray(x[:, j]), params[j % mod_count]) for j in range(w)], axis=1)
+    d = to_dev(x, bits)
+    mods_d = to_dev(mods.ravel(), bits)
+    s = torch.cuda.current_stream().cuda_stream
+    capi.merge_ntt(in_ptr=d.data_ptr(), out_ptr=d.data_ptr(), table_ptr=to_dev(fwd_tab, bits).data_ptr(), n_power=logh,
+                   batch=w, element_bits=bits, direction=capi.FORWARD, reduction_poly=O.X_N_plus,
+                   layout=capi.PerCoefficient, mod_count=mod_count, modulus_dev=mods_d.data_ptr(), stream=s)
+    torch.cuda.synchronize()
+    assert (to_host(d, bits).reshape(h, w) == want).all()
+    with pytest.raises(capi.GpuNttError) as ei:
+        capi.merge_ntt(in_ptr=d.data_ptr(), out_ptr=d.data_ptr(), table_ptr=d.data_ptr(), n_power=10, batch=4,
+                       layout=capi.PerCoefficient, modulus=primes[0][0], stream=s)
+    assert ei.value.status == capi.ERR_N_POWER
