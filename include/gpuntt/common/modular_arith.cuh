@@ -127,7 +127,7 @@ namespace modular_operation_gpu
             if constexpr (std::is_same<T1, Data32>::value)
                 return reduce_wide(static_cast<Data64>(a) * b, m);
             else
-                return reduce_wide(__umul64hi(a, b), a * b, m);
+                return reduce_wide(mulhi64(a, b), a * b, m);
         }
         static __device__ __forceinline__ T1 reduce(const T1& a, const Modulus<T1>& m)
         {
@@ -164,6 +164,15 @@ namespace modular_operation_gpu
         }
 
       private:
+        // the header also has to parse as plain C++ (host-only translation units include it)
+        static __device__ __forceinline__ Data64 mulhi64(Data64 a, Data64 b)
+        {
+#ifdef __CUDA_ARCH__
+            return __umul64hi(a, b);
+#else
+            return static_cast<Data64>((static_cast<unsigned __int128>(a) * b) >> 64);
+#endif
+        }
         static __device__ __forceinline__ Data32 reduce_wide(Data64 z, const Modulus<Data32>& m)
         {
             Data64 q = ((z >> (m.bit - 2)) * m.mu) >> (m.bit + 3);
@@ -177,7 +186,7 @@ namespace modular_operation_gpu
             const int s1 = static_cast<int>(m.bit) - 2;
             const Data64 t = s1 >= 64 ? (hi >> (s1 - 64)) : (s1 == 0 ? lo : ((lo >> s1) | (hi << (64 - s1))));
             // q = (t * mu) >> (bit+3)
-            const Data64 ph = __umul64hi(t, m.mu), pl = t * m.mu;
+            const Data64 ph = mulhi64(t, m.mu), pl = t * m.mu;
             const int s2 = static_cast<int>(m.bit) + 3;
             const Data64 q = s2 >= 64 ? (ph >> (s2 - 64)) : ((pl >> s2) | (ph << (64 - s2)));
             Data64 r = lo - q * m.value;
