@@ -951,6 +951,44 @@ extern "C"
         return merge_execute(&d);
     }
 
+    // Host-buffer pipeline: the batch is cut into chunks of whole polynomials; chunk i's H2D copy, transform and D2H
+    // copy run on three engine-owned streams chained by events, so the two DMA directions and the kernels overlap
+    // (PCIe is full duplex).  Ordered after everything already enqueued on the caller's stream; synchronises it.
+    struct HostPipe
+    {
+        cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+        cudaEvent_t start = nullptr, done = nullptr;
+        std::vector<cudaEvent_t> ev_in, ev_cmp;
+    };
+    static std::mutex g_pipe_mutex;
+    static std::map<int, HostPipe> g_pipes; // per device
+
+    static cudaError_t get_pipe(int nchunks, HostPipe** out)
+    {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        HostPipe& hp = g_pipes[dev];
+        if (!hp.s_in)
+        {
+            if ((e = cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking)) != cudaSuccess) return e;
+            if ((e = cudaStreamCreateWithFlags(&hp.s_cmp, cudaStreamNonBlocking)) != cudaSuccess) return e;
+            if ((e = cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&hp.start, cudaEventDisableTiming)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&hp.done, cudaEventDisableTiming)) != cudaSuccess) return e;
+        }
+        while ((int) hp.ev_in.size() < nchunks)
+        {
+            cudaEvent_t a, b;
+            if ((e = cudaEventCreateWithFlags(&a, cudaEventDisableTiming)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&b, cudaEventDisableTiming)) != cudaSuccess) return e;
+            hp.ev_in.push_back(a);
+            hp.ev_cmp.push_back(b);
+        }
+        *out = &hp;
+        return cudaSuccess;
+    }
+
     int gpuntt_b200_merge_ntt_host(const gpuntt_b200_merge_desc* hd, const void* host_root_table,
                                    size_t root_table_elems)
     {
@@ -960,27 +998,65 @@ extern "C"
         if (hd->n_power < 1 || hd->n_power > 28) return fail(GPUNTT_B200_ERR_N_POWER, "Invalid n_power range!");
         if (hd->element_bits != 32 && hd->element_bits != 64)
             return fail(GPUNTT_B200_ERR_ARGUMENT, "element_bits must be 32 or 64");
+        if (hd->batch_size < 0) return fail(GPUNTT_B200_ERR_ARGUMENT, "negative batch_size");
         const size_t esz = hd->element_bits / 8;
-        const size_t data_bytes = ((size_t) hd->batch_size << hd->n_power) * esz;
+        const size_t poly_bytes = ((size_t) 1 << hd->n_power) * esz;
+        const size_t data_bytes = (size_t) hd->batch_size * poly_bytes;
         const size_t table_bytes = root_table_elems * esz;
         cudaStream_t st = (cudaStream_t) hd->stream;
+        // chunks of ~32 MiB, whole polynomials; PerCoefficient interleaves the batch, so it stays one chunk
+        int chunk_polys = hd->batch_size;
+        if (hd->ntt_layout == GPUNTT_B200_PER_POLYNOMIAL && hd->batch_size > 1)
+        {
+            const size_t target = (size_t) 32 << 20;
+            size_t cp = poly_bytes >= target ? 1 : target / poly_bytes;
+            if (cp < (size_t) hd->batch_size) chunk_polys = (int) cp;
+        }
+        const int nchunks = hd->batch_size == 0 ? 0 : (hd->batch_size + chunk_polys - 1) / chunk_polys;
+        std::lock_guard<std::mutex> lk(g_pipe_mutex);
+        HostPipe* hp = nullptr;
+        cudaError_t e = get_pipe(nchunks, &hp);
+        if (e != cudaSuccess) return cuda_fail(e, "host pipeline streams");
         void *dbuf = nullptr, *dtab = nullptr;
-        cudaError_t e = get_workspace(hd->stream, 1, data_bytes, &dbuf);
+        e = get_workspace((void*) hp->s_cmp, 1, data_bytes, &dbuf);
         if (e != cudaSuccess) return cuda_fail(e, "staging allocation");
-        e = get_workspace(hd->stream, 2, table_bytes, &dtab);
+        e = get_workspace((void*) hp->s_cmp, 2, table_bytes, &dtab);
         if (e != cudaSuccess) return cuda_fail(e, "staging allocation");
-        e = cudaMemcpyAsync(dtab, host_root_table, table_bytes, cudaMemcpyHostToDevice, st);
+        if ((e = cudaEventRecord(hp->start, st)) != cudaSuccess) return cuda_fail(e, "event record");
+        cudaStreamWaitEvent(hp->s_in, hp->start, 0);
+        cudaStreamWaitEvent(hp->s_cmp, hp->start, 0);
+        cudaStreamWaitEvent(hp->s_out, hp->start, 0);
+        e = cudaMemcpyAsync(dtab, host_root_table, table_bytes, cudaMemcpyHostToDevice, hp->s_in);
         if (e != cudaSuccess) return cuda_fail(e, "table H2D");
-        e = cudaMemcpyAsync(dbuf, hd->in, data_bytes, cudaMemcpyHostToDevice, st);
-        if (e != cudaSuccess) return cuda_fail(e, "data H2D");
-        gpuntt_b200_merge_desc d = *hd;
-        d.in = dbuf;
-        d.out = dbuf;
-        d.root_of_unity_table = dtab;
-        int rc = merge_execute(&d);
-        if (rc != GPUNTT_B200_OK) return rc;
-        e = cudaMemcpyAsync(hd->out, dbuf, data_bytes, cudaMemcpyDeviceToHost, st);
-        if (e != cudaSuccess) return cuda_fail(e, "data D2H");
+        int launches = 0;
+        for (int c = 0; c < nchunks; c++)
+        {
+            const int b0 = c * chunk_polys;
+            const int nb = (b0 + chunk_polys <= hd->batch_size) ? chunk_polys : hd->batch_size - b0;
+            unsigned char* dchunk = static_cast<unsigned char*>(dbuf) + (size_t) b0 * poly_bytes;
+            e = cudaMemcpyAsync(dchunk, static_cast<const unsigned char*>(hd->in) + (size_t) b0 * poly_bytes,
+                                (size_t) nb * poly_bytes, cudaMemcpyHostToDevice, hp->s_in);
+            if (e != cudaSuccess) return cuda_fail(e, "data H2D");
+            cudaEventRecord(hp->ev_in[c], hp->s_in);
+            cudaStreamWaitEvent(hp->s_cmp, hp->ev_in[c], 0);
+            gpuntt_b200_merge_desc d = *hd;
+            d.in = dchunk;
+            d.out = dchunk;
+            d.batch_size = nb;
+            d.root_of_unity_table = dtab;
+            d.stream = (void*) hp->s_cmp;
+            int rc = merge_execute(&d);
+            if (rc != GPUNTT_B200_OK) return rc;
+            launches += g_last_launches;
+            cudaEventRecord(hp->ev_cmp[c], hp->s_cmp);
+            cudaStreamWaitEvent(hp->s_out, hp->ev_cmp[c], 0);
+            e = cudaMemcpyAsync(static_cast<unsigned char*>(hd->out) + (size_t) b0 * poly_bytes, dchunk,
+                                (size_t) nb * poly_bytes, cudaMemcpyDeviceToHost, hp->s_out);
+            if (e != cudaSuccess) return cuda_fail(e, "data D2H");
+        }
+        g_last_launches = launches;
+        cudaEventRecord(hp->done, hp->s_out);
+        cudaStreamWaitEvent(st, hp->done, 0);
         e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) return cuda_fail(e, "stream synchronize");
         return GPUNTT_B200_OK;

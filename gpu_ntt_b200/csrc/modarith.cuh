@@ -96,9 +96,9 @@ namespace gpuntt_b200
     template <> struct Mod<uint64_t, true>
     {
         using T = uint64_t;
-        T p, four_p, six_p;
+        T p, four_p, six_p, neg_four_p;
         uint32_t n0, n1, f0, f1; // -p mod 2^64 ; 4p
-        __device__ __forceinline__ explicit Mod(T p_) : p(p_), four_p(4 * p_), six_p(6 * p_)
+        __device__ __forceinline__ explicit Mod(T p_) : p(p_), four_p(4 * p_), six_p(6 * p_), neg_four_p(0 - 4 * p_)
         {
             const T np = 0 - p_;
             n0 = (uint32_t) np;
@@ -107,8 +107,12 @@ namespace gpuntt_b200
             f1 = (uint32_t) (four_p >> 32);
         }
 
-        // r = w*y - q~*p in [0,4p) for ANY 64-bit y;  q~ = a1*y1 + hi32(a1*y0) + hi32(a0*y1) in {Q-2..Q}.
-        // 3 IMAD.WIDE + 2 IMAD.HI + 4 IMAD; the only additions are the carry of the two cross terms.
+        // r = w*y - q~*p in [0,3p) for ANY 64-bit y;  q~ = a1*y1 + floor((a1*y0 + a0*y1) / 2^32) in {Q-1, Q}
+        // (only the a0*y0 partial product of the quotient is dropped).  4 IMAD.WIDE + 1 IMAD.HI + 4 IMAD on the
+        // multiplier pipe = 28 issue cycles per warp; the formulation is what ptxas turns into exactly that with
+        // NO extra IMAD.X / IMAD.MOV / IMAD.IADD (see tools/bfly_lab.cu): the cross terms are a 64-bit
+        // multiply-add with carry-out, the high word of r is an IMAD chain that starts from the high word of
+        // q0*n0 + w0*y0, so the product needs two additions in total (q += cross terms).
         __device__ __forceinline__ T mul(T y, const Twiddle<T>& tw) const
         {
             const uint32_t y0 = (uint32_t) y, y1 = (uint32_t) (y >> 32);
@@ -116,24 +120,24 @@ namespace gpuntt_b200
             const uint32_t a0 = (uint32_t) tw.wq, a1 = (uint32_t) (tw.wq >> 32);
             uint32_t r0, r1;
             asm("{\n\t"
-                ".reg .u32 q0, q1, u, h1, h2, z;\n\t"
-                ".reg .u64 q, A, B, H;\n\t"
-                "mul.hi.u32 h1, %6, %2;\n\t"      // hi(a1*y0)
-                "mul.hi.u32 h2, %7, %3;\n\t"      // hi(a0*y1)
-                "mov.u32 z, 0;\n\t"
-                "add.cc.u32 h1, h1, h2;\n\t"
-                "addc.u32 h2, z, z;\n\t"
-                "mov.b64 H, {h1, h2};\n\t"
-                "mad.wide.u32 q, %6, %3, H;\n\t"  // a1*y1 + cross terms
+                ".reg .u32 q0, q1, c0, c1, d0, d1;\n\t"
+                ".reg .u64 q, A, B, C;\n\t"
+                "mul.wide.u32 C, %6, %2;\n\t"        // a1*y0
+                "mov.b64 {c0, c1}, C;\n\t"
+                "mul.wide.u32 q, %6, %3;\n\t"        // a1*y1
                 "mov.b64 {q0, q1}, q;\n\t"
-                "mul.wide.u32 A, %4, %2;\n\t"     // w0*y0
-                "mul.lo.u32 u, %5, %2;\n\t"       // w1*y0
-                "mad.lo.u32 u, %4, %3, u;\n\t"    // w0*y1
-                "mad.lo.u32 u, q1, %8, u;\n\t"    // q1*n0
-                "mad.lo.u32 u, q0, %9, u;\n\t"    // q0*n1
-                "mad.wide.u32 B, q0, %8, A;\n\t"  // q0*n0 + w0*y0
+                "mad.lo.cc.u32 d0, %7, %3, c0;\n\t"  // a0*y1 + a1*y0 (64-bit, carry out)
+                "madc.hi.cc.u32 d1, %7, %3, c1;\n\t"
+                "addc.u32 q1, q1, 0;\n\t"
+                "add.cc.u32 q0, q0, d1;\n\t"
+                "addc.u32 q1, q1, 0;\n\t"
+                "mul.wide.u32 A, %4, %2;\n\t"        // w0*y0
+                "mad.wide.u32 B, q0, %8, A;\n\t"     // q0*n0 + w0*y0
                 "mov.b64 {%0, %1}, B;\n\t"
-                "add.u32 %1, %1, u;\n\t"
+                "mad.lo.u32 %1, %5, %2, %1;\n\t"     // + w1*y0
+                "mad.lo.u32 %1, %4, %3, %1;\n\t"     // + w0*y1
+                "mad.lo.u32 %1, q1, %8, %1;\n\t"     // + q1*n0
+                "mad.lo.u32 %1, q0, %9, %1;\n\t"     // + q0*n1
                 "}"
                 : "=r"(r0), "=r"(r1)
                 : "r"(y0), "r"(y1), "r"(w0), "r"(w1), "r"(a1), "r"(a0), "r"(n0), "r"(n1));
@@ -153,13 +157,19 @@ namespace gpuntt_b200
                 : "r"(f0), "r"(f1));
             return ((T) x1 << 32) | x0;
         }
-        // Forward values live in [0, 8p + 2^32).
+        // Forward values live in [0, 8p + 2^32).  x = X - 4p when hi32(X) > hi32(4p); X' = x + t, Y' = x - t + 4p are
+        // written as three-operand 64-bit sums (X + g + t, X + k - t with g = -4p or 0, k = 0 or 4p): ptxas then
+        // emits IADD3 / IADD3.X pairs on the alu pipe and cannot move the carry additions onto the multiplier pipe.
         __device__ __forceinline__ void ct(T& X, T& Y, const Twiddle<T>& tw) const
         {
-            const T x = csub_hi(X);
             const T t = mul(Y, tw);
-            X = x + t;
-            Y = x - t + four_p;
+            uint32_t xh;
+            asm("{\n\t.reg .u32 lo;\n\tmov.b64 {lo, %0}, %1;\n\t}" : "=r"(xh) : "l"(X)); // opaque: keeps a 32-bit compare
+            const bool P = xh > f1;
+            const T g = P ? neg_four_p : T(0), k = P ? T(0) : four_p;
+            const T Xn = X + g + t;
+            Y = X + k - t;
+            X = Xn;
         }
         // butterfly with twiddle 1 (first stages of X^N-1 transforms): no multiply, Y only range-reduced
         __device__ __forceinline__ void ct_one(T& X, T& Y) const

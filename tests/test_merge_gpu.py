@@ -258,6 +258,21 @@ def test_host_buffer_entry_point():
     assert capi.lib().gpuntt_b200_last_launch_count() >= 2
 
 
+def test_host_buffer_entry_point_chunked_pipeline():
+    """Same entry point at a size that is cut into several chunks (64 polynomials of 2^16 each) with a ragged
+    last chunk: H2D / transform / D2H of different chunks overlap on the engine's three streams."""
+    import ctypes as C
+    logn, batch = 16, 150
+    P = O.merge_params(logn, O.X_N_minus, 64)
+    x = O.example_input(P.modulus, batch << logn, seed=21)
+    out = np.zeros_like(x)
+    d = capi.MergeDesc(64, 0, capi.FORWARD, logn, capi.PerPolynomial, O.X_N_minus, batch, 0,
+                       x.ctypes.data, out.ctypes.data, None, P.modulus, 0, None, None, None)
+    capi.check(capi.lib().gpuntt_b200_merge_ntt_host(C.byref(d), P.fwd_br.ctypes.data, P.fwd_br.size))
+    assert (out == O.merge_ntt(x, P)).all()
+    assert capi.lib().gpuntt_b200_last_launch_count() == 6      # 3 chunks x 2 passes
+
+
 def test_streams_and_no_sync():
     """Calls only enqueue on cfg.stream: two streams, two different transforms, results both right."""
     P = O.merge_params(13, O.X_N_minus, 64)

@@ -1,0 +1,126 @@
+#!/usr/bin/env python
+"""Device-time of the BASELINE.json configurations other than the bench.py headline (C3, C4) and a sweep over ring
+sizes, through the C ABI, CUDA events, data resident in HBM.  Timing only (parity is tests/ -m gpu): the 4-step
+tables are random residues, the merge tables come from NTTParameters.  One JSON object per line.
+
+    python tools/perf_configs.py [--quick]
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from gpu_ntt_b200 import capi  # noqa: E402
+from gpu_ntt_b200.params import NTTParameters, X_N_minus, X_N_plus  # noqa: E402
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def time_ms(fn, iters, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def dev(a, bits):
+    if bits == 64:
+        return torch.from_numpy(np.ascontiguousarray(a).astype(np.uint64).view(np.int64)).cuda()
+    return torch.from_numpy(np.ascontiguousarray(a).astype(np.uint32).view(np.int32)).cuda()
+
+
+def merge_case(name, logn, batch, bits, poly, iters, inverse=False, both=False):
+    P = NTTParameters(logn, poly, bits)
+    p = P.modulus
+    tab = dev(P.gpu_root_of_unity_table_generator(P.forward_root_of_unity_table), bits)
+    itab = dev(P.gpu_root_of_unity_table_generator(P.inverse_root_of_unity_table), bits)
+    dt = torch.int64 if bits == 64 else torch.int32
+    x = torch.randint(0, p, (batch, 1 << logn), dtype=dt, device="cuda")
+
+    def fwd():
+        capi.ntt(x, tab, p, logn, poly)
+
+    def inv():
+        capi.intt(x, itab, p, P.n_inv, logn, poly)
+
+    def rt():
+        fwd()
+        inv()
+    fn = rt if both else (inv if inverse else fwd)
+    ms = time_ms(fn, iters)
+    ntts = batch * (2 if both else 1)
+    bytes_alg = 2 * (1 << logn) * (bits // 8) * ntts
+    gbs = bytes_alg / (ms * 1e-3) / 1e9
+    out = {"case": name, "logn": logn, "batch": batch, "bits": bits, "ring": "X^N-1" if poly == X_N_minus else "X^N+1",
+           "op": "fwd+inv" if both else ("inv" if inverse else "fwd"), "ms": round(ms, 4),
+           "ntt_per_s": round(ntts / (ms * 1e-3), 1), "alg_GBps": round(gbs, 1), "frac_hbm": round(gbs / peak(), 4),
+           "plan": capi.describe_plan(logn, bits).strip()}
+    print(json.dumps(out), flush=True)
+    del x
+    torch.cuda.empty_cache()
+
+
+def fourstep_case(name, logn, batch, iters, contract):
+    n1, n2 = capi.fourstep_shape(logn)
+    p = 576460753175838721 if logn == 24 else 576460752303415297
+    rng = np.random.default_rng(1)
+    t1 = dev(rng.integers(1, p, n1 // 2, dtype=np.uint64), 64)
+    t2 = dev(rng.integers(1, p, n2 // 2, dtype=np.uint64), 64)
+    t2[0] = 1
+    t1[0] = 1
+    w = torch.randint(0, p, (1 << logn,), dtype=torch.int64, device="cuda")
+    x = torch.randint(0, p, (batch, 1 << logn), dtype=torch.int64, device="cuda")
+    out = torch.empty_like(x) if contract == capi.FOURSTEP_REFERENCE else None
+
+    def fn():
+        capi.fourstep_ntt(x, t1, t2, w, p, logn, io_contract=contract, out=out)
+    ms = time_ms(fn, iters, warm=2)
+    bytes_alg = 2 * (1 << logn) * 8 * batch
+    gbs = bytes_alg / (ms * 1e-3) / 1e9
+    print(json.dumps({"case": name, "logn": logn, "batch": batch, "bits": 64, "n1": n1, "n2": n2,
+                      "contract": "fused" if contract == capi.FOURSTEP_FUSED else "reference", "ms": round(ms, 4),
+                      "ntt_per_s": round(batch / (ms * 1e-3), 2), "alg_GBps": round(gbs, 1),
+                      "frac_hbm": round(gbs / peak(), 4)}), flush=True)
+    del x, w, out
+    torch.cuda.empty_cache()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    it = 5 if args.quick else 20
+    capi.lib()
+    merge_case("C2 fwd", 16, 1024, 64, X_N_minus, it)
+    merge_case("C2 inv", 16, 1024, 64, X_N_minus, it, inverse=True)
+    merge_case("C2 negacyclic fwd", 16, 1024, 64, X_N_plus, it)
+    merge_case("C3 fwd+inv", 14, 4096, 32, X_N_minus, it, both=True)
+    merge_case("C3 fwd", 14, 4096, 32, X_N_minus, it)
+    fourstep_case("C4 4-step fused", 24, 16, max(2, it // 4), capi.FOURSTEP_FUSED)
+    fourstep_case("C4 4-step reference contract", 24, 16, max(2, it // 4), capi.FOURSTEP_REFERENCE)
+    if not args.quick:
+        for logn in (12, 13, 14, 15, 17, 18, 20):
+            merge_case(f"u64 logN={logn}", logn, max(1, (1 << 26) >> logn), 64, X_N_minus, it)
+        for logn in (12, 16):
+            merge_case(f"u32 logN={logn}", logn, max(1, (1 << 27) >> logn), 32, X_N_minus, it)
+
+
+if __name__ == "__main__":
+    main()
