@@ -99,10 +99,13 @@ namespace gpuntt_b200
     // STRIDED: tile = 2^D rows (row stride 2^lo elements) x 2^C adjacent columns, K = D + C.
     // !STRIDED: tile = 2^NPLOG polynomials x 2^KC adjacent elements of the same ring range.
     // Two register rounds: R1 stages on the high bits, R2 on the low bits (D = R1 + R2).
-    template <typename T_, bool INV_, bool FAST_, bool STRIDED_, int R1_, int R2_, int K_, int NPLOG_> struct Shape
+    // POL: arithmetic policy -- 0 exact (any modulus the reference accepts), 1 fast lazy (inverse), 2 F60 (forward).
+    template <typename T_, bool INV_, int POL_, bool STRIDED_, int R1_, int R2_, int K_, int NPLOG_> struct Shape
     {
         using T = T_;
-        static constexpr bool INV = INV_, FAST = FAST_, STRIDED = STRIDED_;
+        static constexpr int POL = POL_;
+        static constexpr bool INV = INV_, FAST = POL_ != 0, STRIDED = STRIDED_;
+        static_assert(POL_ == 0 || (POL_ == 1 && INV_) || (POL_ == 2 && !INV_), "policy 1 is inverse-only, policy 2 forward-only");
         static constexpr int R1 = R1_, R2 = R2_, K = K_, NPLOG = NPLOG_;
         static constexpr int D = R1 + R2;
         static constexpr int C = STRIDED ? (K - D) : 0;
@@ -120,12 +123,27 @@ namespace gpuntt_b200
         static_assert(LB1 >= CB, "high round must start on a row boundary");
     };
 
+    template <typename S> struct ModOf
+    {
+        using type = Mod<typename S::T, false>;
+    };
+    template <bool INV_, bool STRIDED_, int R1_, int R2_, int K_, int NPLOG_> struct ModOf<Shape<uint64_t, INV_, 1, STRIDED_, R1_, R2_, K_, NPLOG_>>
+    {
+        using type = Mod<uint64_t, true>;
+    };
+    template <bool INV_, bool STRIDED_, int R1_, int R2_, int K_, int NPLOG_> struct ModOf<Shape<uint64_t, INV_, 2, STRIDED_, R1_, R2_, K_, NPLOG_>>
+    {
+        using type = ModF60;
+    };
+
     template <typename T> struct FastArgs
     {
         const T* in;
         T* out;
         const T* table; // the caller's bit-reversed root table (w only)
         T p, ninv_w, ninv_wq;
+        T mu;      // floor(2^(63 + pbits) / p): companions without a division (shoup_companion_mu)
+        int pbits; // bit length of p
         int n, lo, plus, first, last, batch;
         long long work; // total tiles of this pass
     };
@@ -142,7 +160,7 @@ namespace gpuntt_b200
     // so those butterflies skip the multiply (15 of the 32 butterflies of a radix-16 round).
     template <typename S, int R, int LB, int G, bool FINAL, bool TRIV = false>
     __device__ __forceinline__ void fast_round(unsigned char* buf, const Twiddle<typename S::T>* __restrict__ tws,
-                                               const Mod<typename S::T, S::FAST>& M, int ctid,
+                                               const typename ModOf<S>::type& M, int ctid,
                                                const Twiddle<typename S::T>& ninv)
     {
         using T = typename S::T;
@@ -209,21 +227,38 @@ namespace gpuntt_b200
 #pragma unroll
                     for (int x = 0; x < (E >> (ab + 1)); x++)
                     {
-                        if constexpr (TRIV && S::FAST)
+                        if constexpr (S::POL == 2)
                         {
-                            if (x == 0)
+                            // first round of a cyclic transform, canonical inputs: before stage it the values are below
+                            // {1, 2, 6, 12}[it] * p, the twiddle-1 butterflies of stages 0..2 are bare add/subtract
+                            if (TRIV && it < 3 && x == 0)
                             {
+                                const T K = (it == 0 ? 1 : it == 1 ? 2 : 6) * M.p;
 #pragma unroll
-                                for (int y = 0; y < (1 << ab); y++) M.ct_one(e[y], e[y | (1 << ab)]);
+                                for (int y = 0; y < (1 << ab); y++) M.add_sub(e[y], e[y | (1 << ab)], K);
                                 continue;
                             }
-                        }
-                        const Twiddle<T> w = tg[((E >> (ab + 1)) - 1 + x) * G];
+                            const Twiddle<T> w = tg[((E >> (ab + 1)) - 1 + x) * G];
+                            const bool kindB = (ab % 2 == 0) && !(TRIV && it < 3);
 #pragma unroll
-                        for (int y = 0; y < (1 << ab); y++)
+                            for (int y = 0; y < (1 << ab); y++)
+                            {
+                                const int a0 = (x << (ab + 1)) | y;
+                                if (kindB)
+                                    M.ctB(e[a0], e[a0 | (1 << ab)], w);
+                                else
+                                    M.ctA(e[a0], e[a0 | (1 << ab)], w);
+                            }
+                        }
+                        else
                         {
-                            const int a0 = (x << (ab + 1)) | y;
-                            M.ct(e[a0], e[a0 | (1 << ab)], w);
+                            const Twiddle<T> w = tg[((E >> (ab + 1)) - 1 + x) * G];
+#pragma unroll
+                            for (int y = 0; y < (1 << ab); y++)
+                            {
+                                const int a0 = (x << (ab + 1)) | y;
+                                M.ct(e[a0], e[a0 | (1 << ab)], w);
+                            }
                         }
                     }
                 }
@@ -314,11 +349,11 @@ namespace gpuntt_b200
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             fence_async();
         }
-        const Mod<T, S::FAST> M(a.p);
+        const typename ModOf<S>::type M(a.p);
         const Twiddle<T> ninv{a.ninv_w, a.ninv_wq};
         // first pass of a cyclic transform: slot 0 of every stage of the high round is table[0]; when that is 1
         // (it is omega^0 in the reference's tables) those butterflies need no multiply
-        const bool triv = S::STRIDED && !S::INV && !a.plus && a.first && (a.lo + S::D == a.n) && a.table[0] == T(1);
+        const bool triv = S::STRIDED && !S::INV && !a.plus && a.first && (a.lo + S::D == a.n) && a.table[0] == T(1); // inputs canonical by contract
         uint32_t uses0 = 0, uses1 = 0; // how often each buffer has been filled so far (phase tracking)
 
         long long w = w_begin;
@@ -353,7 +388,10 @@ namespace gpuntt_b200
                     const int J = j0 | (group << (LB + R - S::C));
                     const long long idx = ((long long) a.plus << s) + (J >> (rb0 + ab + 1)) + x;
                     const T wv = a.table[idx];
-                    (hi ? tw1 : tw2)[ii] = Twiddle<T>{wv, shoup_companion(wv, a.p)};
+                    if constexpr (sizeof(T) == 8)
+                        (hi ? tw1 : tw2)[ii] = Twiddle<T>{wv, shoup_companion_mu(wv, a.p, a.mu, a.pbits)};
+                    else
+                        (hi ? tw1 : tw2)[ii] = Twiddle<T>{wv, shoup_companion(wv, a.p)};
                 }
             }
             __syncthreads();
@@ -427,7 +465,7 @@ namespace gpuntt_b200
                     mbar_wait(smem_u32(&bars[b]), k & 1); // tile landed
                     if constexpr (!S::INV)
                     {
-                        if constexpr (S::STRIDED && S::FAST && S::G1 == 1)
+                        if constexpr (S::STRIDED && S::POL == 2 && S::G1 == 1)
                         {
                             if (triv)
                                 fast_round<S, S::R1, S::LB1, S::G1, false, true>(buf, tw1, M, tid, ninv);
@@ -569,26 +607,34 @@ namespace gpuntt_b200
         if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return cudaSuccess;
         if constexpr (sizeof(T) == 8)
         {
-            const bool fast_arith = (uint64_t) p < kFastModulusLimit;
+            // forward: F60 policy for 2^40 <= p < 2^60 - 2^31, else exact; inverse: lazy fast policy or exact
+            const bool f60 = (uint64_t) p >= kF60ModulusMin && (uint64_t) p < kF60ModulusLimit;
+            const bool fast_inv = (uint64_t) p >= kFastModulusMin && (uint64_t) p < kFastModulusLimit;
+            const bool fast_arith = inverse ? fast_inv : f60;
             FastArgs<T> a{};
             a.table = table;
             a.p = p;
             a.ninv_w = ninv;
             a.ninv_wq = inverse ? shoup_companion(ninv, p) : 0;
+            a.pbits = 64 - __builtin_clzll((unsigned long long) p);
+            {
+                const unsigned __int128 m = (((unsigned __int128) 1) << (63 + a.pbits)) / (unsigned __int128) p;
+                a.mu = (m >> 64) ? ~0ull : (uint64_t) m;
+            }
             a.n = n_power;
             a.plus = plus;
             a.batch = batch;
             cudaError_t e = cudaSuccess;
             // n = 16: strided pass (8 stages, 256 rows x 16 columns) + contiguous pass (8 stages,
             // 2 polynomials x 2048 adjacent elements)
-            using Sf = Shape<T, false, true, true, 4, 4, 12, 0>;
-            using Cf = Shape<T, false, true, false, 4, 4, 12, 1>;
-            using Si = Shape<T, true, true, true, 4, 4, 12, 0>;
-            using Ci = Shape<T, true, true, false, 4, 4, 12, 1>;
-            using Sfx = Shape<T, false, false, true, 4, 4, 12, 0>;
-            using Cfx = Shape<T, false, false, false, 4, 4, 12, 1>;
-            using Six = Shape<T, true, false, true, 4, 4, 12, 0>;
-            using Cix = Shape<T, true, false, false, 4, 4, 12, 1>;
+            using Sf = Shape<T, false, 2, true, 4, 4, 12, 0>;
+            using Cf = Shape<T, false, 2, false, 4, 4, 12, 1>;
+            using Si = Shape<T, true, 1, true, 4, 4, 12, 0>;
+            using Ci = Shape<T, true, 1, false, 4, 4, 12, 1>;
+            using Sfx = Shape<T, false, 0, true, 4, 4, 12, 0>;
+            using Cfx = Shape<T, false, 0, false, 4, 4, 12, 1>;
+            using Six = Shape<T, true, 0, true, 4, 4, 12, 0>;
+            using Cix = Shape<T, true, 0, false, 4, 4, 12, 1>;
             const int d2 = 8;
             auto strided_args = [&](bool first, bool last)
             {

@@ -198,6 +198,86 @@ namespace gpuntt_b200
         }
     };
 
+    // ------------------------------------------------------------------ "F60" forward policy (u64, 2^40 <= p < 2^60 - 2^31)
+    // What bounds the 64-bit butterfly on B200 is not one pipe but three things at once -- multiplier-pipe cycles,
+    // alu-pipe cycles and register-file operand reads (tools/pipe_probes2.cu: an IMAD and an IADD3 with distinct
+    // registers co-issue at 3.3 cycles per pair, not 2) -- so the forward path also trims the alu side:
+    //   * values live in [0, 12p + 2^32) at round boundaries and the range correction (subtract 8p when the HIGH
+    //     WORD exceeds hi32(8p)) runs on every OTHER stage only: stage kind A adds at most 4p (16p + 2^32 < 2^64),
+    //     kind B brings the X input back under 8p + 2^32 first;
+    //   * the first round of a cyclic transform sees canonical inputs, so its twiddle-1 butterflies are a bare
+    //     add / subtract with a constant multiple of p and nothing else (add_sub);
+    //   * the final correction is one Barrett step from the top 32 bits (q~ in {q-1, q}) and one conditional
+    //     subtraction instead of four.
+    struct ModF60 : Mod<uint64_t, true>
+    {
+        T neg_eight_p;
+        uint32_t e1;     // hi32(8p)
+        uint32_t red_m;  // floor(2^59 / ((p >> red_sh) + 1))
+        int red_sh;      // bit length of p - 28
+        __device__ __forceinline__ explicit ModF60(T p_) : Mod<uint64_t, true>(p_), neg_eight_p(0 - 8 * p_)
+        {
+            e1 = (uint32_t) ((8 * p_) >> 32);
+            red_sh = (64 - __clzll((long long) p_)) - 28;
+            const uint32_t pt = (uint32_t) (p_ >> red_sh) + 1u;
+            red_m = (uint32_t) ((1ull << 59) / pt);
+        }
+        // kind A: no correction.  In: X < 12p + 2^32, any Y.  Out: < 16p + 2^32.
+        __device__ __forceinline__ void ctA(T& X, T& Y, const Twiddle<T>& tw) const
+        {
+            const T t = mul(Y, tw);
+            Y = X + four_p - t;
+            X = X + t;
+        }
+        // kind B: x = X - 8p when hi32(X) > hi32(8p).  In: X < 16p + 2^32.  Out: < 12p + 2^32.
+        __device__ __forceinline__ void ctB(T& X, T& Y, const Twiddle<T>& tw) const
+        {
+            const T t = mul(Y, tw);
+            uint32_t xh;
+            asm("{\n\t.reg .u32 lo;\n\tmov.b64 {lo, %0}, %1;\n\t}" : "=r"(xh) : "l"(X)); // opaque: keeps a 32-bit compare
+            const bool P = xh > e1;
+            const T g = P ? neg_eight_p : T(0), k = P ? neg_four_p : four_p;
+            const T Xn = X + g + t;
+            Y = X + k - t;
+            X = Xn;
+        }
+        // twiddle-1 butterfly on values below K (K a multiple of p): X' = X + Y, Y' = X - Y + K, both below 2K
+        __device__ __forceinline__ void add_sub(T& X, T& Y, T K) const
+        {
+            const T s = X + Y;
+            Y = X + K - Y;
+            X = s;
+        }
+        // [0, 13p) -> [0, p)
+        __device__ __forceinline__ T canon_fwd(T x) const
+        {
+            const uint32_t xt = __funnelshift_rc((uint32_t) x, (uint32_t) (x >> 32), red_sh);
+            const uint32_t q = __umulhi(xt, red_m) >> 27;
+            T r = (T) q * n0 + x;                 // x - q*p, low word
+            r += (T) (q * n1) << 32;
+            return csub(r, p);
+        }
+    };
+    constexpr uint64_t kF60ModulusMin = 1ull << 40;
+    constexpr uint64_t kF60ModulusLimit = (1ull << 60) - (1ull << 31);
+
+    // companion w' = floor(w * 2^64 / p) without a 128-bit division: mu = floor(2^(63 + bits) / p) (host-computed,
+    // bits = bit length of p), estimate (w * mu) >> (bits - 1) is at most 3 short and is corrected against
+    // w * 2^64 - q * p = -(q * p) mod 2^64.
+    __device__ __forceinline__ uint64_t shoup_companion_mu(uint64_t w, uint64_t p, uint64_t mu, int bits)
+    {
+        const uint64_t hi = __umul64hi(w, mu), lo = w * mu;
+        const int s = bits - 1;
+        uint64_t q = (hi << (64 - s)) | (lo >> s);
+        uint64_t r = 0 - q * p;
+        while (r >= p)
+        {
+            r -= p;
+            q++;
+        }
+        return q;
+    }
+
     // ------------------------------------------------------------------ plain Barrett product
     // a * b mod p for canonical a, b with the reference's Modulus constants (bit = bit length of p,
     // mu = floor(2^(2 bit + 1) / p), modular_arith.cuh:28-57): q = ((z >> (bit-2)) * mu) >> (bit+3) is at most
@@ -225,5 +305,8 @@ namespace gpuntt_b200
 
     // largest modulus the fast policy accepts: forward needs 8p + 2^33 < 2^64, inverse 10p + 2^37 < 2^64
     constexpr uint64_t kFastModulusLimit = (1ull << 60) + (1ull << 58);
+    // ... and the smallest: the high-word range tests leave up to 2^32 of slack, which the final correction (at most
+    // 11p) only absorbs when 2^32 is small against p
+    constexpr uint64_t kFastModulusMin = 1ull << 36;
 
 } // namespace gpuntt_b200
