@@ -7,7 +7,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libgpuntt_b200.so")
+LIB_PATH = os.environ.get("GPUNTT_B200_LIB") or os.path.join(HERE, "lib", "libgpuntt_b200.so")  # override: A/B builds
 
 # enum values == the reference's (nttparameters.cuh:19-36)
 FORWARD, INVERSE = 0, 1

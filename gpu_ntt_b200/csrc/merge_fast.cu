@@ -31,6 +31,15 @@
 namespace gpuntt_b200
 {
 
+#ifndef GPUNTT_FAST_P0_BLOCKS
+#define GPUNTT_FAST_P0_BLOCKS 2 // CTAs per SM of the forward strided pass (3 fits at 72 registers but measured 4% slower)
+#endif
+#ifndef GPUNTT_FAST_P1_BLOCKS
+#define GPUNTT_FAST_P1_BLOCKS 2 // CTAs per SM of the forward contiguous pass
+#endif
+#ifndef GPUNTT_FAST_P1_NPLOG
+#define GPUNTT_FAST_P1_NPLOG 1  // log2 polynomials per tile of the forward contiguous pass
+#endif
     constexpr int kConsumers = 256;
     constexpr int kFastThreads = kConsumers + 32;
 
@@ -317,7 +326,7 @@ namespace gpuntt_b200
     //   !STRIDED:  w = range * tiles_per_range + polynomial group (range-major, so a CTA's
     //              contiguous share of the work stays inside one or two ranges)
     template <typename S>
-    __global__ void __launch_bounds__(kFastThreads, 2)
+    __global__ void __launch_bounds__(kFastThreads, (!S::INV && S::POL == 2) ? (S::STRIDED ? GPUNTT_FAST_P0_BLOCKS : GPUNTT_FAST_P1_BLOCKS) : 2)
         fast_pass_kernel(const FastArgs<typename S::T> a, const __grid_constant__ CUtensorMap map_in,
                          const __grid_constant__ CUtensorMap map_out)
     {
@@ -628,7 +637,7 @@ namespace gpuntt_b200
             // n = 16: strided pass (8 stages, 256 rows x 16 columns) + contiguous pass (8 stages,
             // 2 polynomials x 2048 adjacent elements)
             using Sf = Shape<T, false, 2, true, 4, 4, 12, 0>;
-            using Cf = Shape<T, false, 2, false, 4, 4, 12, 1>;
+            using Cf = Shape<T, false, 2, false, 4, 4, 12, GPUNTT_FAST_P1_NPLOG>;
             using Si = Shape<T, true, 1, true, 4, 4, 12, 0>;
             using Ci = Shape<T, true, 1, false, 4, 4, 12, 1>;
             using Sfx = Shape<T, false, 0, true, 4, 4, 12, 0>;
