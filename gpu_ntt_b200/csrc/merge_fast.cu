@@ -342,7 +342,10 @@ namespace gpuntt_b200
         const int n = a.n;
         const long long w_begin = a.work * blockIdx.x / gridDim.x;
         const long long w_end = a.work * (blockIdx.x + 1) / gridDim.x;
-        const int tiles_per_range = S::STRIDED ? 1 : ((a.batch + (1 << S::NPLOG) - 1) >> S::NPLOG);
+        // tiles that share one twiddle set ("range" = the index bits above this pass's stage window):
+        //   STRIDED: every polynomial x every column chunk of one 2^D-row block;  else: every polynomial group
+        const long long tiles_per_range =
+            S::STRIDED ? ((long long) a.batch << (a.lo - S::C)) : (long long) ((a.batch + (1 << S::NPLOG) - 1) >> S::NPLOG);
 
         if (tid == kConsumers)
         {
@@ -371,7 +374,6 @@ namespace gpuntt_b200
             // ---- segment: a run of tiles sharing one twiddle set
             long long seg_end = w_end;
             int range = 0;
-            if constexpr (!S::STRIDED)
             {
                 range = (int) (w / tiles_per_range);
                 const long long re = (long long) (range + 1) * tiles_per_range;
@@ -382,7 +384,7 @@ namespace gpuntt_b200
             __syncthreads(); // everybody is done with the previous segment's twiddles and buffers
             {
                 // (w, w') pairs for both rounds, slot-major: entry (slot, group) at slot*G + group
-                const int j0 = S::STRIDED ? 0 : (range << S::KC); // index (>> lo) of the tile's first row
+                const int j0 = S::STRIDED ? (range << S::D) : (range << S::KC); // index (>> lo) of the tile's first row
                 for (int i = tid; i < S::TW1 + S::TW2; i += kFastThreads)
                 {
                     const bool hi = i < S::TW1;
@@ -420,8 +422,10 @@ namespace gpuntt_b200
                         if constexpr (S::STRIDED)
                         {
                             const int ccb = a.lo - S::C;
-                            const long long poly = ww >> ccb, cc = ww & ((1LL << ccb) - 1);
-                            tma_load_2d(dst, &map_in, (int) (cc << S::C), (int) (poly << S::D), bar);
+                            const long long within = ww % tiles_per_range;
+                            const long long poly = within >> ccb, cc = within & ((1LL << ccb) - 1);
+                            tma_load_3d(dst, &map_in, 0, (int) (cc << (S::C - S::CB)),
+                                        (int) ((poly << (a.n - a.lo)) + ((long long) range << S::D)), bar);
                         }
                         else
                         {
@@ -445,8 +449,10 @@ namespace gpuntt_b200
                         if constexpr (S::STRIDED)
                         {
                             const int ccb = a.lo - S::C;
-                            const long long poly = ww >> ccb, cc = ww & ((1LL << ccb) - 1);
-                            tma_store_2d(&map_out, (int) (cc << S::C), (int) (poly << S::D), src);
+                            const long long within = ww % tiles_per_range;
+                            const long long poly = within >> ccb, cc = within & ((1LL << ccb) - 1);
+                            tma_store_3d(&map_out, 0, (int) (cc << (S::C - S::CB)),
+                                         (int) ((poly << (a.n - a.lo)) + ((long long) range << S::D)), src);
                         }
                         else
                         {
@@ -472,29 +478,40 @@ namespace gpuntt_b200
                     const uint32_t k = b ? uses1 : uses0;
                     unsigned char* buf = bufs + b * S::TILE_SMEM;
                     mbar_wait(smem_u32(&bars[b]), k & 1); // tile landed
+                    // In this path the contiguous pass is always the LAST forward / FIRST inverse pass, so only it
+                    // canonicalises forward and only a strided pass (the top one) applies n^-1 on the inverse.
                     if constexpr (!S::INV)
                     {
+                        constexpr bool FIN1 = !S::STRIDED && S::R2 == 0, FIN2 = !S::STRIDED;
                         if constexpr (S::STRIDED && S::POL == 2 && S::G1 == 1)
                         {
                             if (triv)
-                                fast_round<S, S::R1, S::LB1, S::G1, false, true>(buf, tw1, M, tid, ninv);
+                                fast_round<S, S::R1, S::LB1, S::G1, FIN1, true>(buf, tw1, M, tid, ninv);
                             else
-                                fast_round<S, S::R1, S::LB1, S::G1, false>(buf, tw1, M, tid, ninv);
+                                fast_round<S, S::R1, S::LB1, S::G1, FIN1>(buf, tw1, M, tid, ninv);
                         }
                         else
-                            fast_round<S, S::R1, S::LB1, S::G1, false>(buf, tw1, M, tid, ninv);
-                        consumer_sync();
-                        if (a.last)
-                            fast_round<S, S::R2, S::LB2, S::G2, true>(buf, tw2, M, tid, ninv);
-                        else
-                            fast_round<S, S::R2, S::LB2, S::G2, false>(buf, tw2, M, tid, ninv);
+                            fast_round<S, S::R1, S::LB1, S::G1, FIN1>(buf, tw1, M, tid, ninv);
+                        if constexpr (S::R2 > 0)
+                        {
+                            consumer_sync();
+                            fast_round<S, S::R2, S::LB2, S::G2, FIN2>(buf, tw2, M, tid, ninv);
+                        }
                     }
                     else
                     {
-                        fast_round<S, S::R2, S::LB2, S::G2, false>(buf, tw2, M, tid, ninv);
-                        consumer_sync();
-                        if (a.last)
-                            fast_round<S, S::R1, S::LB1, S::G1, true>(buf, tw1, M, tid, ninv);
+                        if constexpr (S::R2 > 0)
+                        {
+                            fast_round<S, S::R2, S::LB2, S::G2, false>(buf, tw2, M, tid, ninv);
+                            consumer_sync();
+                        }
+                        if constexpr (S::STRIDED)
+                        {
+                            if (a.last)
+                                fast_round<S, S::R1, S::LB1, S::G1, true>(buf, tw1, M, tid, ninv);
+                            else
+                                fast_round<S, S::R1, S::LB1, S::G1, false>(buf, tw1, M, tid, ninv);
+                        }
                         else
                             fast_round<S, S::R1, S::LB1, S::G1, false>(buf, tw1, M, tid, ninv);
                     }
@@ -543,12 +560,16 @@ namespace gpuntt_b200
         int rank;
         if constexpr (S::STRIDED)
         {
-            rank = 2;
-            gdim[0] = 1ull << lo;
-            gdim[1] = (cuuint64_t) batch << (n - lo);
-            gstride[0] = (cuuint64_t) sizeof(T) << lo;
-            box[0] = 1u << S::C;
-            box[1] = 1u << S::D;
+            // {one 128-byte row, column blocks of a matrix row, all matrix rows of all polynomials}
+            rank = 3;
+            gdim[0] = 1ull << S::CB;
+            gdim[1] = 1ull << (lo - S::CB);
+            gdim[2] = (cuuint64_t) batch << (n - lo);
+            gstride[0] = 128;
+            gstride[1] = (cuuint64_t) sizeof(T) << lo;
+            box[0] = 1u << S::CB;
+            box[1] = 1u << (S::C - S::CB);
+            box[2] = 1u << S::D;
         }
         else
         {
@@ -597,11 +618,58 @@ namespace gpuntt_b200
         return cudaGetLastError();
     }
 
-    // which (n_power, element width) the fast path covers: two passes of two rounds each
+    // which (n_power, element width) the fast path covers.  64-bit: the last forward pass is the contiguous
+    // 8-stage pass, the n - 8 stages above it are one (n <= 16) or two (n <= 24) strided passes of 4..8 stages.
     bool fast_supported(int n_power, int element_bits)
     {
-        if (element_bits == 64) return n_power == 16;
+        if (element_bits == 64) return n_power >= 12 && n_power <= 24;
         return false;
+    }
+
+    struct FastPlan
+    {
+        int npass = 0;     // forward order
+        int d[3] = {0, 0, 0}, lo[3] = {0, 0, 0};
+        bool strided[3] = {false, false, false};
+    };
+    static FastPlan make_fast_plan(int n)
+    {
+        FastPlan pl;
+        const int dc = 8, rest = n - dc;
+        if (rest <= 8)
+        {
+            pl.npass = 2;
+            pl.d[0] = rest;
+            pl.lo[0] = dc;
+            pl.strided[0] = true;
+        }
+        else
+        {
+            pl.npass = 3;
+            pl.d[0] = (rest + 1) / 2;
+            pl.lo[0] = n - pl.d[0];
+            pl.strided[0] = true;
+            pl.d[1] = rest - pl.d[0];
+            pl.lo[1] = dc;
+            pl.strided[1] = true;
+        }
+        pl.d[pl.npass - 1] = dc;
+        pl.lo[pl.npass - 1] = 0;
+        return pl;
+    }
+
+    // strided pass of D stages: rounds (D, 0) up to 4 stages, else (ceil(D/2), floor(D/2))
+    template <typename T, bool INV, int POL> static cudaError_t launch_strided(int d, const FastArgs<T>& args, cudaStream_t st)
+    {
+        switch (d)
+        {
+            case 4: return launch_fast<Shape<T, INV, POL, true, 4, 0, 12, 0>>(args, st);
+            case 5: return launch_fast<Shape<T, INV, POL, true, 3, 2, 12, 0>>(args, st);
+            case 6: return launch_fast<Shape<T, INV, POL, true, 3, 3, 12, 0>>(args, st);
+            case 7: return launch_fast<Shape<T, INV, POL, true, 4, 3, 12, 0>>(args, st);
+            case 8: return launch_fast<Shape<T, INV, POL, true, 4, 4, 12, 0>>(args, st);
+            default: return cudaErrorNotSupported;
+        }
     }
 
     // Returns cudaSuccess and sets *launched to the number of kernels, or *launched = 0 if this
@@ -616,10 +684,13 @@ namespace gpuntt_b200
         if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return cudaSuccess;
         if constexpr (sizeof(T) == 8)
         {
-            // forward: F60 policy for 2^40 <= p < 2^60 - 2^31, else exact; inverse: lazy fast policy or exact
+            // forward: F60 policy for 2^40 <= p < 2^60 - 2^31; inverse: the lazy policy, whose high-word range test
+            // lets the slack above 4p double per stage (2^(31 + stages)), so it needs 2^(32 + n) <= p.  Other moduli:
+            // exact-policy kernels exist for n = 16 only, everything else goes to the generic pass kernel.
             const bool f60 = (uint64_t) p >= kF60ModulusMin && (uint64_t) p < kF60ModulusLimit;
-            const bool fast_inv = (uint64_t) p >= kFastModulusMin && (uint64_t) p < kFastModulusLimit;
+            const bool fast_inv = (uint64_t) p >= kFastModulusMin && (uint64_t) p < kFastModulusLimit && ((uint64_t) p >> (32 + n_power)) != 0;
             const bool fast_arith = inverse ? fast_inv : f60;
+            if (!fast_arith && n_power != 16) return cudaSuccess;
             FastArgs<T> a{};
             a.table = table;
             a.p = p;
@@ -633,65 +704,46 @@ namespace gpuntt_b200
             a.n = n_power;
             a.plus = plus;
             a.batch = batch;
-            cudaError_t e = cudaSuccess;
-            // n = 16: strided pass (8 stages, 256 rows x 16 columns) + contiguous pass (8 stages,
-            // 2 polynomials x 2048 adjacent elements)
-            using Sf = Shape<T, false, 2, true, 4, 4, 12, 0>;
             using Cf = Shape<T, false, 2, false, 4, 4, 12, GPUNTT_FAST_P1_NPLOG>;
-            using Si = Shape<T, true, 1, true, 4, 4, 12, 0>;
             using Ci = Shape<T, true, 1, false, 4, 4, 12, 1>;
-            using Sfx = Shape<T, false, 0, true, 4, 4, 12, 0>;
             using Cfx = Shape<T, false, 0, false, 4, 4, 12, 1>;
-            using Six = Shape<T, true, 0, true, 4, 4, 12, 0>;
             using Cix = Shape<T, true, 0, false, 4, 4, 12, 1>;
-            const int d2 = 8;
-            auto strided_args = [&](bool first, bool last)
+            const FastPlan pl = make_fast_plan(n_power);
+            for (int k = 0; k < pl.npass; k++)
             {
+                const int i = inverse ? pl.npass - 1 - k : k; // pass of the forward plan executed k-th
                 FastArgs<T> s = a;
-                s.in = first ? in : out;
+                s.in = (k == 0) ? in : out;
                 s.out = out;
-                s.lo = d2;
-                s.first = first;
-                s.last = last;
-                s.work = (long long) batch << (d2 - Sf::C);
-                return s;
-            };
-            auto contig_args = [&](bool first, bool last)
-            {
-                FastArgs<T> s = a;
-                s.in = first ? in : out;
-                s.out = out;
-                s.lo = 0;
-                s.first = first;
-                s.last = last;
-                const long long tpr = (batch + (1 << Cf::NPLOG) - 1) >> Cf::NPLOG;
-                s.work = tpr << (n_power - Cf::KC);
-                return s;
-            };
-            if (!inverse)
-            {
-                prof_begin(1, st);
-                e = fast_arith ? launch_fast<Sf>(strided_args(true, false), st) : launch_fast<Sfx>(strided_args(true, false), st);
+                s.lo = pl.lo[i];
+                s.first = (k == 0);
+                s.last = (k == pl.npass - 1);
+                cudaError_t e;
+                prof_begin(k + 1, st);
+                if (pl.strided[i])
+                {
+                    const int c = 12 - pl.d[i];
+                    s.work = ((long long) batch << (pl.lo[i] - c)) << (n_power - pl.lo[i] - pl.d[i]);
+                    if (fast_arith)
+                        e = inverse ? launch_strided<T, true, 1>(pl.d[i], s, st) : launch_strided<T, false, 2>(pl.d[i], s, st);
+                    else
+                        e = inverse ? launch_strided<T, true, 0>(8, s, st) : launch_strided<T, false, 0>(8, s, st);
+                }
+                else
+                {
+                    const int nplog = (!inverse && fast_arith) ? Cf::NPLOG : 1;
+                    const long long tpr = (batch + (1 << nplog) - 1) >> nplog;
+                    s.work = tpr << (n_power - (12 - nplog));
+                    if (fast_arith)
+                        e = inverse ? launch_fast<Ci>(s, st) : launch_fast<Cf>(s, st);
+                    else
+                        e = inverse ? launch_fast<Cix>(s, st) : launch_fast<Cfx>(s, st);
+                }
                 prof_end(st);
-                if (e == cudaErrorNotSupported) return cudaSuccess; // no tensor maps: generic path
+                if (e == cudaErrorNotSupported && k == 0) return cudaSuccess; // no tensor maps: generic path
                 if (e != cudaSuccess) return e;
-                prof_begin(2, st);
-                e = fast_arith ? launch_fast<Cf>(contig_args(false, true), st) : launch_fast<Cfx>(contig_args(false, true), st);
-                prof_end(st);
             }
-            else
-            {
-                prof_begin(1, st);
-                e = fast_arith ? launch_fast<Ci>(contig_args(true, false), st) : launch_fast<Cix>(contig_args(true, false), st);
-                prof_end(st);
-                if (e == cudaErrorNotSupported) return cudaSuccess;
-                if (e != cudaSuccess) return e;
-                prof_begin(2, st);
-                e = fast_arith ? launch_fast<Si>(strided_args(false, true), st) : launch_fast<Six>(strided_args(false, true), st);
-                prof_end(st);
-            }
-            if (e != cudaSuccess) return e;
-            *launched = 2;
+            *launched = pl.npass;
         }
         return cudaSuccess;
     }

@@ -765,7 +765,8 @@ namespace gpuntt_b200
         args.w_hi = cc.w_hi;
         if (!rns) barrett_constants<T>(cc.p, args.bar_bit, args.bar_mu);
         bool fast = false;
-        if constexpr (sizeof(T) == 8) fast = !rns && (uint64_t) cc.p >= kFastModulusMin && (uint64_t) cc.p < kFastModulusLimit;
+        if constexpr (sizeof(T) == 8) fast = !rns && (uint64_t) cc.p >= kFastModulusMin && (uint64_t) cc.p < kFastModulusLimit &&
+                                         (!cc.inverse || (((uint64_t) cc.p >> 32) >> cc.n_power) != 0); // inverse slack doubles per stage
         for (int i = 0; i < cc.npasses; i++)
         {
             args.plan = cc.pass[i];

@@ -65,6 +65,20 @@ def test_large_rings(bits, logn):
     assert (run_inv(want, P, bits, O.X_N_minus) == x).all()
 
 
+@pytest.mark.parametrize("logn,batch,poly", [(18, 3, O.X_N_plus), (19, 2, O.X_N_minus), (21, 2, O.X_N_plus),
+                                             (22, 1, O.X_N_minus), (24, 1, O.X_N_plus), (24, 2, O.X_N_minus)])
+def test_large_rings_tuned_three_pass_plans(logn, batch, poly):
+    """64-bit rings of 2^17..2^24 take the tuned kernels as two strided passes + the contiguous pass (ranges of
+    twiddles per block of matrix rows); several polynomials per call, both ring types, in place and out of place."""
+    P = O.merge_params(logn, poly, 64)
+    x = O.example_input(P.modulus, batch << logn, seed=logn)
+    want = O.merge_ntt(x, P)
+    assert (run_fwd(x, P, 64, poly) == want).all()
+    assert (run_fwd(x, P, 64, poly, inplace=False) == want).all()
+    assert (run_inv(want, P, 64, poly) == x).all()
+    assert (run_inv(want, P, 64, poly, inplace=False) == x).all()
+
+
 def test_golden_vectors_through_c_abi(golden):
     """Outputs on the example drivers' seed-0 input equal the hashes recorded from the reference."""
     for g in golden["merge"]:
