@@ -151,7 +151,7 @@ namespace gpuntt_b200
         T* out;
         const T* table; // the caller's bit-reversed root table (w only)
         T p, ninv_w, ninv_wq;
-        T mu;      // floor(2^(63 + pbits) / p): companions without a division (shoup_companion_mu)
+        uint64_t mu; // 64-bit: floor(2^(63 + pbits) / p), 32-bit: floor(2^64 / p) -- companions without a division
         int pbits; // bit length of p
         int n, lo, plus, first, last, batch;
         long long work; // total tiles of this pass
@@ -402,7 +402,7 @@ namespace gpuntt_b200
                     if constexpr (sizeof(T) == 8)
                         (hi ? tw1 : tw2)[ii] = Twiddle<T>{wv, shoup_companion_mu(wv, a.p, a.mu, a.pbits)};
                     else
-                        (hi ? tw1 : tw2)[ii] = Twiddle<T>{wv, shoup_companion(wv, a.p)};
+                        (hi ? tw1 : tw2)[ii] = Twiddle<T>{wv, shoup_companion_mu32(wv, a.p, a.mu)};
                 }
             }
             __syncthreads();
@@ -620,10 +620,11 @@ namespace gpuntt_b200
 
     // which (n_power, element width) the fast path covers.  64-bit: the last forward pass is the contiguous
     // 8-stage pass, the n - 8 stages above it are one (n <= 16) or two (n <= 24) strided passes of 4..8 stages.
+    // 32-bit: contiguous 10-stage pass (two radix-32 rounds on 8192-element tiles), strided passes of 3..8 stages.
     bool fast_supported(int n_power, int element_bits)
     {
         if (element_bits == 64) return n_power >= 12 && n_power <= 24;
-        return false;
+        return n_power >= 13 && n_power <= 26;
     }
 
     struct FastPlan
@@ -632,10 +633,10 @@ namespace gpuntt_b200
         int d[3] = {0, 0, 0}, lo[3] = {0, 0, 0};
         bool strided[3] = {false, false, false};
     };
-    static FastPlan make_fast_plan(int n)
+    static FastPlan make_fast_plan(int n, int element_bits)
     {
         FastPlan pl;
-        const int dc = 8, rest = n - dc;
+        const int dc = element_bits == 64 ? 8 : 10, rest = n - dc;
         if (rest <= 8)
         {
             pl.npass = 2;
@@ -658,7 +659,33 @@ namespace gpuntt_b200
         return pl;
     }
 
+    // text form of the tuned plan for gpuntt_b200_describe_plan; returns the number of launches (0: not covered)
+    int fast_describe(int n_power, int element_bits, char* buf, size_t len)
+    {
+        if (!fast_supported(n_power, element_bits)) return 0;
+        const FastPlan pl = make_fast_plan(n_power, element_bits);
+        size_t off = 0;
+        for (int i = 0; i < pl.npass && off < len; i++)
+            off += (size_t) snprintf(buf + off, len - off, "pass%d{tile=2^%d %s lo=%d stages=%d TMA persistent} ", i, element_bits == 64 ? 12 : 13,
+                                     pl.strided[i] ? "strided" : "contiguous", pl.lo[i], pl.d[i]);
+        return pl.npass;
+    }
+
     // strided pass of D stages: rounds (D, 0) up to 4 stages, else (ceil(D/2), floor(D/2))
+    template <bool INV> static cudaError_t launch_strided32(int d, const FastArgs<uint32_t>& args, cudaStream_t st)
+    {
+        using T = uint32_t;
+        switch (d)
+        {
+            case 3: return launch_fast<Shape<T, INV, 0, true, 3, 0, 13, 0>>(args, st);
+            case 4: return launch_fast<Shape<T, INV, 0, true, 4, 0, 13, 0>>(args, st);
+            case 5: return launch_fast<Shape<T, INV, 0, true, 5, 0, 13, 0>>(args, st);
+            case 6: return launch_fast<Shape<T, INV, 0, true, 3, 3, 13, 0>>(args, st);
+            case 7: return launch_fast<Shape<T, INV, 0, true, 4, 3, 13, 0>>(args, st);
+            case 8: return launch_fast<Shape<T, INV, 0, true, 4, 4, 13, 0>>(args, st);
+            default: return cudaErrorNotSupported;
+        }
+    }
     template <typename T, bool INV, int POL> static cudaError_t launch_strided(int d, const FastArgs<T>& args, cudaStream_t st)
     {
         switch (d)
@@ -708,7 +735,7 @@ namespace gpuntt_b200
             using Ci = Shape<T, true, 1, false, 4, 4, 12, 1>;
             using Cfx = Shape<T, false, 0, false, 4, 4, 12, 1>;
             using Cix = Shape<T, true, 0, false, 4, 4, 12, 1>;
-            const FastPlan pl = make_fast_plan(n_power);
+            const FastPlan pl = make_fast_plan(n_power, 64);
             for (int k = 0; k < pl.npass; k++)
             {
                 const int i = inverse ? pl.npass - 1 - k : k; // pass of the forward plan executed k-th
@@ -741,6 +768,52 @@ namespace gpuntt_b200
                 }
                 prof_end(st);
                 if (e == cudaErrorNotSupported && k == 0) return cudaSuccess; // no tensor maps: generic path
+                if (e != cudaSuccess) return e;
+            }
+            *launched = pl.npass;
+        }
+        else
+        {
+            // 32-bit: exact Harvey butterflies ([0,4p) forward, [0,2p) inverse; p < 2^30 like the reference)
+            if ((uint32_t) p >= (1u << 30) || (uint32_t) p < 3) return cudaSuccess;
+            FastArgs<T> a{};
+            a.table = table;
+            a.p = p;
+            a.ninv_w = ninv;
+            a.ninv_wq = inverse ? shoup_companion(ninv, p) : 0;
+            a.pbits = 32 - __builtin_clz((unsigned) p);
+            a.mu = ~0ull / (uint64_t) p; // floor((2^64 - 1) / p) = floor(2^64 / p) unless p divides 2^64 (p is odd here)
+            a.n = n_power;
+            a.plus = plus;
+            a.batch = batch;
+            using Cf = Shape<T, false, 0, false, 5, 5, 13, 1>;
+            using Ci = Shape<T, true, 0, false, 5, 5, 13, 1>;
+            const FastPlan pl = make_fast_plan(n_power, 32);
+            for (int k = 0; k < pl.npass; k++)
+            {
+                const int i = inverse ? pl.npass - 1 - k : k;
+                FastArgs<T> s = a;
+                s.in = (k == 0) ? in : out;
+                s.out = out;
+                s.lo = pl.lo[i];
+                s.first = (k == 0);
+                s.last = (k == pl.npass - 1);
+                cudaError_t e;
+                prof_begin(k + 1, st);
+                if (pl.strided[i])
+                {
+                    const int c = 13 - pl.d[i];
+                    s.work = ((long long) batch << (pl.lo[i] - c)) << (n_power - pl.lo[i] - pl.d[i]);
+                    e = inverse ? launch_strided32<true>(pl.d[i], s, st) : launch_strided32<false>(pl.d[i], s, st);
+                }
+                else
+                {
+                    const long long tpr = (batch + 1) >> 1;
+                    s.work = tpr << (n_power - 12);
+                    e = inverse ? launch_fast<Ci>(s, st) : launch_fast<Cf>(s, st);
+                }
+                prof_end(st);
+                if (e == cudaErrorNotSupported && k == 0) return cudaSuccess;
                 if (e != cudaSuccess) return e;
             }
             *launched = pl.npass;

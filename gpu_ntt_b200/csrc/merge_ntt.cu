@@ -589,6 +589,7 @@ namespace gpuntt_b200
     }
 
     // merge_fast.cu
+    int fast_describe(int n_power, int element_bits, char* buf, size_t len);
     template <typename T>
     cudaError_t fast_merge(const T* in, T* out, const T* table, T p, T ninv, int n_power, int plus, bool inverse,
                            int batch, cudaStream_t st, int* launched, void (*prof_begin)(int, cudaStream_t),
@@ -1086,6 +1087,16 @@ extern "C"
         MergePlan mp = make_merge_plan(n_power, element_bits);
         std::string s;
         char tmp[256];
+        {
+            // single-modulus unsigned PerPolynomial calls with a modulus in the lazy-policy range take the tuned kernels
+            char fb[512];
+            const int nf = fast_describe(n_power, element_bits, fb, sizeof(fb));
+            if (nf > 0)
+            {
+                s = std::string("tuned: ") + fb + "| generic: ";
+                if (buf && buf_len) snprintf(buf, buf_len, "%s", s.c_str());
+            }
+        }
         for (int i = 0; i < mp.npasses; i++)
         {
             const PassPlan& p = mp.pass[i];

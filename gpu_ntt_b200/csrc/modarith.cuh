@@ -278,6 +278,19 @@ namespace gpuntt_b200
         return q;
     }
 
+    // 32-bit companion floor(w * 2^32 / p) from mu = floor(2^64 / p): (w * mu) >> 32 is at most 2 short
+    __device__ __forceinline__ uint32_t shoup_companion_mu32(uint32_t w, uint32_t p, uint64_t mu)
+    {
+        uint64_t q = (uint64_t) w * (uint32_t) (mu >> 32) + (((uint64_t) w * (uint32_t) mu) >> 32);
+        uint64_t r = ((uint64_t) w << 32) - q * p;
+        while (r >= p)
+        {
+            r -= p;
+            q++;
+        }
+        return (uint32_t) q;
+    }
+
     // ------------------------------------------------------------------ plain Barrett product
     // a * b mod p for canonical a, b with the reference's Modulus constants (bit = bit length of p,
     // mu = floor(2^(2 bit + 1) / p), modular_arith.cuh:28-57): q = ((z >> (bit-2)) * mu) >> (bit+3) is at most
