@@ -175,6 +175,24 @@ template <typename T> static int fourstep_execute_t(const gpuntt_b200_4step_desc
             if (e != cudaSuccess) return cuda_fail(e, "transpose_kernel launch");
             src = out;
         }
+        bool columns_done = false;
+        if constexpr (sizeof(T) == 8)
+        {
+            // tuned strided kernel with the W product as its epilogue (single modulus, F60 moduli)
+            if (!rns && !g_force_generic.load())
+            {
+                void* pairs = nullptr;
+                cudaError_t we = get_workspace(d->stream, 6, (size_t) N * sizeof(Twiddle<T>), &pairs);
+                if (we != cudaSuccess) return cuda_fail(we, "4-step twiddle-pair workspace allocation");
+                int launched = 0;
+                we = fast_fourstep_columns(reinterpret_cast<const uint64_t*>(src), reinterpret_cast<uint64_t*>(work),
+                                           reinterpret_cast<const uint64_t*>(d->n1_table), reinterpret_cast<const uint64_t*>(d->w_table), pairs,
+                                           (uint64_t) d->modulus_value, n, lg1, lg2, batch, st, &launched, prof_begin, prof_end);
+                if (we != cudaSuccess) return cuda_fail(we, "fast 4-step column pass launch");
+                columns_done = launched > 0;
+            }
+        }
+        if (!columns_done)
         {
             // column transforms: stages on index bits [lg2, n), then W[offset] as the pass is stored
             CoreCall<T> cc;

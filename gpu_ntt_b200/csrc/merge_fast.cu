@@ -153,8 +153,9 @@ namespace gpuntt_b200
         T p, ninv_w, ninv_wq;
         uint64_t mu; // 64-bit: floor(2^(63 + pbits) / p), 32-bit: floor(2^64 / p) -- companions without a division
         int pbits; // bit length of p
-        int n, lo, plus, first, last, batch;
+        int n, lo, plus, first, last, batch, rr;
         long long work; // total tiles of this pass
+        const void* w_pairs; // WMUL kernels: Twiddle<T>[N], the 4-step twiddle matrix with Shoup companions
     };
 
     // byte offset of local element l inside a (1 KiB aligned) tile buffer: TMA SWIZZLE_128B
@@ -167,10 +168,14 @@ namespace gpuntt_b200
     // ------------------------------------------------------------------ one register round
     // TRIV: the twiddle in slot 0 of every stage is 1 (first round of an X^N-1 transform: table[0] = omega^0),
     // so those butterflies skip the multiply (15 of the 32 butterflies of a radix-16 round).
-    template <typename S, int R, int LB, int G, bool FINAL, bool TRIV = false>
+    // WMUL (forward strided passes only): after the stages every element is multiplied by the (w, w') pair at its
+    // offset inside the polynomial -- the 4-step twiddle-matrix product (w_pairs: see fast_fourstep_columns) -- and
+    // canonicalised.  wtile points at the pair of the tile's first element, lo is the pass's row stride (log2).
+    template <typename S, int R, int LB, int G, bool FINAL, bool TRIV = false, bool WMUL = false>
     __device__ __forceinline__ void fast_round(unsigned char* buf, const Twiddle<typename S::T>* __restrict__ tws,
                                                const typename ModOf<S>::type& M, int ctid,
-                                               const Twiddle<typename S::T>& ninv)
+                                               const Twiddle<typename S::T>& ninv,
+                                               const Twiddle<typename S::T>* __restrict__ wtile = nullptr, int lo = 0)
     {
         using T = typename S::T;
         constexpr int E = 1 << R;
@@ -276,6 +281,29 @@ namespace gpuntt_b200
 #pragma unroll
                     for (int a = 0; a < E; a++) e[a] = M.canon_fwd(e[a]);
                 }
+                if constexpr (WMUL)
+                {
+                    static_assert(S::STRIDED && LB >= S::C, "the twiddle-matrix product is an epilogue of strided passes");
+                    // offset of element a: row (l >> C) * 2^lo + column (l & (2^C - 1)); a only moves the row
+                    const Twiddle<T>* wp = wtile + (((long long) (l_base >> S::C)) << lo) + (l_base & ((1 << S::C) - 1));
+                    // loads in batches of 8 (32 registers): ptxas otherwise serialises load -> multiply -> load and
+                    // exposes 16 global-memory latencies per tile
+                    constexpr int WB = E < 8 ? E : 8;
+#pragma unroll
+                    for (int h = 0; h < E; h += WB)
+                    {
+                        ulonglong2 v[WB];
+#pragma unroll
+                        for (int j = 0; j < WB; j++)
+                            v[j] = __ldg(reinterpret_cast<const ulonglong2*>(wp + (((long long) (h + j) << (LB - S::C)) << lo)));
+#pragma unroll
+                        for (int j = 0; j < WB; j++)
+                        {
+                            const Twiddle<T> tw{v[j].x, v[j].y};
+                            e[h + j] = csub(csub(M.mul(e[h + j], tw), M.p + M.p), M.p); // any 64-bit value in, [0,3p) out
+                        }
+                    }
+                }
             }
             else
             {
@@ -325,7 +353,7 @@ namespace gpuntt_b200
     //   STRIDED:   w = poly * 2^(lo-C) + column chunk            (any CTA, any order)
     //   !STRIDED:  w = range * tiles_per_range + polynomial group (range-major, so a CTA's
     //              contiguous share of the work stays inside one or two ranges)
-    template <typename S>
+    template <typename S, bool WMUL = false>
     __global__ void __launch_bounds__(kFastThreads, (!S::INV && S::POL == 2) ? (S::STRIDED ? GPUNTT_FAST_P0_BLOCKS : GPUNTT_FAST_P1_BLOCKS) : 2)
         fast_pass_kernel(const FastArgs<typename S::T> a, const __grid_constant__ CUtensorMap map_in,
                          const __grid_constant__ CUtensorMap map_out)
@@ -340,8 +368,14 @@ namespace gpuntt_b200
 
         const int tid = threadIdx.x;
         const int n = a.n;
-        const long long w_begin = a.work * blockIdx.x / gridDim.x;
-        const long long w_end = a.work * (blockIdx.x + 1) / gridDim.x;
+        // Work assignment.  Default: a contiguous share of the work items (a CTA stays inside one or two twiddle ranges).
+        // a.rr (strided passes with ONE range and a long row stride): round robin, item(i) = blockIdx + i * grid, with the
+        // items ordered column-chunk-major, so the tiles in flight across the chip at any moment are the polynomials
+        // of a few ADJACENT column chunks -- whole DRAM pages are consumed together and, for the 4-step column pass,
+        // the 16 polynomials of a chunk share one fetch of the twiddle-matrix pairs through the L2.
+        const long long step = a.rr ? (long long) gridDim.x : 1LL;
+        const long long w_begin = a.rr ? (long long) blockIdx.x : a.work * blockIdx.x / gridDim.x;
+        const long long w_end = a.rr ? a.work : a.work * (blockIdx.x + 1) / gridDim.x;
         // tiles that share one twiddle set ("range" = the index bits above this pass's stage window):
         //   STRIDED: every polynomial x every column chunk of one 2^D-row block;  else: every polynomial group
         const long long tiles_per_range =
@@ -379,7 +413,7 @@ namespace gpuntt_b200
                 const long long re = (long long) (range + 1) * tiles_per_range;
                 if (re < seg_end) seg_end = re;
             }
-            const int ntiles = (int) (seg_end - w);
+            const int ntiles = (int) ((seg_end - w + step - 1) / step);
 
             __syncthreads(); // everybody is done with the previous segment's twiddles and buffers
             {
@@ -423,7 +457,8 @@ namespace gpuntt_b200
                         {
                             const int ccb = a.lo - S::C;
                             const long long within = ww % tiles_per_range;
-                            const long long poly = within >> ccb, cc = within & ((1LL << ccb) - 1);
+                            const long long poly = a.rr ? within % a.batch : within >> ccb;
+                            const long long cc = a.rr ? within / a.batch : (within & ((1LL << ccb) - 1));
                             tma_load_3d(dst, &map_in, 0, (int) (cc << (S::C - S::CB)),
                                         (int) ((poly << (a.n - a.lo)) + ((long long) range << S::D)), bar);
                         }
@@ -434,7 +469,7 @@ namespace gpuntt_b200
                         }
                     }
                 };
-                for (int i = 0; i < 2 && i < ntiles; i++) issue_load(w + i, (int) ((uses0 + uses1 + i) & 1));
+                for (int i = 0; i < 2 && i < ntiles; i++) issue_load(w + i * step, (int) ((uses0 + uses1 + i) & 1));
                 // tile t of the CTA's whole stream uses buffer (t & 1); uses0 + uses1 = tiles so far
                 for (int i = 0; i < ntiles; i++)
                 {
@@ -445,12 +480,13 @@ namespace gpuntt_b200
                     if (lane == 0)
                     {
                         const uint32_t src = smem_u32(bufs + b * S::TILE_SMEM);
-                        const long long ww = w + i;
+                        const long long ww = w + i * step;
                         if constexpr (S::STRIDED)
                         {
                             const int ccb = a.lo - S::C;
                             const long long within = ww % tiles_per_range;
-                            const long long poly = within >> ccb, cc = within & ((1LL << ccb) - 1);
+                            const long long poly = a.rr ? within % a.batch : within >> ccb;
+                            const long long cc = a.rr ? within / a.batch : (within & ((1LL << ccb) - 1));
                             tma_store_3d(&map_out, 0, (int) (cc << (S::C - S::CB)),
                                          (int) ((poly << (a.n - a.lo)) + ((long long) range << S::D)), src);
                         }
@@ -464,7 +500,7 @@ namespace gpuntt_b200
                     }
                     __syncwarp();
                     if (b) uses1++; else uses0++;
-                    if (i + 2 < ntiles) issue_load(w + i + 2, b);
+                    if (i + 2 < ntiles) issue_load(w + (i + 2) * step, b);
                 }
                 if (lane == 0) bulk_wait0();
             }
@@ -483,19 +519,42 @@ namespace gpuntt_b200
                     if constexpr (!S::INV)
                     {
                         constexpr bool FIN1 = !S::STRIDED && S::R2 == 0, FIN2 = !S::STRIDED;
+                        constexpr bool W1 = WMUL && S::R2 == 0, W2 = WMUL && S::R2 > 0;
+                        const Twiddle<T>* wtile = nullptr;
+                        if constexpr (WMUL)
+                        {
+                            // pair of the tile's first element: row block `range`, column chunk cc (same for every polynomial)
+                            const long long within = (w + i * step) % tiles_per_range;
+                            const long long cc = a.rr ? within / a.batch : (within & ((1LL << (a.lo - S::C)) - 1));
+                            wtile = reinterpret_cast<const Twiddle<T>*>(a.w_pairs) + ((((long long) range << S::D)) << a.lo) + (cc << S::C);
+                        }
+                        if constexpr (WMUL)
+                        {
+                            // pull this thread's pairs towards the SM now; they are consumed after the last round
+                            constexpr int RW = S::R2 > 0 ? S::R2 : S::R1, LBW = S::R2 > 0 ? S::LB2 : S::LB1;
+#pragma unroll 1
+                            for (int item = tid; item < ((1 << S::K) >> RW); item += kConsumers)
+                            {
+                                const int l_base = ((item >> LBW) << (LBW + RW)) | (item & ((1 << LBW) - 1));
+                                const Twiddle<T>* wp = wtile + (((long long) (l_base >> S::C)) << a.lo) + (l_base & ((1 << S::C) - 1));
+#pragma unroll
+                                for (int x = 0; x < (1 << RW); x++)
+                                    asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + (((long long) x << (LBW - S::C)) << a.lo)));
+                            }
+                        }
                         if constexpr (S::STRIDED && S::POL == 2 && S::G1 == 1)
                         {
                             if (triv)
-                                fast_round<S, S::R1, S::LB1, S::G1, FIN1, true>(buf, tw1, M, tid, ninv);
+                                fast_round<S, S::R1, S::LB1, S::G1, FIN1, true, W1>(buf, tw1, M, tid, ninv, wtile, a.lo);
                             else
-                                fast_round<S, S::R1, S::LB1, S::G1, FIN1>(buf, tw1, M, tid, ninv);
+                                fast_round<S, S::R1, S::LB1, S::G1, FIN1, false, W1>(buf, tw1, M, tid, ninv, wtile, a.lo);
                         }
                         else
                             fast_round<S, S::R1, S::LB1, S::G1, FIN1>(buf, tw1, M, tid, ninv);
                         if constexpr (S::R2 > 0)
                         {
                             consumer_sync();
-                            fast_round<S, S::R2, S::LB2, S::G2, FIN2>(buf, tw2, M, tid, ninv);
+                            fast_round<S, S::R2, S::LB2, S::G2, FIN2, false, W2>(buf, tw2, M, tid, ninv, wtile, a.lo);
                         }
                     }
                     else
@@ -590,10 +649,10 @@ namespace gpuntt_b200
     }
 
     // returns cudaErrorNotSupported when the tensor maps cannot be built (caller falls back)
-    template <typename S> static cudaError_t launch_fast(const FastArgs<typename S::T>& args, cudaStream_t st)
+    template <typename S, bool WMUL = false> static cudaError_t launch_fast(const FastArgs<typename S::T>& args, cudaStream_t st)
     {
         static int blocks_per_sm = -1, sms = 0; // per process; devices on one box are identical
-        auto kern = fast_pass_kernel<S>;
+        auto kern = fast_pass_kernel<S, WMUL>;
         if (blocks_per_sm < 0)
         {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM);
@@ -711,11 +770,10 @@ namespace gpuntt_b200
         if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return cudaSuccess;
         if constexpr (sizeof(T) == 8)
         {
-            // forward: F60 policy for 2^40 <= p < 2^60 - 2^31; inverse: the lazy policy, whose high-word range test
-            // lets the slack above 4p double per stage (2^(31 + stages)), so it needs 2^(32 + n) <= p.  Other moduli:
-            // exact-policy kernels exist for n = 16 only, everything else goes to the generic pass kernel.
+            // forward: F60 policy for 2^40 <= p < 2^60 - 2^31; inverse: the lazy policy (exact range test, any p below
+            // 1.25 * 2^60).  Other moduli: exact-policy kernels exist for n = 16 only, the rest goes to the generic kernel.
             const bool f60 = (uint64_t) p >= kF60ModulusMin && (uint64_t) p < kF60ModulusLimit;
-            const bool fast_inv = (uint64_t) p >= kFastModulusMin && (uint64_t) p < kFastModulusLimit && ((uint64_t) p >> (32 + n_power)) != 0;
+            const bool fast_inv = (uint64_t) p < kFastModulusLimit;
             const bool fast_arith = inverse ? fast_inv : f60;
             if (!fast_arith && n_power != 16) return cudaSuccess;
             FastArgs<T> a{};
@@ -751,6 +809,7 @@ namespace gpuntt_b200
                 {
                     const int c = 12 - pl.d[i];
                     s.work = ((long long) batch << (pl.lo[i] - c)) << (n_power - pl.lo[i] - pl.d[i]);
+                    s.rr = (n_power == pl.lo[i] + pl.d[i]) && pl.lo[i] > 10; // one range, long row stride
                     if (fast_arith)
                         e = inverse ? launch_strided<T, true, 1>(pl.d[i], s, st) : launch_strided<T, false, 2>(pl.d[i], s, st);
                     else
@@ -818,6 +877,68 @@ namespace gpuntt_b200
             }
             *launched = pl.npass;
         }
+        return cudaSuccess;
+    }
+
+    // (w, w') pairs of the 4-step twiddle matrix, once per call (the batch shares it)
+    __global__ void __launch_bounds__(256) w_pairs_kernel(const uint64_t* __restrict__ w, Twiddle<uint64_t>* __restrict__ out, long long count,
+                                                          uint64_t p, uint64_t mu, int pbits)
+    {
+        const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= count) return;
+        const uint64_t v = w[i];
+        out[i] = Twiddle<uint64_t>{v, shoup_companion_mu(v, p, mu, pbits)};
+    }
+
+    // Forward 4-step column phase on the tuned strided kernel: the first lg1 stages of a size-2^n transform with the
+    // n1 table (rows 2^lg2 elements apart), then every element times W[offset] (pairs built into w_pairs_ws, N
+    // entries), canonical outputs.  Single modulus, 64-bit, F60 moduli; *launched = 0 when not covered.
+    cudaError_t fast_fourstep_columns(const uint64_t* in, uint64_t* out, const uint64_t* n1_table, const uint64_t* w_table,
+                                      void* w_pairs_ws, uint64_t p, int n_power, int lg1, int lg2, int batch, cudaStream_t st,
+                                      int* launched, void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t))
+    {
+        using T = uint64_t;
+        *launched = 0;
+        if (lg1 < 5 || lg1 > 8 || lg2 < 12 - lg1 || n_power != lg1 + lg2) return cudaSuccess;
+        if (!(p >= kF60ModulusMin && p < kF60ModulusLimit)) return cudaSuccess;
+        if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return cudaSuccess;
+        FastArgs<T> a{};
+        a.in = in;
+        a.out = out;
+        a.table = n1_table;
+        a.p = p;
+        a.pbits = 64 - __builtin_clzll((unsigned long long) p);
+        {
+            const unsigned __int128 m = (((unsigned __int128) 1) << (63 + a.pbits)) / (unsigned __int128) p;
+            a.mu = (m >> 64) ? ~0ull : (uint64_t) m;
+        }
+        a.n = n_power;
+        a.lo = lg2;
+        a.plus = 0;
+        a.first = 1;
+        a.last = 0;
+        a.batch = batch;
+        a.w_pairs = w_pairs_ws;
+        a.work = (long long) batch << (lg2 - (12 - lg1));
+        a.rr = 1; // column-chunk-major round robin: the polynomials of a chunk share the pair fetch through the L2
+        const long long N = 1LL << n_power;
+        prof_begin(0, st);
+        w_pairs_kernel<<<(unsigned) ((N + 255) / 256), 256, 0, st>>>(w_table, reinterpret_cast<Twiddle<T>*>(w_pairs_ws), N, p, a.mu, a.pbits);
+        prof_end(st);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        prof_begin(1, st);
+        switch (lg1)
+        {
+            case 5: e = launch_fast<Shape<T, false, 2, true, 3, 2, 12, 0>, true>(a, st); break;
+            case 6: e = launch_fast<Shape<T, false, 2, true, 3, 3, 12, 0>, true>(a, st); break;
+            case 7: e = launch_fast<Shape<T, false, 2, true, 4, 3, 12, 0>, true>(a, st); break;
+            default: e = launch_fast<Shape<T, false, 2, true, 4, 4, 12, 0>, true>(a, st); break;
+        }
+        prof_end(st);
+        if (e == cudaErrorNotSupported) return cudaSuccess; // (the pair table was written for nothing)
+        if (e != cudaSuccess) return e;
+        *launched = 2;
         return cudaSuccess;
     }
 

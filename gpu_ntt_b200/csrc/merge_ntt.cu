@@ -590,6 +590,9 @@ namespace gpuntt_b200
 
     // merge_fast.cu
     int fast_describe(int n_power, int element_bits, char* buf, size_t len);
+    cudaError_t fast_fourstep_columns(const uint64_t* in, uint64_t* out, const uint64_t* n1_table, const uint64_t* w_table,
+                                      void* w_pairs_ws, uint64_t p, int n_power, int lg1, int lg2, int batch, cudaStream_t st,
+                                      int* launched, void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t));
     template <typename T>
     cudaError_t fast_merge(const T* in, T* out, const T* table, T p, T ninv, int n_power, int plus, bool inverse,
                            int batch, cudaStream_t st, int* launched, void (*prof_begin)(int, cudaStream_t),
@@ -766,8 +769,7 @@ namespace gpuntt_b200
         args.w_hi = cc.w_hi;
         if (!rns) barrett_constants<T>(cc.p, args.bar_bit, args.bar_mu);
         bool fast = false;
-        if constexpr (sizeof(T) == 8) fast = !rns && (uint64_t) cc.p >= kFastModulusMin && (uint64_t) cc.p < kFastModulusLimit &&
-                                         (!cc.inverse || (((uint64_t) cc.p >> 32) >> cc.n_power) != 0); // inverse slack doubles per stage
+        if constexpr (sizeof(T) == 8) fast = !rns && (uint64_t) cc.p < kFastModulusLimit && (cc.inverse || (uint64_t) cc.p >= kFastModulusMin);
         for (int i = 0; i < cc.npasses; i++)
         {
             args.plan = cc.pass[i];

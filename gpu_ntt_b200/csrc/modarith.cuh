@@ -96,9 +96,9 @@ namespace gpuntt_b200
     template <> struct Mod<uint64_t, true>
     {
         using T = uint64_t;
-        T p, four_p, six_p, neg_four_p;
+        T p, four_p, neg_four_p;
         uint32_t n0, n1, f0, f1; // -p mod 2^64 ; 4p
-        __device__ __forceinline__ explicit Mod(T p_) : p(p_), four_p(4 * p_), six_p(6 * p_), neg_four_p(0 - 4 * p_)
+        __device__ __forceinline__ explicit Mod(T p_) : p(p_), four_p(4 * p_), neg_four_p(0 - 4 * p_)
         {
             const T np = 0 - p_;
             n0 = (uint32_t) np;
@@ -179,12 +179,15 @@ namespace gpuntt_b200
             X = x + t;
             Y = x - t + four_p;
         }
-        // Inverse values live in [0, 4p + 17 * 2^32): the high-word test leaves 2^32 of slack per stage.
+        // Inverse values live in [0, 4p): the range test of the sum is an exact 64-bit compare (a high-word test would
+        // leave slack that DOUBLES per stage, because both inputs of a Gentleman-Sande sum are lazy), and the three
+        // 64-bit results are three-operand sums so that they stay on the alu pipe.
         __device__ __forceinline__ void gs(T& X, T& Y, const Twiddle<T>& tw) const
         {
+            const T d = X + four_p - Y;
             const T s = X + Y;
-            const T d = X - Y + six_p;
-            X = csub_hi(s);
+            const T g = (s >= four_p) ? neg_four_p : T(0);
+            X = X + Y + g;
             Y = mul(d, tw);
         }
         __device__ __forceinline__ T canon_fwd(T x) const

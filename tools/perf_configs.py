@@ -65,13 +65,19 @@ def merge_case(name, logn, batch, bits, poly, iters, inverse=False, both=False):
         inv()
     fn = rt if both else (inv if inverse else fwd)
     ms = time_ms(fn, iters)
+    lib = capi.lib()
+    lib.gpuntt_b200_set_profiling(1)
+    capi.profile_read()
+    fn()
+    launches = [(k, round(m, 4)) for k, m in capi.profile_read()]
+    lib.gpuntt_b200_set_profiling(0)
     ntts = batch * (2 if both else 1)
     bytes_alg = 2 * (1 << logn) * (bits // 8) * ntts
     gbs = bytes_alg / (ms * 1e-3) / 1e9
     out = {"case": name, "logn": logn, "batch": batch, "bits": bits, "ring": "X^N-1" if poly == X_N_minus else "X^N+1",
            "op": "fwd+inv" if both else ("inv" if inverse else "fwd"), "ms": round(ms, 4),
            "ntt_per_s": round(ntts / (ms * 1e-3), 1), "alg_GBps": round(gbs, 1), "frac_hbm": round(gbs / peak(), 4),
-           "plan": capi.describe_plan(logn, bits).strip()}
+           "launches_kind_ms": launches, "plan": capi.describe_plan(logn, bits).strip()}
     print(json.dumps(out), flush=True)
     del x
     torch.cuda.empty_cache()
@@ -92,12 +98,18 @@ def fourstep_case(name, logn, batch, iters, contract):
     def fn():
         capi.fourstep_ntt(x, t1, t2, w, p, logn, io_contract=contract, out=out)
     ms = time_ms(fn, iters, warm=2)
+    lib = capi.lib()
+    lib.gpuntt_b200_set_profiling(1)
+    capi.profile_read()
+    fn()
+    launches = [(k, round(m, 4)) for k, m in capi.profile_read()]   # kind 9 = transpose, 0 = twiddle prep, k = k-th pass
+    lib.gpuntt_b200_set_profiling(0)
     bytes_alg = 2 * (1 << logn) * 8 * batch
     gbs = bytes_alg / (ms * 1e-3) / 1e9
     print(json.dumps({"case": name, "logn": logn, "batch": batch, "bits": 64, "n1": n1, "n2": n2,
                       "contract": "fused" if contract == capi.FOURSTEP_FUSED else "reference", "ms": round(ms, 4),
                       "ntt_per_s": round(batch / (ms * 1e-3), 2), "alg_GBps": round(gbs, 1),
-                      "frac_hbm": round(gbs / peak(), 4)}), flush=True)
+                      "frac_hbm": round(gbs / peak(), 4), "launches_kind_ms": launches}), flush=True)
     del x, w, out
     torch.cuda.empty_cache()
 
@@ -116,7 +128,7 @@ def main():
     fourstep_case("C4 4-step fused", 24, 16, max(2, it // 4), capi.FOURSTEP_FUSED)
     fourstep_case("C4 4-step reference contract", 24, 16, max(2, it // 4), capi.FOURSTEP_REFERENCE)
     if not args.quick:
-        for logn in (12, 13, 14, 15, 17, 18, 20):
+        for logn in (12, 13, 14, 15, 17, 18, 20, 22, 24):
             merge_case(f"u64 logN={logn}", logn, max(1, (1 << 26) >> logn), 64, X_N_minus, it)
         for logn in (12, 16):
             merge_case(f"u32 logN={logn}", logn, max(1, (1 << 27) >> logn), 32, X_N_minus, it)
