@@ -224,9 +224,17 @@ def run_b200_arm(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("merge_pass_kernel_dram_bytes_per_launch")
+            traffic = json.load(f).get("fast_pass_kernel_dram_bytes_per_launch")   # from one ncu --set full capture
     except Exception:
         pass
+    # informational second roof: the 32-bit integer multiplier pipe.  One 64-bit Shoup butterfly costs
+    # 28 issue cycles of that pipe per warp and SM sub-partition (4 IMAD.WIDE + 1 IMAD.HI at 4, 4 IMAD at 2 --
+    # profiles/r1_pipe_probes2.txt); an N = 2^16 cyclic transform has 16 * 2^15 butterflies of which the
+    # twiddle-1 ones of the first three stages (2^15 + 2^14 + 2^13) need no multiply.
+    muls_per_ntt = LOGN * (1 << (LOGN - 1)) - ((1 << 15) + (1 << 14) + (1 << 13))
+    sms = torch.cuda.get_device_properties(local).multi_processor_count
+    clk = (clocks or {}).get("sm_mhz") or 1965.0
+    int_roof = sms * 4 * clk * 1e6 / (28.0 * muls_per_ntt / 32.0)
 
     # end to end: pinned host buffers -> H2D -> NTT -> D2H through the host-buffer C-ABI entry point
     import ctypes as C
@@ -265,7 +273,11 @@ def run_b200_arm(args):
                 "d2h_bytes_per_step": nbytes, "steps": e2e_steps,
                 "api": "gpuntt_b200_merge_ntt_host (pinned host in/out, copies + kernels + sync per step)"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "merge_pass_kernel<u64,fwd>", "achieved": achieved, "peak": peak,
+        "int_mul_roof": {"ntt_per_s_per_gpu": int_roof, "frac": (value / world) / int_roof,
+                         "model": "28 multiplier-pipe issue cycles per warp-butterfly, %d multiplying butterflies per NTT, "
+                                  "%d SMs x 4 sub-partitions at %.0f MHz" % (muls_per_ntt, sms, clk)},
+        "roofline": {"bound": "hbm", "kernel": "fast_pass_kernel (2 launches per step: strided stages 0-7, contiguous stages 8-15)",
+                     "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                      "peak_source": peak_src, "launches_per_step": npasses,
                      "algorithmic_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": avg_pass_ms,
