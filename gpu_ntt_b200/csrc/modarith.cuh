@@ -9,16 +9,18 @@
 // output canonical in [0,p), so results are bit-identical to the reference's
 // OPERATOR::mult/add/sub chain.
 //
-// Two arithmetic policies (struct Mod<T, FAST>):
-//   exact (FAST=false): q exact; values in [0,4p) forward / [0,2p) inverse; needs 4p < 2^BITS,
+// Arithmetic policies:
+//   exact (Mod<T,false>): q exact; values in [0,4p) forward / [0,2p) inverse; needs 4p < 2^BITS,
 //         i.e. the reference's whole supported modulus range (p < 2^62 / p < 2^30,
 //         modular_arith.cuh:66-67).
-//   fast  (FAST=true, 64-bit only, p < 2^60.9): B200's IMAD.WIDE / IMAD.HI issue at half the
-//         rate of a 32-bit IMAD (tools/microbench.cu), and everything a 64-bit butterfly does is
-//         bound by that pipe, so the quotient is taken from three partial products only
-//             q~ = a1*y1 + hi32(a1*y0) + hi32(a0*y1)   in {Q-2, Q-1, Q},  r = w*y - q~*p in [0,4p)
-//         and r is accumulated with mad chains against -p (no separate subtract).  Values live
-//         in [0, 8p + 2^32) forward (range test on the high word only) / [0,4p) inverse.
+//   fast  (Mod<u64,true>, p < 1.25 * 2^60): B200's IMAD.WIDE / IMAD.HI issue at half the rate of a
+//         32-bit IMAD and everything a 64-bit butterfly does is bound by that pipe, so the quotient
+//         is taken from three partial products only (q~ in {Q-1, Q}, r in [0,3p) for ANY 64-bit
+//         input) and r is accumulated with mad chains against -p.  Forward values live in
+//         [0, 8p + 2^32) (range test on the high word only; needs p >= 2^36), inverse values in
+//         [0, 4p) (exact range test).
+//   F60   (ModF60, forward, 2^40 <= p < 2^60 - 2^31): the tuned kernels' policy -- range correction
+//         every other stage, bare add/subtract for twiddle-1 butterflies, one-step canonicalisation.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
