@@ -229,8 +229,28 @@ template <typename T> static int fourstep_execute_t(const gpuntt_b200_4step_desc
             if (e != cudaSuccess) return cuda_fail(e, "transpose_kernel launch");
             src = ws;
         }
-        rc = row_transforms(src, ws, lg1, (long long) batch * n2, d->n1_table, lg2, true);
+        bool inverse_done = false;
+        if constexpr (sizeof(T) == 8)
+        {
+            // tuned kernels: row phase + strided Gentleman-Sande passes with the W^-1 product as the first one loads
+            if (!rns && !g_force_generic.load())
+            {
+                void* pairs = nullptr;
+                cudaError_t we = get_workspace(d->stream, 6, (size_t) N * sizeof(Twiddle<T>), &pairs);
+                if (we != cudaSuccess) return cuda_fail(we, "4-step twiddle-pair workspace allocation");
+                int launched = 0;
+                we = fast_fourstep_inverse(reinterpret_cast<const uint64_t*>(src), reinterpret_cast<uint64_t*>(ws),
+                                           reinterpret_cast<uint64_t*>(fused ? out : ws), reinterpret_cast<const uint64_t*>(d->n1_table),
+                                           reinterpret_cast<const uint64_t*>(d->n2_table), reinterpret_cast<const uint64_t*>(d->w_table), pairs,
+                                           (uint64_t) d->modulus_value, (uint64_t) d->mod_inverse_value, n, lg1, lg2, batch, st, &launched,
+                                           prof_begin, prof_end);
+                if (we != cudaSuccess) return cuda_fail(we, "fast 4-step inverse launch");
+                inverse_done = launched > 0;
+            }
+        }
+        if (!inverse_done) rc = row_transforms(src, ws, lg1, (long long) batch * n2, d->n1_table, lg2, true);
         if (rc != GPUNTT_B200_OK) return rc;
+        if (!inverse_done)
         {
             CoreCall<T> cc;
             base_call(cc);

@@ -109,7 +109,9 @@ namespace gpuntt_b200
     // !STRIDED: tile = 2^NPLOG polynomials x 2^KC adjacent elements of the same ring range.
     // Two register rounds: R1 stages on the high bits, R2 on the low bits (D = R1 + R2).
     // POL: arithmetic policy -- 0 exact (any modulus the reference accepts), 1 fast lazy (inverse), 2 F60 (forward).
-    template <typename T_, bool INV_, int POL_, bool STRIDED_, int R1_, int R2_, int K_, int NPLOG_> struct Shape
+    // NT: contiguous passes of transforms SHORTER than a tile row group (the 4-step inverse row phase, N = n1 <= 256): twiddles
+    // depend on the low NT index bits only and a tile holds several whole transforms.
+    template <typename T_, bool INV_, int POL_, bool STRIDED_, int R1_, int R2_, int K_, int NPLOG_, int NT_ = 0> struct Shape
     {
         using T = T_;
         static constexpr int POL = POL_;
@@ -119,7 +121,8 @@ namespace gpuntt_b200
         static constexpr int D = R1 + R2;
         static constexpr int C = STRIDED ? (K - D) : 0;
         static constexpr int KC = K - NPLOG;          // contiguous elements per polynomial in a tile
-        static constexpr int KTW = STRIDED ? K : KC;  // local index bits that select twiddles
+        static constexpr int NT = NT_;
+        static constexpr int KTW = STRIDED ? K : (NT_ ? NT_ : KC);  // local index bits that select twiddles
         static constexpr int CB = (sizeof(T) == 8) ? 4 : 5; // log2 elements per 128-byte row
         static constexpr int ROWS = (1 << K) >> CB;
         static constexpr int TILE_SMEM = ROWS * 128;
@@ -132,17 +135,21 @@ namespace gpuntt_b200
         static_assert(LB1 >= CB, "high round must start on a row boundary");
     };
 
-    template <typename S> struct ModOf
+    template <typename T, int POL> struct ModSel
     {
-        using type = Mod<typename S::T, false>;
+        using type = Mod<T, false>;
     };
-    template <bool INV_, bool STRIDED_, int R1_, int R2_, int K_, int NPLOG_> struct ModOf<Shape<uint64_t, INV_, 1, STRIDED_, R1_, R2_, K_, NPLOG_>>
+    template <> struct ModSel<uint64_t, 1>
     {
         using type = Mod<uint64_t, true>;
     };
-    template <bool INV_, bool STRIDED_, int R1_, int R2_, int K_, int NPLOG_> struct ModOf<Shape<uint64_t, INV_, 2, STRIDED_, R1_, R2_, K_, NPLOG_>>
+    template <> struct ModSel<uint64_t, 2>
     {
         using type = ModF60;
+    };
+    template <typename S> struct ModOf
+    {
+        using type = typename ModSel<typename S::T, S::POL>::type;
     };
 
     template <typename T> struct FastArgs
@@ -154,6 +161,7 @@ namespace gpuntt_b200
         uint64_t mu; // 64-bit: floor(2^(63 + pbits) / p), 32-bit: floor(2^64 / p) -- companions without a division
         int pbits; // bit length of p
         int n, lo, plus, first, last, batch, rr;
+        int n_tw; // transform size (log2) for twiddle indexing when it differs from the layout size n (0: n)
         long long work; // total tiles of this pass
         const void* w_pairs; // WMUL kernels: Twiddle<T>[N], the 4-step twiddle matrix with Shoup companions
     };
@@ -231,6 +239,34 @@ namespace gpuntt_b200
                 for (int a = 0; a < E; a++) e[a] = *reinterpret_cast<const T*>(addr(a));
             }
 
+            // 4-step twiddle-matrix product on the item's elements (forward: epilogue, canonical results; inverse:
+            // prologue, lazy results in [0,3p)).  Loads in batches of 8 (32 registers): ptxas otherwise serialises
+            // load -> multiply -> load and exposes one global-memory latency per element.
+            auto w_product = [&](bool canonical)
+            {
+                if constexpr (WMUL)
+                {
+                    static_assert(!WMUL || (S::STRIDED && LB >= S::C), "the twiddle-matrix product belongs to strided passes");
+                    // offset of element a: row (l >> C) * 2^lo + column (l & (2^C - 1)); a only moves the row
+                    const Twiddle<T>* wp = wtile + (((long long) (l_base >> S::C)) << lo) + (l_base & ((1 << S::C) - 1));
+                    constexpr int WB = E < 8 ? E : 8;
+#pragma unroll
+                    for (int h = 0; h < E; h += WB)
+                    {
+                        ulonglong2 v[WB];
+#pragma unroll
+                        for (int j = 0; j < WB; j++)
+                            v[j] = __ldg(reinterpret_cast<const ulonglong2*>(wp + (((long long) (h + j) << (LB - S::C)) << lo)));
+#pragma unroll
+                        for (int j = 0; j < WB; j++)
+                        {
+                            const Twiddle<T> tw{v[j].x, v[j].y};
+                            const T r = M.mul(e[h + j], tw); // any 64-bit value in, [0,3p) out
+                            e[h + j] = canonical ? csub(csub(r, M.p + M.p), M.p) : r;
+                        }
+                    }
+                }
+            };
             const Twiddle<T>* tg = tws + group;
             if constexpr (!S::INV)
             {
@@ -281,32 +317,11 @@ namespace gpuntt_b200
 #pragma unroll
                     for (int a = 0; a < E; a++) e[a] = M.canon_fwd(e[a]);
                 }
-                if constexpr (WMUL)
-                {
-                    static_assert(S::STRIDED && LB >= S::C, "the twiddle-matrix product is an epilogue of strided passes");
-                    // offset of element a: row (l >> C) * 2^lo + column (l & (2^C - 1)); a only moves the row
-                    const Twiddle<T>* wp = wtile + (((long long) (l_base >> S::C)) << lo) + (l_base & ((1 << S::C) - 1));
-                    // loads in batches of 8 (32 registers): ptxas otherwise serialises load -> multiply -> load and
-                    // exposes 16 global-memory latencies per tile
-                    constexpr int WB = E < 8 ? E : 8;
-#pragma unroll
-                    for (int h = 0; h < E; h += WB)
-                    {
-                        ulonglong2 v[WB];
-#pragma unroll
-                        for (int j = 0; j < WB; j++)
-                            v[j] = __ldg(reinterpret_cast<const ulonglong2*>(wp + (((long long) (h + j) << (LB - S::C)) << lo)));
-#pragma unroll
-                        for (int j = 0; j < WB; j++)
-                        {
-                            const Twiddle<T> tw{v[j].x, v[j].y};
-                            e[h + j] = csub(csub(M.mul(e[h + j], tw), M.p + M.p), M.p); // any 64-bit value in, [0,3p) out
-                        }
-                    }
-                }
+                if constexpr (WMUL) w_product(true);
             }
             else
             {
+                if constexpr (WMUL) w_product(false);
 #pragma unroll
                 for (int ab = 0; ab < R; ab++)
                 {
@@ -418,7 +433,8 @@ namespace gpuntt_b200
             __syncthreads(); // everybody is done with the previous segment's twiddles and buffers
             {
                 // (w, w') pairs for both rounds, slot-major: entry (slot, group) at slot*G + group
-                const int j0 = S::STRIDED ? (range << S::D) : (range << S::KC); // index (>> lo) of the tile's first row
+                const int j0 = S::STRIDED ? (range << S::D) : (S::NT ? 0 : (range << S::KC)); // index (>> lo) of the tile's first row
+                const int ntw = a.n_tw ? a.n_tw : n;
                 for (int i = tid; i < S::TW1 + S::TW2; i += kFastThreads)
                 {
                     const bool hi = i < S::TW1;
@@ -429,7 +445,7 @@ namespace gpuntt_b200
                     const int lvl = 31 - __clz(slot + 1); // = R-1-ab
                     const int ab = R - 1 - lvl, x = slot + 1 - (1 << lvl);
                     const int rb0 = LB - S::C;
-                    const int s = n - 1 - a.lo - (rb0 + ab);
+                    const int s = ntw - 1 - a.lo - (rb0 + ab);
                     const int J = j0 | (group << (LB + R - S::C));
                     const long long idx = ((long long) a.plus << s) + (J >> (rb0 + ab + 1)) + x;
                     const T wv = a.table[idx];
@@ -516,32 +532,31 @@ namespace gpuntt_b200
                     mbar_wait(smem_u32(&bars[b]), k & 1); // tile landed
                     // In this path the contiguous pass is always the LAST forward / FIRST inverse pass, so only it
                     // canonicalises forward and only a strided pass (the top one) applies n^-1 on the inverse.
+                    // 4-step twiddle-matrix product: forward = epilogue of the last round, inverse = prologue of the first
+                    // executed round; either way that is the low round when there are two.
+                    const Twiddle<T>* wtile = nullptr;
+                    if constexpr (WMUL)
+                    {
+                        // pair of the tile's first element: row block `range`, column chunk cc (same for every polynomial)
+                        const long long within = (w + i * step) % tiles_per_range;
+                        const long long cc = a.rr ? within / a.batch : (within & ((1LL << (a.lo - S::C)) - 1));
+                        wtile = reinterpret_cast<const Twiddle<T>*>(a.w_pairs) + ((((long long) range << S::D)) << a.lo) + (cc << S::C);
+                        // pull this thread's pairs towards the SM now
+                        constexpr int RW = S::R2 > 0 ? S::R2 : S::R1, LBW = S::R2 > 0 ? S::LB2 : S::LB1;
+#pragma unroll 1
+                        for (int item = tid; item < ((1 << S::K) >> RW); item += kConsumers)
+                        {
+                            const int l_base = ((item >> LBW) << (LBW + RW)) | (item & ((1 << LBW) - 1));
+                            const Twiddle<T>* wp = wtile + (((long long) (l_base >> S::C)) << a.lo) + (l_base & ((1 << S::C) - 1));
+#pragma unroll
+                            for (int x = 0; x < (1 << RW); x++)
+                                asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + (((long long) x << (LBW - S::C)) << a.lo)));
+                        }
+                    }
+                    constexpr bool W1 = WMUL && S::R2 == 0, W2 = WMUL && S::R2 > 0;
                     if constexpr (!S::INV)
                     {
                         constexpr bool FIN1 = !S::STRIDED && S::R2 == 0, FIN2 = !S::STRIDED;
-                        constexpr bool W1 = WMUL && S::R2 == 0, W2 = WMUL && S::R2 > 0;
-                        const Twiddle<T>* wtile = nullptr;
-                        if constexpr (WMUL)
-                        {
-                            // pair of the tile's first element: row block `range`, column chunk cc (same for every polynomial)
-                            const long long within = (w + i * step) % tiles_per_range;
-                            const long long cc = a.rr ? within / a.batch : (within & ((1LL << (a.lo - S::C)) - 1));
-                            wtile = reinterpret_cast<const Twiddle<T>*>(a.w_pairs) + ((((long long) range << S::D)) << a.lo) + (cc << S::C);
-                        }
-                        if constexpr (WMUL)
-                        {
-                            // pull this thread's pairs towards the SM now; they are consumed after the last round
-                            constexpr int RW = S::R2 > 0 ? S::R2 : S::R1, LBW = S::R2 > 0 ? S::LB2 : S::LB1;
-#pragma unroll 1
-                            for (int item = tid; item < ((1 << S::K) >> RW); item += kConsumers)
-                            {
-                                const int l_base = ((item >> LBW) << (LBW + RW)) | (item & ((1 << LBW) - 1));
-                                const Twiddle<T>* wp = wtile + (((long long) (l_base >> S::C)) << a.lo) + (l_base & ((1 << S::C) - 1));
-#pragma unroll
-                                for (int x = 0; x < (1 << RW); x++)
-                                    asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + (((long long) x << (LBW - S::C)) << a.lo)));
-                            }
-                        }
                         if constexpr (S::STRIDED && S::POL == 2 && S::G1 == 1)
                         {
                             if (triv)
@@ -561,15 +576,15 @@ namespace gpuntt_b200
                     {
                         if constexpr (S::R2 > 0)
                         {
-                            fast_round<S, S::R2, S::LB2, S::G2, false>(buf, tw2, M, tid, ninv);
+                            fast_round<S, S::R2, S::LB2, S::G2, false, false, W2>(buf, tw2, M, tid, ninv, wtile, a.lo);
                             consumer_sync();
                         }
                         if constexpr (S::STRIDED)
                         {
                             if (a.last)
-                                fast_round<S, S::R1, S::LB1, S::G1, true>(buf, tw1, M, tid, ninv);
+                                fast_round<S, S::R1, S::LB1, S::G1, true, false, W1>(buf, tw1, M, tid, ninv, wtile, a.lo);
                             else
-                                fast_round<S, S::R1, S::LB1, S::G1, false>(buf, tw1, M, tid, ninv);
+                                fast_round<S, S::R1, S::LB1, S::G1, false, false, W1>(buf, tw1, M, tid, ninv, wtile, a.lo);
                         }
                         else
                             fast_round<S, S::R1, S::LB1, S::G1, false>(buf, tw1, M, tid, ninv);
@@ -881,12 +896,15 @@ namespace gpuntt_b200
     }
 
     // (w, w') pairs of the 4-step twiddle matrix, once per call (the batch shares it)
+    // t_lo > 0: entry i comes from the transposed index ((i mod 2^t_lo) << t_hi) | (i >> t_lo) (4-step inverse: the data
+    // is the n2 x n1 matrix, the reference's inverse twiddle matrix is laid out n1 x n2)
     __global__ void __launch_bounds__(256) w_pairs_kernel(const uint64_t* __restrict__ w, Twiddle<uint64_t>* __restrict__ out, long long count,
-                                                          uint64_t p, uint64_t mu, int pbits)
+                                                          uint64_t p, uint64_t mu, int pbits, int t_lo, int t_hi)
     {
         const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
         if (i >= count) return;
-        const uint64_t v = w[i];
+        const long long src = t_lo ? (((i & ((1LL << t_lo) - 1)) << t_hi) | (i >> t_lo)) : i;
+        const uint64_t v = w[src];
         out[i] = Twiddle<uint64_t>{v, shoup_companion_mu(v, p, mu, pbits)};
     }
 
@@ -923,7 +941,7 @@ namespace gpuntt_b200
         a.rr = 1; // column-chunk-major round robin: the polynomials of a chunk share the pair fetch through the L2
         const long long N = 1LL << n_power;
         prof_begin(0, st);
-        w_pairs_kernel<<<(unsigned) ((N + 255) / 256), 256, 0, st>>>(w_table, reinterpret_cast<Twiddle<T>*>(w_pairs_ws), N, p, a.mu, a.pbits);
+        w_pairs_kernel<<<(unsigned) ((N + 255) / 256), 256, 0, st>>>(w_table, reinterpret_cast<Twiddle<T>*>(w_pairs_ws), N, p, a.mu, a.pbits, 0, 0);
         prof_end(st);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -939,6 +957,124 @@ namespace gpuntt_b200
         if (e == cudaErrorNotSupported) return cudaSuccess; // (the pair table was written for nothing)
         if (e != cudaSuccess) return e;
         *launched = 2;
+        return cudaSuccess;
+    }
+
+    // Inverse 4-step on the tuned kernels.  `rows_in` holds the n2 x n1 matrix (n2 rows of n1 contiguous elements):
+    //   1. contiguous inverse pass: a size-n1 Gentleman-Sande transform on every row (n1 table, no n^-1), rows_in -> work;
+    //   2. strided inverse passes over the top lg2 index bits with the n2 table: the first multiplies by the inverse twiddle
+    //      matrix as it loads (pairs in data layout, built from the transposed index), the last applies n^-1 and canonicalises;
+    //      work -> dst.
+    // Single modulus, 64-bit, p below the lazy inverse limit, shapes whose pass splits fit the tile; *launched = 0 otherwise.
+    cudaError_t fast_fourstep_inverse(const uint64_t* rows_in, uint64_t* work, uint64_t* dst, const uint64_t* n1_table,
+                                      const uint64_t* n2_table, const uint64_t* w_table, void* w_pairs_ws, uint64_t p, uint64_t ninv,
+                                      int n_power, int lg1, int lg2, int batch, cudaStream_t st, int* launched,
+                                      void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t))
+    {
+        using T = uint64_t;
+        *launched = 0;
+        if (lg1 < 5 || lg1 > 8 || n_power != lg1 + lg2 || n_power < 12) return cudaSuccess;
+        if (!(p < kFastModulusLimit) || p < 5) return cudaSuccess;
+        if ((reinterpret_cast<uintptr_t>(rows_in) | reinterpret_cast<uintptr_t>(work) | reinterpret_cast<uintptr_t>(dst)) & 15) return cudaSuccess;
+        // split of the lg2 strided stages (executed low bits first)
+        int da, db;
+        if (lg2 <= 8)
+        {
+            da = lg2;
+            db = 0;
+            if (da < 4 || 12 - da > lg1) return cudaSuccess;
+        }
+        else
+        {
+            da = lg2 - 8;
+            if (da < 12 - lg1) da = 12 - lg1;
+            if (da < 4) da = 4;
+            db = lg2 - da;
+            if (da > 8 || db < 4 || db > 8) return cudaSuccess;
+        }
+        FastArgs<T> a{};
+        a.p = p;
+        a.ninv_w = ninv;
+        a.ninv_wq = shoup_companion(ninv, p);
+        a.pbits = 64 - __builtin_clzll((unsigned long long) p);
+        {
+            const unsigned __int128 m = (((unsigned __int128) 1) << (63 + a.pbits)) / (unsigned __int128) p;
+            a.mu = (m >> 64) ? ~0ull : (uint64_t) m;
+        }
+        a.plus = 0;
+        const long long N = 1LL << n_power;
+        cudaError_t e;
+        prof_begin(0, st);
+        w_pairs_kernel<<<(unsigned) ((N + 255) / 256), 256, 0, st>>>(w_table, reinterpret_cast<Twiddle<T>*>(w_pairs_ws), N, p, a.mu, a.pbits, lg1, lg2);
+        prof_end(st);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        int kind = 1;
+        {
+            // row phase: the array as (batch * N / 2048) chunks of 2048 elements, transforms of 2^lg1 inside
+            FastArgs<T> s = a;
+            s.in = rows_in;
+            s.out = work;
+            s.table = n1_table;
+            s.n = 11;
+            s.n_tw = lg1;
+            s.lo = 0;
+            s.first = 1;
+            s.last = 0;
+            const long long chunks = ((long long) batch << n_power) >> 11;
+            if (chunks > 0x7fffffffLL) return cudaSuccess;
+            s.batch = (int) chunks;
+            s.work = (chunks + 1) >> 1;
+            prof_begin(kind++, st);
+            switch (lg1)
+            {
+                case 5: e = launch_fast<Shape<T, true, 1, false, 1, 4, 12, 1, 5>>(s, st); break;
+                case 6: e = launch_fast<Shape<T, true, 1, false, 2, 4, 12, 1, 6>>(s, st); break;
+                case 7: e = launch_fast<Shape<T, true, 1, false, 3, 4, 12, 1, 7>>(s, st); break;
+                default: e = launch_fast<Shape<T, true, 1, false, 4, 4, 12, 1, 8>>(s, st); break;
+            }
+            prof_end(st);
+            if (e == cudaErrorNotSupported) return cudaSuccess;
+            if (e != cudaSuccess) return e;
+        }
+        auto strided = [&](int d, int lo, bool wmul, bool last, const T* src, T* out) -> cudaError_t
+        {
+            FastArgs<T> s = a;
+            s.in = src;
+            s.out = out;
+            s.table = n2_table;
+            s.n = n_power;
+            s.lo = lo;
+            s.first = 0;
+            s.last = last ? 1 : 0;
+            s.batch = batch;
+            s.w_pairs = w_pairs_ws;
+            s.work = ((long long) batch << (lo - (12 - d))) << (n_power - lo - d);
+            s.rr = (!wmul && n_power == lo + d && lo > 10) ? 1 : 0;
+            prof_begin(kind++, st);
+            cudaError_t r;
+            if (wmul)
+                switch (d)
+                {
+                    case 4: r = launch_fast<Shape<T, true, 1, true, 4, 0, 12, 0>, true>(s, st); break;
+                    case 5: r = launch_fast<Shape<T, true, 1, true, 3, 2, 12, 0>, true>(s, st); break;
+                    case 6: r = launch_fast<Shape<T, true, 1, true, 3, 3, 12, 0>, true>(s, st); break;
+                    case 7: r = launch_fast<Shape<T, true, 1, true, 4, 3, 12, 0>, true>(s, st); break;
+                    default: r = launch_fast<Shape<T, true, 1, true, 4, 4, 12, 0>, true>(s, st); break;
+                }
+            else
+                r = launch_strided<T, true, 1>(d, s, st);
+            prof_end(st);
+            return r;
+        };
+        if (db == 0)
+            e = strided(da, lg1, true, true, work, dst);
+        else
+        {
+            e = strided(da, lg1, true, false, work, dst);
+            if (e == cudaSuccess) e = strided(db, lg1 + da, false, true, dst, dst);
+        }
+        if (e != cudaSuccess) return e; // (cudaErrorNotSupported cannot appear here: the row pass already built a tensor map)
+        *launched = kind;
         return cudaSuccess;
     }
 

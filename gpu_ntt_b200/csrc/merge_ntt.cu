@@ -590,6 +590,10 @@ namespace gpuntt_b200
 
     // merge_fast.cu
     int fast_describe(int n_power, int element_bits, char* buf, size_t len);
+    cudaError_t fast_fourstep_inverse(const uint64_t* rows_in, uint64_t* work, uint64_t* dst, const uint64_t* n1_table,
+                                      const uint64_t* n2_table, const uint64_t* w_table, void* w_pairs_ws, uint64_t p, uint64_t ninv,
+                                      int n_power, int lg1, int lg2, int batch, cudaStream_t st, int* launched,
+                                      void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t));
     cudaError_t fast_fourstep_columns(const uint64_t* in, uint64_t* out, const uint64_t* n1_table, const uint64_t* w_table,
                                       void* w_pairs_ws, uint64_t p, int n_power, int lg1, int lg2, int batch, cudaStream_t st,
                                       int* launched, void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t));

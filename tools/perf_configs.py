@@ -83,7 +83,7 @@ def merge_case(name, logn, batch, bits, poly, iters, inverse=False, both=False):
     torch.cuda.empty_cache()
 
 
-def fourstep_case(name, logn, batch, iters, contract):
+def fourstep_case(name, logn, batch, iters, contract, inverse=False):
     n1, n2 = capi.fourstep_shape(logn)
     p = 576460753175838721 if logn == 24 else 576460752303415297
     rng = np.random.default_rng(1)
@@ -96,7 +96,10 @@ def fourstep_case(name, logn, batch, iters, contract):
     out = torch.empty_like(x) if contract == capi.FOURSTEP_REFERENCE else None
 
     def fn():
-        capi.fourstep_ntt(x, t1, t2, w, p, logn, io_contract=contract, out=out)
+        if inverse:
+            capi.fourstep_ntt(x, t1, t2, w, p, logn, direction=capi.INVERSE, mod_inverse=12345, io_contract=contract, out=out)
+        else:
+            capi.fourstep_ntt(x, t1, t2, w, p, logn, io_contract=contract, out=out)
     ms = time_ms(fn, iters, warm=2)
     lib = capi.lib()
     lib.gpuntt_b200_set_profiling(1)
@@ -107,7 +110,7 @@ def fourstep_case(name, logn, batch, iters, contract):
     bytes_alg = 2 * (1 << logn) * 8 * batch
     gbs = bytes_alg / (ms * 1e-3) / 1e9
     print(json.dumps({"case": name, "logn": logn, "batch": batch, "bits": 64, "n1": n1, "n2": n2,
-                      "contract": "fused" if contract == capi.FOURSTEP_FUSED else "reference", "ms": round(ms, 4),
+                      "contract": "fused" if contract == capi.FOURSTEP_FUSED else "reference", "op": "inv" if inverse else "fwd", "ms": round(ms, 4),
                       "ntt_per_s": round(batch / (ms * 1e-3), 2), "alg_GBps": round(gbs, 1),
                       "frac_hbm": round(gbs / peak(), 4), "launches_kind_ms": launches}), flush=True)
     del x, w, out
@@ -127,6 +130,8 @@ def main():
     merge_case("C3 fwd", 14, 4096, 32, X_N_minus, it)
     fourstep_case("C4 4-step fused", 24, 16, max(2, it // 4), capi.FOURSTEP_FUSED)
     fourstep_case("C4 4-step reference contract", 24, 16, max(2, it // 4), capi.FOURSTEP_REFERENCE)
+    fourstep_case("C4 4-step inverse fused", 24, 16, max(2, it // 4), capi.FOURSTEP_FUSED, inverse=True)
+    fourstep_case("4-step fused logN=20", 20, 64, max(2, it // 4), capi.FOURSTEP_FUSED)
     if not args.quick:
         for logn in (12, 13, 14, 15, 17, 18, 20, 22, 24):
             merge_case(f"u64 logN={logn}", logn, max(1, (1 << 26) >> logn), 64, X_N_minus, it)
