@@ -19,6 +19,7 @@
 //     instead of once per polynomial.
 // Replaces ForwardCore/InverseCore of the reference (src/lib/ntt_merge/ntt.cu:435-1318) for
 // the plans listed in fast_supported().
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cuda.h>
@@ -666,19 +667,28 @@ namespace gpuntt_b200
     // returns cudaErrorNotSupported when the tensor maps cannot be built (caller falls back)
     template <typename S, bool WMUL = false> static cudaError_t launch_fast(const FastArgs<typename S::T>& args, cudaStream_t st)
     {
-        static int blocks_per_sm = -1, sms = 0; // per process; devices on one box are identical
+        // per device (the shared-memory opt-in is a per-device function attribute); a race between first callers only
+        // repeats idempotent work
+        constexpr int kMaxDev = 64;
+        static std::atomic<int> cached_bps[kMaxDev];
+        static std::atomic<int> cached_sms[kMaxDev];
         auto kern = fast_pass_kernel<S, WMUL>;
-        if (blocks_per_sm < 0)
+        int dev = 0;
+        cudaError_t ge = cudaGetDevice(&dev);
+        if (ge != cudaSuccess) return ge;
+        if (dev < 0 || dev >= kMaxDev) return cudaErrorNotSupported;
+        int blocks_per_sm = cached_bps[dev].load(std::memory_order_acquire), sms = cached_sms[dev].load(std::memory_order_acquire);
+        if (blocks_per_sm <= 0 || sms <= 0)
         {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM);
             if (e != cudaSuccess) return e;
-            int dev = 0;
-            cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             int bps = 0;
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kFastThreads, S::SMEM);
             if (e != cudaSuccess) return e;
             blocks_per_sm = bps > 0 ? bps : 1;
+            cached_sms[dev].store(sms, std::memory_order_release);
+            cached_bps[dev].store(blocks_per_sm, std::memory_order_release);
         }
         alignas(64) CUtensorMap map_in, map_out;
         if (!make_map<S>(&map_in, args.in, args.n, args.lo, args.batch)) return cudaErrorNotSupported;
