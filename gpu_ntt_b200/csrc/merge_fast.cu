@@ -83,6 +83,18 @@ namespace gpuntt_b200
                      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
                      : "memory");
     }
+    __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar)
+    {
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+                     "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+                     : "memory");
+    }
+    __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t src)
+    {
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(map), "r"(c0),
+                     "r"(c1), "r"(c2), "r"(c3), "r"(src)
+                     : "memory");
+    }
     __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src)
     {
         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0),
@@ -131,7 +143,7 @@ namespace gpuntt_b200
         static constexpr int G1 = 1 << (KTW - LB1 - R1), G2 = 1 << (KTW - LB2 - R2); // twiddle groups
         static constexpr int TW1 = ((1 << R1) - 1) * G1, TW2 = ((1 << R2) - 1) * G2;
         static constexpr int TW_SMEM = (TW1 + TW2) * (int) sizeof(Twiddle<T>);
-        static constexpr int SMEM = 2 * TILE_SMEM + TW_SMEM + 64 + 1024; // + slack to align the tiles to 1 KiB
+        static constexpr int SMEM = 2 * TILE_SMEM + TW_SMEM + 128 + 1024; // barriers, segment constants + slack to align the tiles to 1 KiB
         static_assert(LB2 == 0 || LB2 >= CB, "low round must start at bit 0 or on a row boundary");
         static_assert(LB1 >= CB, "high round must start on a row boundary");
     };
@@ -164,6 +176,14 @@ namespace gpuntt_b200
         int n, lo, plus, first, last, batch, rr;
         int n_tw; // transform size (log2) for twiddle indexing when it differs from the layout size n (0: n)
         long long work; // total tiles of this pass
+        // RNS kernels (polynomial b uses modulus slot b % mod_count, ntt.cu:613-619 of the reference): `batch` is then the
+        // number of polynomials PER SLOT, mod_dev the device array of {value, bit, mu} triples, ninv_dev the per-slot
+        // N^-1; policy_flag/want_policy: a kernel returns at once unless *policy_flag == want_policy (the moduli live on
+        // the device, so the lazy-policy and the exact-policy kernel are both enqueued and the data decides)
+        const T* mod_dev;
+        const T* ninv_dev;
+        const int* policy_flag;
+        int mod_count, want_policy;
         const void* w_pairs; // WMUL kernels: Twiddle<T>[N], the 4-step twiddle matrix with Shoup companions
     };
 
@@ -369,7 +389,14 @@ namespace gpuntt_b200
     //   STRIDED:   w = poly * 2^(lo-C) + column chunk            (any CTA, any order)
     //   !STRIDED:  w = range * tiles_per_range + polynomial group (range-major, so a CTA's
     //              contiguous share of the work stays inside one or two ranges)
-    template <typename S, bool WMUL = false>
+    template <typename T> struct SegConsts // per-segment modulus data of the RNS kernels, in shared memory
+    {
+        T p, ninv_w, ninv_wq;
+        uint64_t mu;
+        int pbits;
+    };
+
+    template <typename S, bool WMUL = false, bool RNS = false>
     __global__ void __launch_bounds__(kFastThreads, (!S::INV && S::POL == 2) ? (S::STRIDED ? GPUNTT_FAST_P0_BLOCKS : GPUNTT_FAST_P1_BLOCKS) : 2)
         fast_pass_kernel(const FastArgs<typename S::T> a, const __grid_constant__ CUtensorMap map_in,
                          const __grid_constant__ CUtensorMap map_out)
@@ -384,6 +411,12 @@ namespace gpuntt_b200
 
         const int tid = threadIdx.x;
         const int n = a.n;
+        if constexpr (RNS)
+        {
+            if (a.policy_flag != nullptr && *a.policy_flag != a.want_policy) return; // the other arithmetic policy's kernel does this pass
+        }
+        SegConsts<T>* segc = reinterpret_cast<SegConsts<T>*>(bars + 4);
+        const int nranges = S::STRIDED ? (1 << (a.n - a.lo - S::D)) : (S::NT ? 1 : (1 << (a.n - S::KC)));
         // Work assignment.  Default: a contiguous share of the work items (a CTA stays inside one or two twiddle ranges).
         // a.rr (strided passes with ONE range and a long row stride): round robin, item(i) = blockIdx + i * grid, with the
         // items ordered column-chunk-major, so the tiles in flight across the chip at any moment are the polynomials
@@ -411,11 +444,15 @@ namespace gpuntt_b200
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             fence_async();
         }
-        const typename ModOf<S>::type M(a.p);
-        const Twiddle<T> ninv{a.ninv_w, a.ninv_wq};
+        typename ModOf<S>::type M(a.p);
+        Twiddle<T> ninv{a.ninv_w, a.ninv_wq};
+        const T* seg_table = a.table;
+        T seg_p = a.p;
+        uint64_t seg_mu = a.mu;
+        int seg_pbits = a.pbits;
         // first pass of a cyclic transform: slot 0 of every stage of the high round is table[0]; when that is 1
         // (it is omega^0 in the reference's tables) those butterflies need no multiply
-        const bool triv = S::STRIDED && !S::INV && !a.plus && a.first && (a.lo + S::D == a.n) && a.table[0] == T(1); // inputs canonical by contract
+        bool triv = S::STRIDED && !S::INV && !a.plus && a.first && (a.lo + S::D == a.n) && a.table[0] == T(1); // inputs canonical by contract
         uint32_t uses0 = 0, uses1 = 0; // how often each buffer has been filled so far (phase tracking)
 
         long long w = w_begin;
@@ -423,15 +460,52 @@ namespace gpuntt_b200
         {
             // ---- segment: a run of tiles sharing one twiddle set
             long long seg_end = w_end;
-            int range = 0;
+            int range = 0, mslot = 0;
             {
-                range = (int) (w / tiles_per_range);
-                const long long re = (long long) (range + 1) * tiles_per_range;
+                const long long sg = w / tiles_per_range; // RNS: (modulus slot, range), slot-major
+                const long long re = (sg + 1) * tiles_per_range;
                 if (re < seg_end) seg_end = re;
+                if constexpr (RNS)
+                {
+                    mslot = (int) (sg / nranges);
+                    range = (int) (sg % nranges);
+                }
+                else
+                    range = (int) sg;
             }
             const int ntiles = (int) ((seg_end - w + step - 1) / step);
 
             __syncthreads(); // everybody is done with the previous segment's twiddles and buffers
+            if constexpr (RNS)
+            {
+                if (tid == 0)
+                {
+                    SegConsts<T> c;
+                    c.p = a.mod_dev[3 * mslot];
+                    if constexpr (sizeof(T) == 8)
+                    {
+                        c.pbits = 64 - __clzll((long long) c.p);
+                        const unsigned __int128 m = (((unsigned __int128) 1) << (63 + c.pbits)) / (unsigned __int128) c.p;
+                        c.mu = (m >> 64) ? ~0ull : (uint64_t) m;
+                    }
+                    else
+                    {
+                        c.pbits = 32 - __clz((int) c.p);
+                        c.mu = ~0ull / (uint64_t) c.p;
+                    }
+                    c.ninv_w = S::INV ? a.ninv_dev[mslot] : T(0);
+                    c.ninv_wq = S::INV ? shoup_companion(c.ninv_w, c.p) : T(0);
+                    *segc = c;
+                }
+                __syncthreads();
+                seg_p = segc->p;
+                seg_mu = segc->mu;
+                seg_pbits = segc->pbits;
+                ninv = Twiddle<T>{segc->ninv_w, segc->ninv_wq};
+                seg_table = a.table + ((size_t) mslot << a.n);
+                M = typename ModOf<S>::type(seg_p);
+                triv = S::STRIDED && !S::INV && !a.plus && a.first && (a.lo + S::D == a.n) && seg_table[0] == T(1);
+            }
             {
                 // (w, w') pairs for both rounds, slot-major: entry (slot, group) at slot*G + group
                 const int j0 = S::STRIDED ? (range << S::D) : (S::NT ? 0 : (range << S::KC)); // index (>> lo) of the tile's first row
@@ -449,11 +523,11 @@ namespace gpuntt_b200
                     const int s = ntw - 1 - a.lo - (rb0 + ab);
                     const int J = j0 | (group << (LB + R - S::C));
                     const long long idx = ((long long) a.plus << s) + (J >> (rb0 + ab + 1)) + x;
-                    const T wv = a.table[idx];
+                    const T wv = seg_table[idx];
                     if constexpr (sizeof(T) == 8)
-                        (hi ? tw1 : tw2)[ii] = Twiddle<T>{wv, shoup_companion_mu(wv, a.p, a.mu, a.pbits)};
+                        (hi ? tw1 : tw2)[ii] = Twiddle<T>{wv, shoup_companion_mu(wv, seg_p, seg_mu, seg_pbits)};
                     else
-                        (hi ? tw1 : tw2)[ii] = Twiddle<T>{wv, shoup_companion_mu32(wv, a.p, a.mu)};
+                        (hi ? tw1 : tw2)[ii] = Twiddle<T>{wv, shoup_companion_mu32(wv, seg_p, seg_mu)};
                 }
             }
             __syncthreads();
@@ -476,13 +550,17 @@ namespace gpuntt_b200
                             const long long within = ww % tiles_per_range;
                             const long long poly = a.rr ? within % a.batch : within >> ccb;
                             const long long cc = a.rr ? within / a.batch : (within & ((1LL << ccb) - 1));
+                            const long long gp = RNS ? poly * a.mod_count + mslot : poly; // polynomial in the caller's array
                             tma_load_3d(dst, &map_in, 0, (int) (cc << (S::C - S::CB)),
-                                        (int) ((poly << (a.n - a.lo)) + ((long long) range << S::D)), bar);
+                                        (int) ((gp << (a.n - a.lo)) + ((long long) range << S::D)), bar);
                         }
                         else
                         {
                             const long long grp = ww % tiles_per_range;
-                            tma_load_3d(dst, &map_in, 0, range << (S::KC - S::CB), (int) (grp << S::NPLOG), bar);
+                            if constexpr (RNS) // {row, rows of a polynomial, modulus slot, polynomial within the slot}
+                                tma_load_4d(dst, &map_in, 0, range << (S::KC - S::CB), mslot, (int) (grp << S::NPLOG), bar);
+                            else
+                                tma_load_3d(dst, &map_in, 0, range << (S::KC - S::CB), (int) (grp << S::NPLOG), bar);
                         }
                     }
                 };
@@ -504,13 +582,17 @@ namespace gpuntt_b200
                             const long long within = ww % tiles_per_range;
                             const long long poly = a.rr ? within % a.batch : within >> ccb;
                             const long long cc = a.rr ? within / a.batch : (within & ((1LL << ccb) - 1));
+                            const long long gp = RNS ? poly * a.mod_count + mslot : poly;
                             tma_store_3d(&map_out, 0, (int) (cc << (S::C - S::CB)),
-                                         (int) ((poly << (a.n - a.lo)) + ((long long) range << S::D)), src);
+                                         (int) ((gp << (a.n - a.lo)) + ((long long) range << S::D)), src);
                         }
                         else
                         {
                             const long long grp = ww % tiles_per_range;
-                            tma_store_3d(&map_out, 0, range << (S::KC - S::CB), (int) (grp << S::NPLOG), src);
+                            if constexpr (RNS)
+                                tma_store_4d(&map_out, 0, range << (S::KC - S::CB), mslot, (int) (grp << S::NPLOG), src);
+                            else
+                                tma_store_3d(&map_out, 0, range << (S::KC - S::CB), (int) (grp << S::NPLOG), src);
                         }
                         bulk_commit();
                         bulk_wait_read0(); // this buffer may be overwritten again
@@ -624,14 +706,16 @@ namespace gpuntt_b200
     // Tensor map of the [batch][N] array for one pass shape.
     //   STRIDED: 2-D view {2^lo (adjacent elements of a matrix row), batch * 2^D rows}; box {2^C, 2^D}
     //   else:    3-D view {2^CB (one 128-byte row), N / 2^CB rows, batch}; box {2^CB, 2^(KC-CB), 2^NPLOG}
-    template <typename S> static bool make_map(CUtensorMap* map, const void* base, int n, int lo, int batch)
+    //   RNS (mod_count > 0; batch = polynomials per slot): strided maps see batch * mod_count polynomials, contiguous
+    //   maps are 4-D {row, rows, slot, polynomial within the slot} so a tile holds polynomials of ONE modulus.
+    template <typename S> static bool make_map(CUtensorMap* map, const void* base, int n, int lo, int batch, int mod_count = 0)
     {
         using T = typename S::T;
         PFN_cuTensorMapEncodeTiled enc = get_encode();
         if (!enc) return false;
         const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32;
-        cuuint64_t gdim[3], gstride[2];
-        cuuint32_t box[3], estr[3] = {1, 1, 1};
+        cuuint64_t gdim[4], gstride[3];
+        cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
         int rank;
         if constexpr (S::STRIDED)
         {
@@ -639,7 +723,7 @@ namespace gpuntt_b200
             rank = 3;
             gdim[0] = 1ull << S::CB;
             gdim[1] = 1ull << (lo - S::CB);
-            gdim[2] = (cuuint64_t) batch << (n - lo);
+            gdim[2] = ((cuuint64_t) batch * (mod_count > 0 ? mod_count : 1)) << (n - lo);
             gstride[0] = 128;
             gstride[1] = (cuuint64_t) sizeof(T) << lo;
             box[0] = 1u << S::CB;
@@ -651,12 +735,24 @@ namespace gpuntt_b200
             rank = 3;
             gdim[0] = 1ull << S::CB;
             gdim[1] = 1ull << (n - S::CB);
-            gdim[2] = (cuuint64_t) batch;
             gstride[0] = 128;
             gstride[1] = (cuuint64_t) sizeof(T) << n;
             box[0] = 1u << S::CB;
             box[1] = 1u << (S::KC - S::CB);
-            box[2] = 1u << S::NPLOG;
+            if (mod_count > 0)
+            {
+                rank = 4;
+                gdim[2] = (cuuint64_t) mod_count;
+                gdim[3] = (cuuint64_t) batch;
+                gstride[2] = ((cuuint64_t) sizeof(T) << n) * (cuuint64_t) mod_count;
+                box[2] = 1;
+                box[3] = 1u << S::NPLOG;
+            }
+            else
+            {
+                gdim[2] = (cuuint64_t) batch;
+                box[2] = 1u << S::NPLOG;
+            }
         }
         CUresult r = enc(map, dt, (cuuint32_t) rank, const_cast<void*>(base), gdim, gstride, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -665,14 +761,14 @@ namespace gpuntt_b200
     }
 
     // returns cudaErrorNotSupported when the tensor maps cannot be built (caller falls back)
-    template <typename S, bool WMUL = false> static cudaError_t launch_fast(const FastArgs<typename S::T>& args, cudaStream_t st)
+    template <typename S, bool WMUL = false, bool RNS = false> static cudaError_t launch_fast(const FastArgs<typename S::T>& args, cudaStream_t st)
     {
         // per device (the shared-memory opt-in is a per-device function attribute); a race between first callers only
         // repeats idempotent work
         constexpr int kMaxDev = 64;
         static std::atomic<int> cached_bps[kMaxDev];
         static std::atomic<int> cached_sms[kMaxDev];
-        auto kern = fast_pass_kernel<S, WMUL>;
+        auto kern = fast_pass_kernel<S, WMUL, RNS>;
         int dev = 0;
         cudaError_t ge = cudaGetDevice(&dev);
         if (ge != cudaSuccess) return ge;
@@ -691,10 +787,11 @@ namespace gpuntt_b200
             cached_bps[dev].store(blocks_per_sm, std::memory_order_release);
         }
         alignas(64) CUtensorMap map_in, map_out;
-        if (!make_map<S>(&map_in, args.in, args.n, args.lo, args.batch)) return cudaErrorNotSupported;
+        const int mc = RNS ? args.mod_count : 0;
+        if (!make_map<S>(&map_in, args.in, args.n, args.lo, args.batch, mc)) return cudaErrorNotSupported;
         if (args.in == args.out)
             map_out = map_in;
-        else if (!make_map<S>(&map_out, args.out, args.n, args.lo, args.batch))
+        else if (!make_map<S>(&map_out, args.out, args.n, args.lo, args.batch, mc))
             return cudaErrorNotSupported;
         long long grid = (long long) sms * blocks_per_sm;
         if (grid > args.work) grid = args.work;
@@ -904,6 +1001,131 @@ namespace gpuntt_b200
         }
         return cudaSuccess;
     }
+
+    // ------------------------------------------------------------------ RNS form on the tuned kernels
+    // flag = 0 when every modulus allows the lazy policy of this direction, else 1 (one warp)
+    template <typename T> __global__ void rns_policy_kernel(const T* __restrict__ mod_dev, int mod_count, int inverse, int* flag)
+    {
+        int bad = 0;
+        for (int i = threadIdx.x; i < mod_count; i += 32)
+        {
+            const uint64_t p = (uint64_t) mod_dev[3 * i];
+            const bool ok = inverse ? (p < kFastModulusLimit) : (p >= kF60ModulusMin && p < kF60ModulusLimit);
+            bad |= ok ? 0 : 1;
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        if (threadIdx.x == 0) *flag = bad ? 1 : 0;
+    }
+
+    template <typename T, bool INV, int POL> static cudaError_t launch_strided_rns(int d, const FastArgs<T>& args, cudaStream_t st)
+    {
+        constexpr int K = sizeof(T) == 8 ? 12 : 13;
+        switch (d)
+        {
+            case 4: return launch_fast<Shape<T, INV, POL, true, 4, 0, K, 0>, false, true>(args, st);
+            case 5: return launch_fast<Shape<T, INV, POL, true, 3, 2, K, 0>, false, true>(args, st);
+            case 6: return launch_fast<Shape<T, INV, POL, true, 3, 3, K, 0>, false, true>(args, st);
+            case 7: return launch_fast<Shape<T, INV, POL, true, 4, 3, K, 0>, false, true>(args, st);
+            case 8: return launch_fast<Shape<T, INV, POL, true, 4, 4, K, 0>, false, true>(args, st);
+            default: return cudaErrorNotSupported;
+        }
+    }
+
+    // GPU_NTT / GPU_INTT RNS overloads (ntt.cu:2560-3058) for the two-pass ring sizes (64-bit 2^12..2^16, 32-bit
+    // 2^14..2^18), batch a multiple of mod_count, no order indirection.  The moduli are device data, so for 64-bit
+    // both the lazy-policy and the exact-policy kernel of every pass are enqueued and a device flag picks one.
+    // flag_ws: one int of device scratch.  *launched = 0 when not covered.
+    template <typename T>
+    cudaError_t fast_merge_rns(const T* in, T* out, const T* table, const T* mod_dev, const T* ninv_dev, int mod_count, int n_power,
+                               int plus, bool inverse, int batch, int* flag_ws, cudaStream_t st, int* launched,
+                               void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t))
+    {
+        *launched = 0;
+        constexpr int bits = (int) sizeof(T) * 8;
+        constexpr int K = bits == 64 ? 12 : 13;
+        if (!fast_supported(n_power, bits) || mod_count < 1 || batch % mod_count != 0) return cudaSuccess;
+        const FastPlan pl = make_fast_plan(n_power, bits);
+        if (pl.npass != 2 || pl.d[0] < 4) return cudaSuccess;
+        if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return cudaSuccess;
+        FastArgs<T> a{};
+        a.table = table;
+        a.p = (T) ((1ull << (bits - 5)) + 1); // placeholder until the first segment reads its modulus
+        a.n = n_power;
+        a.plus = plus;
+        a.batch = batch / mod_count;
+        a.mod_count = mod_count;
+        a.mod_dev = mod_dev;
+        a.ninv_dev = ninv_dev;
+        a.policy_flag = nullptr;
+        int kind = 1;
+        if (bits == 64)
+        {
+            prof_begin(0, st);
+            rns_policy_kernel<T><<<1, 32, 0, st>>>(mod_dev, mod_count, inverse ? 1 : 0, flag_ws);
+            prof_end(st);
+            cudaError_t pe = cudaGetLastError();
+            if (pe != cudaSuccess) return pe;
+            a.policy_flag = flag_ws;
+        }
+        for (int k = 0; k < pl.npass; k++)
+        {
+            const int i = inverse ? pl.npass - 1 - k : k;
+            FastArgs<T> s = a;
+            s.in = (k == 0) ? in : out;
+            s.out = out;
+            s.lo = pl.lo[i];
+            s.first = (k == 0);
+            s.last = (k == pl.npass - 1);
+            cudaError_t e = cudaSuccess;
+            for (int variant = 0; variant < (bits == 64 ? 2 : 1) && e == cudaSuccess; variant++)
+            {
+                const bool lazy = bits == 64 && variant == 0;
+                s.want_policy = lazy ? 0 : 1;
+                prof_begin(kind, st);
+                if (pl.strided[i])
+                {
+                    const int c = K - pl.d[i];
+                    s.work = ((long long) mod_count * s.batch) << (pl.lo[i] - c); // one range per slot in a two-pass plan
+                    if constexpr (bits == 64)
+                    {
+                        if (lazy)
+                            e = inverse ? launch_strided_rns<T, true, 1>(pl.d[i], s, st) : launch_strided_rns<T, false, 2>(pl.d[i], s, st);
+                        else
+                            e = inverse ? launch_strided_rns<T, true, 0>(pl.d[i], s, st) : launch_strided_rns<T, false, 0>(pl.d[i], s, st);
+                    }
+                    else
+                        e = inverse ? launch_strided_rns<T, true, 0>(pl.d[i], s, st) : launch_strided_rns<T, false, 0>(pl.d[i], s, st);
+                }
+                else
+                {
+                    const long long tpr = (s.batch + 1) >> 1;
+                    s.work = ((long long) mod_count * tpr) << (n_power - (K - 1));
+                    if constexpr (bits == 64)
+                    {
+                        if (lazy)
+                            e = inverse ? launch_fast<Shape<T, true, 1, false, 4, 4, 12, 1>, false, true>(s, st)
+                                        : launch_fast<Shape<T, false, 2, false, 4, 4, 12, 1>, false, true>(s, st);
+                        else
+                            e = inverse ? launch_fast<Shape<T, true, 0, false, 4, 4, 12, 1>, false, true>(s, st)
+                                        : launch_fast<Shape<T, false, 0, false, 4, 4, 12, 1>, false, true>(s, st);
+                    }
+                    else
+                        e = inverse ? launch_fast<Shape<T, true, 0, false, 5, 5, 13, 1>, false, true>(s, st)
+                                    : launch_fast<Shape<T, false, 0, false, 5, 5, 13, 1>, false, true>(s, st);
+                }
+                prof_end(st);
+            }
+            kind++;
+            if (e == cudaErrorNotSupported && k == 0) return cudaSuccess;
+            if (e != cudaSuccess) return e;
+        }
+        *launched = pl.npass;
+        return cudaSuccess;
+    }
+    template cudaError_t fast_merge_rns<uint64_t>(const uint64_t*, uint64_t*, const uint64_t*, const uint64_t*, const uint64_t*, int, int, int,
+                                                  bool, int, int*, cudaStream_t, int*, void (*)(int, cudaStream_t), void (*)(cudaStream_t));
+    template cudaError_t fast_merge_rns<uint32_t>(const uint32_t*, uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, int, int, int,
+                                                  bool, int, int*, cudaStream_t, int*, void (*)(int, cudaStream_t), void (*)(cudaStream_t));
 
     // (w, w') pairs of the 4-step twiddle matrix, once per call (the batch shares it)
     // t_lo > 0: entry i comes from the transposed index ((i mod 2^t_lo) << t_hi) | (i >> t_lo) (4-step inverse: the data

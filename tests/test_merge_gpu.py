@@ -145,9 +145,9 @@ def _is_prime(n):
     return True
 
 
-def rns_primes(bits, logn, count):
+def rns_primes(bits, logn, count, top_log2=None):
     m = 1 << (logn + 1)
-    top = (1 << (61 if bits == 64 else 29)) // m
+    top = (1 << (top_log2 or (61 if bits == 64 else 29))) // m
     out = []
     k = top
     while len(out) < count:
@@ -168,9 +168,31 @@ def test_rns_form(bits, logn, batch, mod_count):
     """RNS overloads: polynomial b uses modulus[b % mod_count], table slice (b % mod_count) << n_power,
     mod_inverse[b % mod_count] (ntt.cu:613-619, 672-673, 1225-1226).  61-/29-bit primes exercise the top
     of the supported modulus range."""
+    _rns_roundtrip(bits, logn, batch, mod_count, rns_primes(bits, logn, mod_count))
+
+
+@pytest.mark.parametrize("bits,logn,batch,mod_count,tops", [
+    (64, 12, 6, 3, (59, 59, 59)),        # every modulus allows the lazy policies -> F60 / lazy inverse kernels
+    (64, 16, 8, 4, (59, 58, 50, 45)),
+    (64, 14, 4, 2, (59, 61)),            # one modulus outside -> the exact-policy kernels do the passes
+    (64, 16, 6, 2, (61, 61)),
+    (64, 13, 9, 3, (59, 59, 59)),        # odd number of polynomials per slot (ragged last tile)
+    (32, 14, 6, 3, (29, 29, 29)),
+    (32, 16, 4, 2, (29, 25)),
+])
+def test_rns_form_tuned_kernels(bits, logn, batch, mod_count, tops):
+    """RNS overloads on the tuned kernels (two-pass ring sizes, batch a multiple of mod_count): per-slot modulus,
+    table slice and N^-1 are read per segment on the device, and for 64-bit data a device flag picks the lazy or
+    the exact arithmetic kernels."""
+    primes = [rns_primes(bits, logn, 1 + i, t)[i] for i, t in enumerate(tops)]
+    assert len({p for p, _ in primes}) == mod_count
+    _rns_roundtrip(bits, logn, batch, mod_count, primes)
+    # the inverse call was the last one: policy kernel + (lazy, exact) x 2 passes for 64-bit, 2 passes for 32-bit
+    assert capi.lib().gpuntt_b200_last_launch_count() == (5 if bits == 64 else 2)
+
+
+def _rns_roundtrip(bits, logn, batch, mod_count, primes):
     n = 1 << logn
-    primes = rns_primes(bits, logn, mod_count)
-    np_dt = np.uint64 if bits == 64 else np.uint32
     fwd_tab = np.zeros(mod_count << logn, dtype=np.uint64)
     inv_tab = np.zeros(mod_count << logn, dtype=np.uint64)
     mods = np.zeros((mod_count, 3), dtype=np.uint64)

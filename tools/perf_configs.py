@@ -83,6 +83,33 @@ def merge_case(name, logn, batch, bits, poly, iters, inverse=False, both=False):
     torch.cuda.empty_cache()
 
 
+def rns_case(name, logn, batch, mod_count, iters, top_log2=59):
+    """RNS forward (GPU_NTT RNS overload): mod_count NTT-friendly primes below 2^top_log2, random tables (timing only)."""
+    sys.path.insert(0, os.path.join(ROOT))
+    from tests.test_merge_gpu import rns_primes
+    primes = [p for p, _ in rns_primes(64, logn, mod_count, top_log2)]
+    rng = np.random.default_rng(2)
+    n = 1 << logn
+    tab = np.concatenate([rng.integers(1, p, n, dtype=np.uint64) for p in primes])
+    mods = np.array([[p, p.bit_length(), 0] for p in primes], dtype=np.uint64).ravel()
+    d_tab, d_mods = dev(tab, 64), dev(mods, 64)
+    x = torch.randint(0, min(primes), (batch, n), dtype=torch.int64, device="cuda")
+    res = {}
+    for label, force in (("tuned", 0), ("generic", 1)):
+        capi.lib().gpuntt_b200_force_generic_path(force)
+
+        def fn():
+            capi.merge_ntt(in_ptr=x.data_ptr(), out_ptr=x.data_ptr(), table_ptr=d_tab.data_ptr(), n_power=logn, batch=batch,
+                           element_bits=64, direction=capi.FORWARD, reduction_poly=X_N_plus, mod_count=mod_count,
+                           modulus_dev=d_mods.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+        res[label] = round(time_ms(fn, iters), 4)
+    capi.lib().gpuntt_b200_force_generic_path(0)
+    gbs = 2 * n * 8 * batch / (res["tuned"] * 1e-3) / 1e9
+    print(json.dumps({"case": name, "logn": logn, "batch": batch, "mod_count": mod_count, "prime_bits": top_log2, "ms": res["tuned"],
+                      "ms_generic_kernel": res["generic"], "ntt_per_s": round(batch / (res["tuned"] * 1e-3), 1),
+                      "alg_GBps": round(gbs, 1), "frac_hbm": round(gbs / peak(), 4)}), flush=True)
+
+
 def fourstep_case(name, logn, batch, iters, contract, inverse=False):
     n1, n2 = capi.fourstep_shape(logn)
     p = 576460753175838721 if logn == 24 else 576460752303415297
@@ -128,6 +155,8 @@ def main():
     merge_case("C2 negacyclic fwd", 16, 1024, 64, X_N_plus, it)
     merge_case("C3 fwd+inv", 14, 4096, 32, X_N_minus, it, both=True)
     merge_case("C3 fwd", 14, 4096, 32, X_N_minus, it)
+    rns_case("RNS fwd 4 x 59-bit primes", 16, 1024, 4, it)
+    rns_case("RNS fwd 4 x 61-bit primes (exact kernels)", 16, 1024, 4, it, top_log2=61)
     fourstep_case("C4 4-step fused", 24, 16, max(2, it // 4), capi.FOURSTEP_FUSED)
     fourstep_case("C4 4-step reference contract", 24, 16, max(2, it // 4), capi.FOURSTEP_REFERENCE)
     fourstep_case("C4 4-step inverse fused", 24, 16, max(2, it // 4), capi.FOURSTEP_FUSED, inverse=True)
