@@ -183,6 +183,7 @@ namespace gpuntt_b200
         const T* mod_dev;
         const T* ninv_dev;
         const int* policy_flag;
+        const int* mod_order; // GPU_NTT_Modulus_Ordered: slot m uses entry mod_order[m] of the modulus / table / N^-1 arrays
         int mod_count, want_policy;
         const void* w_pairs; // WMUL kernels: Twiddle<T>[N], the 4-step twiddle matrix with Shoup companions
     };
@@ -393,7 +394,7 @@ namespace gpuntt_b200
     {
         T p, ninv_w, ninv_wq;
         uint64_t mu;
-        int pbits;
+        int pbits, mi;
     };
 
     template <typename S, bool WMUL = false, bool RNS = false>
@@ -481,7 +482,9 @@ namespace gpuntt_b200
                 if (tid == 0)
                 {
                     SegConsts<T> c;
-                    c.p = a.mod_dev[3 * mslot];
+                    const int mi = a.mod_order ? a.mod_order[mslot] : mslot;
+                    c.mi = mi;
+                    c.p = a.mod_dev[3 * mi];
                     if constexpr (sizeof(T) == 8)
                     {
                         c.pbits = 64 - __clzll((long long) c.p);
@@ -493,7 +496,7 @@ namespace gpuntt_b200
                         c.pbits = 32 - __clz((int) c.p);
                         c.mu = ~0ull / (uint64_t) c.p;
                     }
-                    c.ninv_w = S::INV ? a.ninv_dev[mslot] : T(0);
+                    c.ninv_w = S::INV ? a.ninv_dev[mi] : T(0);
                     c.ninv_wq = S::INV ? shoup_companion(c.ninv_w, c.p) : T(0);
                     *segc = c;
                 }
@@ -502,7 +505,7 @@ namespace gpuntt_b200
                 seg_mu = segc->mu;
                 seg_pbits = segc->pbits;
                 ninv = Twiddle<T>{segc->ninv_w, segc->ninv_wq};
-                seg_table = a.table + ((size_t) mslot << a.n);
+                seg_table = a.table + ((size_t) segc->mi << a.n);
                 M = typename ModOf<S>::type(seg_p);
                 triv = S::STRIDED && !S::INV && !a.plus && a.first && (a.lo + S::D == a.n) && seg_table[0] == T(1);
             }
@@ -1004,12 +1007,13 @@ namespace gpuntt_b200
 
     // ------------------------------------------------------------------ RNS form on the tuned kernels
     // flag = 0 when every modulus allows the lazy policy of this direction, else 1 (one warp)
-    template <typename T> __global__ void rns_policy_kernel(const T* __restrict__ mod_dev, int mod_count, int inverse, int* flag)
+    template <typename T>
+    __global__ void rns_policy_kernel(const T* __restrict__ mod_dev, const int* __restrict__ mod_order, int mod_count, int inverse, int* flag)
     {
         int bad = 0;
         for (int i = threadIdx.x; i < mod_count; i += 32)
         {
-            const uint64_t p = (uint64_t) mod_dev[3 * i];
+            const uint64_t p = (uint64_t) mod_dev[3 * (mod_order ? mod_order[i] : i)];
             const bool ok = inverse ? (p < kFastModulusLimit) : (p >= kF60ModulusMin && p < kF60ModulusLimit);
             bad |= ok ? 0 : 1;
         }
@@ -1036,8 +1040,8 @@ namespace gpuntt_b200
     // both the lazy-policy and the exact-policy kernel of every pass are enqueued and a device flag picks one.
     // flag_ws: one int of device scratch.  *launched = 0 when not covered.
     template <typename T>
-    cudaError_t fast_merge_rns(const T* in, T* out, const T* table, const T* mod_dev, const T* ninv_dev, int mod_count, int n_power,
-                               int plus, bool inverse, int batch, int* flag_ws, cudaStream_t st, int* launched,
+    cudaError_t fast_merge_rns(const T* in, T* out, const T* table, const T* mod_dev, const T* ninv_dev, const int* mod_order, int mod_count,
+                               int n_power, int plus, bool inverse, int batch, int* flag_ws, cudaStream_t st, int* launched,
                                void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t))
     {
         *launched = 0;
@@ -1056,12 +1060,13 @@ namespace gpuntt_b200
         a.mod_count = mod_count;
         a.mod_dev = mod_dev;
         a.ninv_dev = ninv_dev;
+        a.mod_order = mod_order;
         a.policy_flag = nullptr;
         int kind = 1;
         if (bits == 64)
         {
             prof_begin(0, st);
-            rns_policy_kernel<T><<<1, 32, 0, st>>>(mod_dev, mod_count, inverse ? 1 : 0, flag_ws);
+            rns_policy_kernel<T><<<1, 32, 0, st>>>(mod_dev, mod_order, mod_count, inverse ? 1 : 0, flag_ws);
             prof_end(st);
             cudaError_t pe = cudaGetLastError();
             if (pe != cudaSuccess) return pe;
@@ -1122,10 +1127,10 @@ namespace gpuntt_b200
         *launched = pl.npass;
         return cudaSuccess;
     }
-    template cudaError_t fast_merge_rns<uint64_t>(const uint64_t*, uint64_t*, const uint64_t*, const uint64_t*, const uint64_t*, int, int, int,
-                                                  bool, int, int*, cudaStream_t, int*, void (*)(int, cudaStream_t), void (*)(cudaStream_t));
-    template cudaError_t fast_merge_rns<uint32_t>(const uint32_t*, uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, int, int, int,
-                                                  bool, int, int*, cudaStream_t, int*, void (*)(int, cudaStream_t), void (*)(cudaStream_t));
+    template cudaError_t fast_merge_rns<uint64_t>(const uint64_t*, uint64_t*, const uint64_t*, const uint64_t*, const uint64_t*, const int*, int, int,
+                                                  int, bool, int, int*, cudaStream_t, int*, void (*)(int, cudaStream_t), void (*)(cudaStream_t));
+    template cudaError_t fast_merge_rns<uint32_t>(const uint32_t*, uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, const int*, int, int,
+                                                  int, bool, int, int*, cudaStream_t, int*, void (*)(int, cudaStream_t), void (*)(cudaStream_t));
 
     // (w, w') pairs of the 4-step twiddle matrix, once per call (the batch shares it)
     // t_lo > 0: entry i comes from the transposed index ((i mod 2^t_lo) << t_hi) | (i >> t_lo) (4-step inverse: the data

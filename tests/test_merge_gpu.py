@@ -367,7 +367,7 @@ def test_fast_path_large_modulus_uses_exact_arithmetic():
 
 
 @pytest.mark.parametrize("bits", [64, 32])
-@pytest.mark.parametrize("logn,batch,mod_count", [(10, 6, 2), (12, 8, 4), (16, 5, 3)])
+@pytest.mark.parametrize("logn,batch,mod_count", [(10, 6, 2), (12, 8, 4), (16, 5, 3), (16, 6, 3)])
 def test_rns_ordered_entry_points(bits, logn, batch, mod_count):
     """GPU_NTT_Modulus_Ordered: polynomial b uses modulus / table slice / n^-1 number order[b % mod_count]
     (ntt.cu:3117-3118); GPU_NTT_Poly_Ordered: the b-th transform runs in polynomial slot order[b] with modulus
