@@ -160,6 +160,10 @@ namespace gpuntt_b200
     {
         using type = ModF60;
     };
+    template <> struct ModSel<uint32_t, 2>
+    {
+        using type = ModL32;
+    };
     template <typename S> struct ModOf
     {
         using type = typename ModSel<typename S::T, S::POL>::type;
@@ -305,13 +309,15 @@ namespace gpuntt_b200
                             // {1, 2, 6, 12}[it] * p, the twiddle-1 butterflies of stages 0..2 are bare add/subtract
                             if (TRIV && it < 3 && x == 0)
                             {
-                                const T K = (it == 0 ? 1 : it == 1 ? 2 : 6) * M.p;
+                                const T K = M.triv_bound(it);
 #pragma unroll
                                 for (int y = 0; y < (1 << ab); y++) M.add_sub(e[y], e[y | (1 << ab)], K);
                                 continue;
                             }
                             const Twiddle<T> w = tg[((E >> (ab + 1)) - 1 + x) * G];
-                            const bool kindB = (ab % 2 == 0) && !(TRIV && it < 3);
+                            // correction on every other stage, ending each round with one; after the special stages of a
+                            // first cyclic round every stage corrects (their outputs may sit at the policy's cap)
+                            const bool kindB = TRIV ? (it >= 3) : (ab % 2 == 0);
 #pragma unroll
                             for (int y = 0; y < (1 << ab); y++)
                             {
@@ -856,17 +862,17 @@ namespace gpuntt_b200
     }
 
     // strided pass of D stages: rounds (D, 0) up to 4 stages, else (ceil(D/2), floor(D/2))
-    template <bool INV> static cudaError_t launch_strided32(int d, const FastArgs<uint32_t>& args, cudaStream_t st)
+    template <bool INV, int POL = 0> static cudaError_t launch_strided32(int d, const FastArgs<uint32_t>& args, cudaStream_t st)
     {
         using T = uint32_t;
         switch (d)
         {
-            case 3: return launch_fast<Shape<T, INV, 0, true, 3, 0, 13, 0>>(args, st);
-            case 4: return launch_fast<Shape<T, INV, 0, true, 4, 0, 13, 0>>(args, st);
-            case 5: return launch_fast<Shape<T, INV, 0, true, 5, 0, 13, 0>>(args, st);
-            case 6: return launch_fast<Shape<T, INV, 0, true, 3, 3, 13, 0>>(args, st);
-            case 7: return launch_fast<Shape<T, INV, 0, true, 4, 3, 13, 0>>(args, st);
-            case 8: return launch_fast<Shape<T, INV, 0, true, 4, 4, 13, 0>>(args, st);
+            case 3: return launch_fast<Shape<T, INV, POL, true, 3, 0, 13, 0>>(args, st);
+            case 4: return launch_fast<Shape<T, INV, POL, true, 4, 0, 13, 0>>(args, st);
+            case 5: return launch_fast<Shape<T, INV, POL, true, 5, 0, 13, 0>>(args, st);
+            case 6: return launch_fast<Shape<T, INV, POL, true, 3, 3, 13, 0>>(args, st);
+            case 7: return launch_fast<Shape<T, INV, POL, true, 4, 3, 13, 0>>(args, st);
+            case 8: return launch_fast<Shape<T, INV, POL, true, 4, 4, 13, 0>>(args, st);
             default: return cudaErrorNotSupported;
         }
     }
@@ -971,7 +977,9 @@ namespace gpuntt_b200
             a.plus = plus;
             a.batch = batch;
             using Cf = Shape<T, false, 0, false, 5, 5, 13, 1>;
+            using Cl = Shape<T, false, 2, false, 5, 5, 13, 1>; // lazy forward policy (p <= 2^29)
             using Ci = Shape<T, true, 0, false, 5, 5, 13, 1>;
+            const bool lazy = !inverse && (uint32_t) p < kL32ModulusLimit;
             const FastPlan pl = make_fast_plan(n_power, 32);
             for (int k = 0; k < pl.npass; k++)
             {
@@ -988,13 +996,15 @@ namespace gpuntt_b200
                 {
                     const int c = 13 - pl.d[i];
                     s.work = ((long long) batch << (pl.lo[i] - c)) << (n_power - pl.lo[i] - pl.d[i]);
-                    e = inverse ? launch_strided32<true>(pl.d[i], s, st) : launch_strided32<false>(pl.d[i], s, st);
+                    s.rr = (n_power == pl.lo[i] + pl.d[i]) && pl.lo[i] > 12;
+                    e = inverse ? launch_strided32<true>(pl.d[i], s, st)
+                                : (lazy ? launch_strided32<false, 2>(pl.d[i], s, st) : launch_strided32<false>(pl.d[i], s, st));
                 }
                 else
                 {
                     const long long tpr = (batch + 1) >> 1;
                     s.work = tpr << (n_power - 12);
-                    e = inverse ? launch_fast<Ci>(s, st) : launch_fast<Cf>(s, st);
+                    e = inverse ? launch_fast<Ci>(s, st) : (lazy ? launch_fast<Cl>(s, st) : launch_fast<Cf>(s, st));
                 }
                 prof_end(st);
                 if (e == cudaErrorNotSupported && k == 0) return cudaSuccess;

@@ -67,20 +67,23 @@ namespace gpuntt_b200
             return tw.w * v - q * p;
         }
         // Cooley-Tukey butterfly (replaces CooleyTukeyUnit, ntt.cuh:69-78 of the reference).
-        // In/out: [0,4p).
+        // In/out: [0,4p).  Three-operand sums (see the fast policy below for why).
         __device__ __forceinline__ void ct(T& X, T& Y, const Twiddle<T>& tw) const
         {
-            T x = csub(X, two_p);
-            T t = mul(Y, tw);
-            X = x + t;
-            Y = x - t + two_p;
+            const T t = mul(Y, tw);
+            const bool P = X >= two_p;
+            const T g = P ? T(0) - two_p : T(0), k = P ? T(0) : two_p;
+            const T Xn = X + g + t;
+            Y = X + k - t;
+            X = Xn;
         }
         // Gentleman-Sande butterfly (replaces GentlemanSandeUnit, ntt.cuh:80-92). In/out: [0,2p).
         __device__ __forceinline__ void gs(T& X, T& Y, const Twiddle<T>& tw) const
         {
-            T s = X + Y;
-            T d = X - Y + two_p;
-            X = csub(s, two_p);
+            const T d = X + two_p - Y;
+            const T s = X + Y;
+            const T g = (s >= two_p) ? T(0) - two_p : T(0);
+            X = X + Y + g;
             Y = mul(d, tw);
         }
         // forward lazy value -> canonical
@@ -253,6 +256,8 @@ namespace gpuntt_b200
             Y = X + K - Y;
             X = s;
         }
+        // bound (multiple of p) of the values before stage it of a first cyclic round with canonical inputs
+        __device__ __forceinline__ T triv_bound(int it) const { return (it == 0 ? 1 : it == 1 ? 2 : 6) * p; }
         // [0, 13p) -> [0, p)
         __device__ __forceinline__ T canon_fwd(T x) const
         {
@@ -263,6 +268,45 @@ namespace gpuntt_b200
             return csub(r, p);
         }
     };
+    // ------------------------------------------------------------------ lazy forward policy for 32-bit data (p <= 2^29)
+    // Same idea as F60 with an exact quotient (one IMAD.HI): products in [0,2p), values below 6p at round
+    // boundaries and 8p <= 2^32 inside, the range correction (-4p, exact 32-bit compare) on every other stage.
+    struct ModL32 : Mod<uint32_t, false>
+    {
+        using T = uint32_t;
+        T four_p, red_m; // red_m = floor(2^32 / p)
+        __device__ __forceinline__ explicit ModL32(T p_) : Mod<uint32_t, false>(p_), four_p(4 * p_), red_m((T) ((1ull << 32) / p_)) {}
+        __device__ __forceinline__ void ctA(T& X, T& Y, const Twiddle<T>& tw) const // in: X < 6p; out < 8p
+        {
+            const T t = mul(Y, tw);
+            Y = X + two_p - t;
+            X = X + t;
+        }
+        __device__ __forceinline__ void ctB(T& X, T& Y, const Twiddle<T>& tw) const // in: X < 8p; out < 6p
+        {
+            const T t = mul(Y, tw);
+            const bool P = X >= four_p;
+            const T g = P ? T(0) - four_p : T(0), k = P ? T(0) - two_p : two_p;
+            const T Xn = X + g + t;
+            Y = X + k - t;
+            X = Xn;
+        }
+        __device__ __forceinline__ void add_sub(T& X, T& Y, T K) const
+        {
+            const T s = X + Y;
+            Y = X + K - Y;
+            X = s;
+        }
+        // bound (multiple of p) of the values before stage it of a first cyclic round with canonical inputs
+        __device__ __forceinline__ T triv_bound(int it) const { return (it == 0 ? 1 : it == 1 ? 2 : 4) * p; }
+        __device__ __forceinline__ T canon_fwd(T x) const // [0, 8p) -> [0, p)
+        {
+            const T q = __umulhi(x, red_m); // in {floor(x/p) - 1, floor(x/p)}
+            return csub(x - q * p, p);
+        }
+    };
+    constexpr uint32_t kL32ModulusLimit = (1u << 29) + 1; // 8p <= 2^32
+
     constexpr uint64_t kF60ModulusMin = 1ull << 40;
     constexpr uint64_t kF60ModulusLimit = (1ull << 60) - (1ull << 31);
 
