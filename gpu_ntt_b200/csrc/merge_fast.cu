@@ -121,7 +121,8 @@ namespace gpuntt_b200
     // STRIDED: tile = 2^D rows (row stride 2^lo elements) x 2^C adjacent columns, K = D + C.
     // !STRIDED: tile = 2^NPLOG polynomials x 2^KC adjacent elements of the same ring range.
     // Two register rounds: R1 stages on the high bits, R2 on the low bits (D = R1 + R2).
-    // POL: arithmetic policy -- 0 exact (any modulus the reference accepts), 1 fast lazy (inverse), 2 F60 (forward).
+    // POL: arithmetic policy -- 0 exact (any modulus the reference accepts), 1 lazy (inverse; forward for 61-bit moduli
+    // above the F60 range: correction on every stage), 2 F60 / L32 (forward).
     // NT: contiguous passes of transforms SHORTER than a tile row group (the 4-step inverse row phase, N = n1 <= 256): twiddles
     // depend on the low NT index bits only and a tile holds several whole transforms.
     template <typename T_, bool INV_, int POL_, bool STRIDED_, int R1_, int R2_, int K_, int NPLOG_, int NT_ = 0> struct Shape
@@ -129,7 +130,7 @@ namespace gpuntt_b200
         using T = T_;
         static constexpr int POL = POL_;
         static constexpr bool INV = INV_, FAST = POL_ != 0, STRIDED = STRIDED_;
-        static_assert(POL_ == 0 || (POL_ == 1 && INV_) || (POL_ == 2 && !INV_), "policy 1 is inverse-only, policy 2 forward-only");
+        static_assert(POL_ == 0 || POL_ == 1 || (POL_ == 2 && !INV_), "policy 2 is forward-only");
         static constexpr int R1 = R1_, R2 = R2_, K = K_, NPLOG = NPLOG_;
         static constexpr int D = R1 + R2;
         static constexpr int C = STRIDED ? (K - D) : 0;
@@ -823,6 +824,8 @@ namespace gpuntt_b200
         int d[3] = {0, 0, 0}, lo[3] = {0, 0, 0};
         bool strided[3] = {false, false, false};
     };
+    // (an 8-stage contiguous pass for the small 32-bit rings -- a "balanced" split -- measured no faster than 4 + 10:
+    // profiles/r1_ab_experiments.txt)
     static FastPlan make_fast_plan(int n, int element_bits)
     {
         FastPlan pl;
@@ -901,11 +904,13 @@ namespace gpuntt_b200
         if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return cudaSuccess;
         if constexpr (sizeof(T) == 8)
         {
-            // forward: F60 policy for 2^40 <= p < 2^60 - 2^31; inverse: the lazy policy (exact range test, any p below
-            // 1.25 * 2^60).  Other moduli: exact-policy kernels exist for n = 16 only, the rest goes to the generic kernel.
+            // forward: F60 policy for 2^40 <= p < 2^60 - 2^31, the every-stage lazy policy for the other moduli in
+            // [2^36, 1.25 * 2^60) (61-bit primes); inverse: the lazy policy (exact range test, any p below 1.25 * 2^60).
+            // Other moduli: exact-policy kernels exist for n = 16 only, the rest goes to the generic kernel.
             const bool f60 = (uint64_t) p >= kF60ModulusMin && (uint64_t) p < kF60ModulusLimit;
+            const bool lazy_fwd = !f60 && (uint64_t) p >= kFastModulusMin && (uint64_t) p < kFastModulusLimit;
             const bool fast_inv = (uint64_t) p < kFastModulusLimit;
-            const bool fast_arith = inverse ? fast_inv : f60;
+            const bool fast_arith = inverse ? fast_inv : (f60 || lazy_fwd);
             if (!fast_arith && n_power != 16) return cudaSuccess;
             FastArgs<T> a{};
             a.table = table;
@@ -942,17 +947,18 @@ namespace gpuntt_b200
                     s.work = ((long long) batch << (pl.lo[i] - c)) << (n_power - pl.lo[i] - pl.d[i]);
                     s.rr = (n_power == pl.lo[i] + pl.d[i]) && pl.lo[i] > 10; // one range, long row stride
                     if (fast_arith)
-                        e = inverse ? launch_strided<T, true, 1>(pl.d[i], s, st) : launch_strided<T, false, 2>(pl.d[i], s, st);
+                        e = inverse ? launch_strided<T, true, 1>(pl.d[i], s, st)
+                                    : (f60 ? launch_strided<T, false, 2>(pl.d[i], s, st) : launch_strided<T, false, 1>(pl.d[i], s, st));
                     else
                         e = inverse ? launch_strided<T, true, 0>(8, s, st) : launch_strided<T, false, 0>(8, s, st);
                 }
                 else
                 {
-                    const int nplog = (!inverse && fast_arith) ? Cf::NPLOG : 1;
+                    const int nplog = (!inverse && f60) ? Cf::NPLOG : 1;
                     const long long tpr = (batch + (1 << nplog) - 1) >> nplog;
                     s.work = tpr << (n_power - (12 - nplog));
                     if (fast_arith)
-                        e = inverse ? launch_fast<Ci>(s, st) : launch_fast<Cf>(s, st);
+                        e = inverse ? launch_fast<Ci>(s, st) : (f60 ? launch_fast<Cf>(s, st) : launch_fast<Shape<T, false, 1, false, 4, 4, 12, 1>>(s, st));
                     else
                         e = inverse ? launch_fast<Cix>(s, st) : launch_fast<Cfx>(s, st);
                 }
