@@ -115,7 +115,11 @@ namespace gpuntt_b200
     __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
     __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
     __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#ifdef GPUNTT_EXPERIMENT_NOSYNC // timing experiment only (wrong results): upper bound of what a barrier-free round structure could gain
+    __device__ __forceinline__ void consumer_sync() {}
+#else
     __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
+#endif
 
     // ------------------------------------------------------------------ compile-time pass shape
     // STRIDED: tile = 2^D rows (row stride 2^lo elements) x 2^C adjacent columns, K = D + C.
@@ -649,7 +653,11 @@ namespace gpuntt_b200
                     constexpr bool W1 = WMUL && S::R2 == 0, W2 = WMUL && S::R2 > 0;
                     if constexpr (!S::INV)
                     {
+#ifdef GPUNTT_EXPERIMENT_NOCANON // timing experiment only (lazy outputs): what the final canonicalisation costs
+                        constexpr bool FIN1 = false, FIN2 = false;
+#else
                         constexpr bool FIN1 = !S::STRIDED && S::R2 == 0, FIN2 = !S::STRIDED;
+#endif
                         if constexpr (S::STRIDED && S::POL == 2 && S::G1 == 1)
                         {
                             if (triv)
