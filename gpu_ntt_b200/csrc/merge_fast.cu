@@ -1,24 +1,29 @@
-// gpu_ntt_b200/csrc/merge_fast.cu -- the tuned Merge-NTT path (single modulus, unsigned data).
+// gpu_ntt_b200/csrc/merge_fast.cu -- the tuned Merge-NTT kernels (unsigned data, PerPolynomial layout).
 //
-// One persistent, warp-specialised kernel per pass ("fast path"):
+// One persistent, warp-specialised kernel per pass:
 //   * 8 consumer warps do nothing but shared-memory <-> register butterfly rounds;
 //   * 1 producer warp moves every coefficient tile with the TMA engine: ONE cp.async.bulk.tensor
 //     (UTMALDG) per 32 KiB tile global -> shared for the next tile while the current one is being
 //     transformed (two tile buffers, mbarrier full/done hand-shake) and one UTMASTG per finished
-//     tile shared -> global; the strided (column) tile of the first pass is a 2-D box
-//     [2^D rows x 128 bytes], the contiguous tile of the last pass a 3-D box
-//     [polynomials x rows x 128 bytes] (out-of-range polynomials are clipped by the hardware);
+//     tile shared -> global.  Strided tiles are 3-D boxes [2^D matrix rows x column blocks x 128 bytes],
+//     contiguous tiles [polynomials x rows x 128 bytes] (4-D with a modulus-slot dimension for RNS);
+//     out-of-range polynomials are clipped by the hardware;
 //   * tiles land in shared memory in the hardware SWIZZLE_128B layout (16-byte chunk index XOR
 //     row mod 8), which makes every round shape bank-conflict free (16-byte accesses for the
 //     lowest round);
-//   * the twiddles of a pass are turned into (w, w') Shoup pairs ONCE per CTA, straight from the
-//     caller's table, into a slot-major shared-memory layout (lanes read adjacent 16-byte
-//     pairs) -- no scratch memory and no pre-kernel on this path;
-//   * the last pass pins each CTA to one contiguous range of the ring and streams polynomials
-//     through it, so the ~N distinct twiddles of the final stages are fetched once per CTA
-//     instead of once per polynomial.
-// Replaces ForwardCore/InverseCore of the reference (src/lib/ntt_merge/ntt.cu:435-1318) for
-// the plans listed in fast_supported().
+//   * the twiddles of a pass are turned into (w, w') Shoup pairs once per CTA and twiddle range,
+//     straight from the caller's table, into a slot-major shared-memory layout -- no scratch memory
+//     and no pre-kernel; the contiguous pass pins each CTA to one range of the ring and streams
+//     polynomials through it, so the ~N distinct twiddles of the final stages are fetched once per
+//     CTA instead of once per polynomial.
+// Entry points (called from merge_ntt.cu / fourstep.inl):
+//   fast_merge             GPU_NTT / GPU_INTT single modulus: 64-bit rings 2^12..2^24, 32-bit 2^13..2^26
+//   fast_merge_rns         the RNS overloads and GPU_NTT_Modulus_Ordered (two-pass ring sizes)
+//   fast_fourstep_columns  forward 4-step column phase with the twiddle-matrix product as epilogue
+//   fast_fourstep_inverse  inverse 4-step (row phase + strided passes with the product as prologue)
+// Replaces ForwardCore/InverseCore (src/lib/ntt_merge/ntt.cu:435-1318) and the FourStep*Core kernels
+// (src/lib/ntt_4step/ntt_4step.cu:571-2291) of the reference for the shapes listed above; everything
+// else takes the generic pass kernel in merge_ntt.cu.
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
