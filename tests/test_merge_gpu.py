@@ -505,3 +505,30 @@ def test_per_coefficient_rns_and_limits():
         capi.merge_ntt(in_ptr=d.data_ptr(), out_ptr=d.data_ptr(), table_ptr=d.data_ptr(), n_power=10, batch=4,
                        layout=capi.PerCoefficient, modulus=primes[0][0], stream=s)
     assert ei.value.status == capi.ERR_N_POWER
+
+
+@pytest.mark.parametrize("bits,logn,batch", [(64, 16, 4), (32, 14, 3), (64, 20, 1)])
+def test_cuda_graph_capture_and_replay(bits, logn, batch):
+    """The entry points only enqueue work on cfg.stream (no synchronisation, no allocation once the cached scratch
+    exists), so a caller may capture them into a CUDA graph: capture forward + inverse, replay on new data."""
+    P = O.merge_params(logn, O.X_N_minus, bits)
+    tab, itab = to_dev(P.fwd_br, bits), to_dev(P.inv_br, bits)
+    x = O.example_input(P.modulus, batch << logn, seed=77)
+    d = to_dev(x, bits).view(batch, -1)
+    fwd = torch.empty_like(d)
+    back = torch.empty_like(d)
+    capi.ntt(d, tab, P.modulus, logn, O.X_N_minus, out=fwd)          # warm-up: scratch buffers, function attributes
+    capi.intt(fwd, itab, P.modulus, P.n_inv, logn, O.X_N_minus, out=back)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        capi.ntt(d, tab, P.modulus, logn, O.X_N_minus, out=fwd)
+        capi.intt(fwd, itab, P.modulus, P.n_inv, logn, O.X_N_minus, out=back)
+    y = O.example_input(P.modulus, batch << logn, seed=78)
+    d.copy_(to_dev(y, bits).view(batch, -1))
+    fwd.zero_()
+    back.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert (to_host(fwd, bits).ravel() == O.merge_ntt(y, P).ravel()).all()
+    assert (to_host(back, bits).ravel() == y).all()
