@@ -493,6 +493,38 @@ namespace gpuntt_b200
             const int ntiles = (int) ((seg_end - w + step - 1) / step);
 
             __syncthreads(); // everybody is done with the previous segment's twiddles and buffers
+            const int lane = tid - kConsumers;
+            // TMA coordinates of work item ww (innermost first)
+            auto issue_load = [&](long long ww, int b)
+            {
+                if (lane == 0)
+                {
+                    const uint32_t bar = smem_u32(&bars[b]);
+                    const uint32_t dst = smem_u32(bufs + b * S::TILE_SMEM);
+                    mbar_expect_tx(bar, S::TILE_SMEM); // out-of-range rows are zero-filled and still counted
+                    if constexpr (S::STRIDED)
+                    {
+                        const int ccb = a.lo - S::C;
+                        const long long within = ww % tiles_per_range;
+                        const long long poly = a.rr ? within % a.batch : within >> ccb;
+                        const long long cc = a.rr ? within / a.batch : (within & ((1LL << ccb) - 1));
+                        const long long gp = RNS ? poly * a.mod_count + mslot : poly; // polynomial in the caller's array
+                        tma_load_3d(dst, &map_in, 0, (int) (cc << (S::C - S::CB)),
+                                    (int) ((gp << (a.n - a.lo)) + ((long long) range << S::D)), bar);
+                    }
+                    else
+                    {
+                        const long long grp = ww % tiles_per_range;
+                        if constexpr (RNS) // {row, rows of a polynomial, modulus slot, polynomial within the slot}
+                            tma_load_4d(dst, &map_in, 0, range << (S::KC - S::CB), mslot, (int) (grp << S::NPLOG), bar);
+                        else
+                            tma_load_3d(dst, &map_in, 0, range << (S::KC - S::CB), (int) (grp << S::NPLOG), bar);
+                    }
+                }
+            };
+            // the first two tiles of the segment start moving now, under the twiddle build
+            if (tid >= kConsumers)
+                for (int i = 0; i < 2 && i < ntiles; i++) issue_load(w + i * step, (int) ((uses0 + uses1 + i) & 1));
             if constexpr (RNS)
             {
                 if (tid == 0)
@@ -554,36 +586,6 @@ namespace gpuntt_b200
             if (tid >= kConsumers)
             {
                 // =================== producer warp ===================
-                const int lane = tid - kConsumers;
-                // TMA coordinates of work item ww (innermost first)
-                auto issue_load = [&](long long ww, int b)
-                {
-                    if (lane == 0)
-                    {
-                        const uint32_t bar = smem_u32(&bars[b]);
-                        const uint32_t dst = smem_u32(bufs + b * S::TILE_SMEM);
-                        mbar_expect_tx(bar, S::TILE_SMEM); // out-of-range rows are zero-filled and still counted
-                        if constexpr (S::STRIDED)
-                        {
-                            const int ccb = a.lo - S::C;
-                            const long long within = ww % tiles_per_range;
-                            const long long poly = a.rr ? within % a.batch : within >> ccb;
-                            const long long cc = a.rr ? within / a.batch : (within & ((1LL << ccb) - 1));
-                            const long long gp = RNS ? poly * a.mod_count + mslot : poly; // polynomial in the caller's array
-                            tma_load_3d(dst, &map_in, 0, (int) (cc << (S::C - S::CB)),
-                                        (int) ((gp << (a.n - a.lo)) + ((long long) range << S::D)), bar);
-                        }
-                        else
-                        {
-                            const long long grp = ww % tiles_per_range;
-                            if constexpr (RNS) // {row, rows of a polynomial, modulus slot, polynomial within the slot}
-                                tma_load_4d(dst, &map_in, 0, range << (S::KC - S::CB), mslot, (int) (grp << S::NPLOG), bar);
-                            else
-                                tma_load_3d(dst, &map_in, 0, range << (S::KC - S::CB), (int) (grp << S::NPLOG), bar);
-                        }
-                    }
-                };
-                for (int i = 0; i < 2 && i < ntiles; i++) issue_load(w + i * step, (int) ((uses0 + uses1 + i) & 1));
                 // tile t of the CTA's whole stream uses buffer (t & 1); uses0 + uses1 = tiles so far
                 for (int i = 0; i < ntiles; i++)
                 {

@@ -28,4 +28,17 @@ for bits in (64, 32):
                 e1.record(); torch.cuda.synchronize()
                 out[label] = round(e0.elapsed_time(e1) / 50 * 1e3, 2)
             capi.lib().gpuntt_b200_force_generic_path(0)
-            print(json.dumps({"bits": bits, "logn": logn, "batch": batch, "us_tuned": out["tuned"], "us_generic": out["generic"]}), flush=True)
+            # the same call replayed from a CUDA graph (20 transforms per graph): launch overhead off the host's critical path
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(20):
+                    capi.ntt(x, tab, pp, logn, 1)
+            g.replay(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                g.replay()
+            e1.record(); torch.cuda.synchronize()
+            out["graph"] = round(e0.elapsed_time(e1) / 100 * 1e3, 2)
+            print(json.dumps({"bits": bits, "logn": logn, "batch": batch, "us_tuned": out["tuned"], "us_tuned_cuda_graph": out["graph"],
+                              "us_generic": out["generic"]}), flush=True)
