@@ -189,6 +189,8 @@ namespace gpuntt_b200
         int pbits; // bit length of p
         int n, lo, plus, first, last, batch, rr;
         int n_tw; // transform size (log2) for twiddle indexing when it differs from the layout size n (0: n)
+        int cta_per_seg, seg_extra; // cta_per_seg > 0: every CTA works inside ONE twiddle segment; the first seg_extra segments get
+                                    // cta_per_seg + 1 CTAs, the others cta_per_seg (set by launch_fast)
         long long work; // total tiles of this pass
         // RNS kernels (polynomial b uses modulus slot b % mod_count, ntt.cu:613-619 of the reference): `batch` is then the
         // number of polynomials PER SLOT, mod_dev the device array of {value, bit, mu} triples, ninv_dev the per-slot
@@ -439,13 +441,43 @@ namespace gpuntt_b200
         // items ordered column-chunk-major, so the tiles in flight across the chip at any moment are the polynomials
         // of a few ADJACENT column chunks -- whole DRAM pages are consumed together and, for the 4-step column pass,
         // the 16 polynomials of a chunk share one fetch of the twiddle-matrix pairs through the L2.
-        const long long step = a.rr ? (long long) gridDim.x : 1LL;
-        const long long w_begin = a.rr ? (long long) blockIdx.x : a.work * blockIdx.x / gridDim.x;
-        const long long w_end = a.rr ? a.work : a.work * (blockIdx.x + 1) / gridDim.x;
         // tiles that share one twiddle set ("range" = the index bits above this pass's stage window):
         //   STRIDED: every polynomial x every column chunk of one 2^D-row block;  else: every polynomial group
         const long long tiles_per_range =
             S::STRIDED ? ((long long) a.batch << (a.lo - S::C)) : (long long) ((a.batch + (1 << S::NPLOG) - 1) >> S::NPLOG);
+        // a.cta_per_seg: when there are fewer segments than CTA slots, cta_per_seg CTAs split each segment, so nobody
+        // builds two twiddle sets for a handful of tiles
+        const long long step = a.rr ? (long long) gridDim.x : 1LL;
+        long long w_begin, w_end;
+        if (a.rr)
+        {
+            w_begin = blockIdx.x;
+            w_end = a.work;
+        }
+        else if (a.cta_per_seg > 0)
+        {
+            const long long big = (long long) a.seg_extra * (a.cta_per_seg + 1); // CTAs of the segments with one more
+            long long sg, j, kk;
+            if ((long long) blockIdx.x < big)
+            {
+                kk = a.cta_per_seg + 1;
+                sg = blockIdx.x / kk;
+                j = blockIdx.x % kk;
+            }
+            else
+            {
+                kk = a.cta_per_seg;
+                sg = a.seg_extra + ((long long) blockIdx.x - big) / kk;
+                j = ((long long) blockIdx.x - big) % kk;
+            }
+            w_begin = sg * tiles_per_range + tiles_per_range * j / kk;
+            w_end = sg * tiles_per_range + tiles_per_range * (j + 1) / kk;
+        }
+        else
+        {
+            w_begin = a.work * blockIdx.x / gridDim.x;
+            w_end = a.work * (blockIdx.x + 1) / gridDim.x;
+        }
 
         if (tid == kConsumers)
         {
@@ -820,7 +852,35 @@ namespace gpuntt_b200
             return cudaErrorNotSupported;
         long long grid = (long long) sms * blocks_per_sm;
         if (grid > args.work) grid = args.work;
-        kern<<<(unsigned) grid, kFastThreads, S::SMEM, st>>>(args, map_in, map_out);
+        FastArgs<typename S::T> la = args;
+        la.cta_per_seg = 0;
+        la.seg_extra = 0;
+        if (!args.rr)
+        {
+            // segment-aligned shares when the segments are fewer than the CTA slots
+            const long long tpr = S::STRIDED ? ((long long) args.batch << (args.lo - S::C)) : (long long) ((args.batch + (1 << S::NPLOG) - 1) >> S::NPLOG);
+            const long long nseg = tpr > 0 ? args.work / tpr : 0;
+            if (nseg > 0 && nseg * tpr == args.work && nseg <= grid)
+            {
+                long long k = grid / nseg, extra = grid % nseg;
+                if (k >= tpr)
+                {
+                    k = tpr; // one tile per CTA
+                    extra = 0;
+                }
+                // cost in tile times, a twiddle build counted as half a tile: aligned shares are uneven (the slowest CTA
+                // has ceil(tpr / k) tiles) but build once; contiguous shares are even but usually straddle two segments
+                const double aligned = (double) ((tpr + k - 1) / k) + 0.5;
+                const double contiguous = (double) ((args.work + grid - 1) / grid) + 1.0;
+                if (aligned < contiguous)
+                {
+                    la.cta_per_seg = (int) k;
+                    la.seg_extra = (int) extra;
+                    grid = nseg * k + extra;
+                }
+            }
+        }
+        kern<<<(unsigned) grid, kFastThreads, S::SMEM, st>>>(la, map_in, map_out);
         return cudaGetLastError();
     }
 
