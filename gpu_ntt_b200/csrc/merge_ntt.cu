@@ -546,12 +546,32 @@ namespace gpuntt_b200
     struct ProfRec
     {
         cudaEvent_t e0, e1;
+        int dev;
         int kind; // 0 = twiddle_prep_kernel, 1.. = merge pass number (1-based, execution order)
     };
     static std::atomic<int> g_profiling{0};
     static std::atomic<int> g_force_generic{0};
     static std::mutex g_prof_mutex;
     static std::vector<ProfRec> g_prof;
+    static std::map<int, std::vector<cudaEvent_t>> g_prof_pool; // per device; recycled: creating an event costs more host time than recording it
+    static cudaEvent_t prof_event()
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        {
+            std::lock_guard<std::mutex> lk(g_prof_mutex);
+            auto& pool = g_prof_pool[dev];
+            if (!pool.empty())
+            {
+                cudaEvent_t e = pool.back();
+                pool.pop_back();
+                return e;
+            }
+        }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
 
     struct ProfScope
     {
@@ -562,8 +582,9 @@ namespace gpuntt_b200
         {
             if (!on) return;
             r.kind = kind;
-            cudaEventCreate(&r.e0);
-            cudaEventCreate(&r.e1);
+            cudaGetDevice(&r.dev);
+            r.e0 = prof_event();
+            r.e1 = prof_event();
             cudaEventRecord(r.e0, st);
         }
         ~ProfScope()
@@ -1164,8 +1185,9 @@ extern "C"
                 if (kind_out) kind_out[n] = r.kind;
                 n++;
             }
-            cudaEventDestroy(r.e0);
-            cudaEventDestroy(r.e1);
+            std::lock_guard<std::mutex> lk(g_prof_mutex);
+            g_prof_pool[r.dev].push_back(r.e0);
+            g_prof_pool[r.dev].push_back(r.e1);
         }
         return n;
     }
