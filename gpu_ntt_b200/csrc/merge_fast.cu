@@ -845,6 +845,12 @@ namespace gpuntt_b200
         }
         alignas(64) CUtensorMap map_in, map_out;
         const int mc = RNS ? args.mod_count : 0;
+        if constexpr (S::STRIDED)
+        {
+            // TMA coordinates are signed 32-bit: the row index of the last polynomial must fit
+            const long long rows = ((long long) args.batch * (mc > 0 ? mc : 1)) << (args.n - args.lo);
+            if (rows >= (1LL << 31)) return cudaErrorNotSupported;
+        }
         if (!make_map<S>(&map_in, args.in, args.n, args.lo, args.batch, mc)) return cudaErrorNotSupported;
         if (args.in == args.out)
             map_out = map_in;
@@ -977,6 +983,8 @@ namespace gpuntt_b200
         *launched = 0;
         if (!fast_supported(n_power, (int) sizeof(T) * 8)) return cudaSuccess;
         if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return cudaSuccess;
+        // TMA coordinates are signed 32-bit: the matrix-row index of the finest strided pass must fit
+        if (((long long) batch << (n_power - (sizeof(T) == 8 ? 8 : 10))) >= (1LL << 31)) return cudaSuccess;
         if constexpr (sizeof(T) == 8)
         {
             // forward: F60 policy for 2^40 <= p < 2^60 - 2^31, the every-stage lazy policy for the other moduli in
@@ -1139,6 +1147,7 @@ namespace gpuntt_b200
         constexpr int bits = (int) sizeof(T) * 8;
         constexpr int K = bits == 64 ? 12 : 13;
         if (!fast_supported(n_power, bits) || mod_count < 1 || batch % mod_count != 0) return cudaSuccess;
+        if (((long long) batch << (n_power - (bits == 64 ? 8 : 10))) >= (1LL << 31)) return cudaSuccess;
         const FastPlan pl = make_fast_plan(n_power, bits);
         if (pl.npass != 2 || pl.d[0] < 4) return cudaSuccess;
         if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return cudaSuccess;
@@ -1246,6 +1255,7 @@ namespace gpuntt_b200
         using T = uint64_t;
         *launched = 0;
         if (lg1 < 5 || lg1 > 8 || lg2 < 12 - lg1 || n_power != lg1 + lg2) return cudaSuccess;
+        if (((long long) batch << lg1) >= (1LL << 31)) return cudaSuccess;
         if (!(p >= kF60ModulusMin && p < kF60ModulusLimit)) return cudaSuccess;
         if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return cudaSuccess;
         FastArgs<T> a{};
@@ -1302,6 +1312,7 @@ namespace gpuntt_b200
         using T = uint64_t;
         *launched = 0;
         if (lg1 < 5 || lg1 > 8 || n_power != lg1 + lg2 || n_power < 12) return cudaSuccess;
+        if (((long long) batch << lg2) >= (1LL << 31)) return cudaSuccess;
         if (!(p < kFastModulusLimit) || p < 5) return cudaSuccess;
         if ((reinterpret_cast<uintptr_t>(rows_in) | reinterpret_cast<uintptr_t>(work) | reinterpret_cast<uintptr_t>(dst)) & 15) return cudaSuccess;
         // split of the lg2 strided stages (executed low bits first)
