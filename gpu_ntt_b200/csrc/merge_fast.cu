@@ -199,6 +199,7 @@ namespace gpuntt_b200
         const T* mod_dev;
         const T* ninv_dev;
         const int* policy_flag;
+        const int* poly_order; // GPU_NTT_Poly_Ordered: the b-th transform (slot b % mod_count) lives in polynomial poly_order[b]
         const int* mod_order; // GPU_NTT_Modulus_Ordered: slot m uses entry mod_order[m] of the modulus / table / N^-1 arrays
         int mod_count, want_policy;
         const void* w_pairs; // WMUL kernels: Twiddle<T>[N], the 4-step twiddle matrix with Shoup companions
@@ -540,7 +541,9 @@ namespace gpuntt_b200
                         const long long within = ww % tiles_per_range;
                         const long long poly = a.rr ? within % a.batch : within >> ccb;
                         const long long cc = a.rr ? within / a.batch : (within & ((1LL << ccb) - 1));
-                        const long long gp = RNS ? poly * a.mod_count + mslot : poly; // polynomial in the caller's array
+                        long long gp = RNS ? poly * a.mod_count + mslot : poly; // polynomial in the caller's array
+                        if constexpr (RNS)
+                            if (a.poly_order) gp = a.poly_order[gp];
                         tma_load_3d(dst, &map_in, 0, (int) (cc << (S::C - S::CB)),
                                     (int) ((gp << (a.n - a.lo)) + ((long long) range << S::D)), bar);
                     }
@@ -548,7 +551,22 @@ namespace gpuntt_b200
                     {
                         const long long grp = ww % tiles_per_range;
                         if constexpr (RNS) // {row, rows of a polynomial, modulus slot, polynomial within the slot}
-                            tma_load_4d(dst, &map_in, 0, range << (S::KC - S::CB), mslot, (int) (grp << S::NPLOG), bar);
+                        {
+                            if (a.poly_order)
+                            {
+                                // the tile's polynomials sit in arbitrary slots: one box per polynomial (3-D map, box of one
+                                // polynomial); a missing last polynomial is an out-of-range coordinate (zero fill)
+#pragma unroll
+                                for (int q = 0; q < (1 << S::NPLOG); q++)
+                                {
+                                    const long long kq = (grp << S::NPLOG) + q;
+                                    const int slot = kq < a.batch ? a.poly_order[kq * a.mod_count + mslot] : 0x7fffffff;
+                                    tma_load_3d(dst + q * (S::TILE_SMEM >> S::NPLOG), &map_in, 0, range << (S::KC - S::CB), slot, bar);
+                                }
+                            }
+                            else
+                                tma_load_4d(dst, &map_in, 0, range << (S::KC - S::CB), mslot, (int) (grp << S::NPLOG), bar);
+                        }
                         else
                             tma_load_3d(dst, &map_in, 0, range << (S::KC - S::CB), (int) (grp << S::NPLOG), bar);
                     }
@@ -635,7 +653,9 @@ namespace gpuntt_b200
                             const long long within = ww % tiles_per_range;
                             const long long poly = a.rr ? within % a.batch : within >> ccb;
                             const long long cc = a.rr ? within / a.batch : (within & ((1LL << ccb) - 1));
-                            const long long gp = RNS ? poly * a.mod_count + mslot : poly;
+                            long long gp = RNS ? poly * a.mod_count + mslot : poly;
+                            if constexpr (RNS)
+                                if (a.poly_order) gp = a.poly_order[gp];
                             tma_store_3d(&map_out, 0, (int) (cc << (S::C - S::CB)),
                                          (int) ((gp << (a.n - a.lo)) + ((long long) range << S::D)), src);
                         }
@@ -643,7 +663,21 @@ namespace gpuntt_b200
                         {
                             const long long grp = ww % tiles_per_range;
                             if constexpr (RNS)
-                                tma_store_4d(&map_out, 0, range << (S::KC - S::CB), mslot, (int) (grp << S::NPLOG), src);
+                            {
+                                if (a.poly_order)
+                                {
+#pragma unroll
+                                    for (int q = 0; q < (1 << S::NPLOG); q++)
+                                    {
+                                        const long long kq = (grp << S::NPLOG) + q;
+                                        if (kq < a.batch)
+                                            tma_store_3d(&map_out, 0, range << (S::KC - S::CB), a.poly_order[kq * a.mod_count + mslot],
+                                                         src + q * (S::TILE_SMEM >> S::NPLOG));
+                                    }
+                                }
+                                else
+                                    tma_store_4d(&map_out, 0, range << (S::KC - S::CB), mslot, (int) (grp << S::NPLOG), src);
+                            }
                             else
                                 tma_store_3d(&map_out, 0, range << (S::KC - S::CB), (int) (grp << S::NPLOG), src);
                         }
@@ -765,7 +799,7 @@ namespace gpuntt_b200
     //   else:    3-D view {2^CB (one 128-byte row), N / 2^CB rows, batch}; box {2^CB, 2^(KC-CB), 2^NPLOG}
     //   RNS (mod_count > 0; batch = polynomials per slot): strided maps see batch * mod_count polynomials, contiguous
     //   maps are 4-D {row, rows, slot, polynomial within the slot} so a tile holds polynomials of ONE modulus.
-    template <typename S> static bool make_map(CUtensorMap* map, const void* base, int n, int lo, int batch, int mod_count = 0)
+    template <typename S> static bool make_map(CUtensorMap* map, const void* base, int n, int lo, int batch, int mod_count = 0, bool one_poly_box = false)
     {
         using T = typename S::T;
         PFN_cuTensorMapEncodeTiled enc = get_encode();
@@ -781,6 +815,7 @@ namespace gpuntt_b200
             gdim[0] = 1ull << S::CB;
             gdim[1] = 1ull << (lo - S::CB);
             gdim[2] = ((cuuint64_t) batch * (mod_count > 0 ? mod_count : 1)) << (n - lo);
+            if (one_poly_box) gdim[2] = 1ull << 31; // Poly_Ordered: the slots may lie anywhere in a larger array of unknown size
             gstride[0] = 128;
             gstride[1] = (cuuint64_t) sizeof(T) << lo;
             box[0] = 1u << S::CB;
@@ -796,7 +831,13 @@ namespace gpuntt_b200
             gstride[1] = (cuuint64_t) sizeof(T) << n;
             box[0] = 1u << S::CB;
             box[1] = 1u << (S::KC - S::CB);
-            if (mod_count > 0)
+            if (mod_count > 0 && one_poly_box)
+            {
+                // Poly_Ordered: plain 3-D view of every polynomial, one polynomial per box
+                gdim[2] = 1ull << 30; // slots may lie anywhere in a larger array; 0x7fffffff stays out of range (ragged last tile)
+                box[2] = 1;
+            }
+            else if (mod_count > 0)
             {
                 rank = 4;
                 gdim[2] = (cuuint64_t) mod_count;
@@ -851,10 +892,12 @@ namespace gpuntt_b200
             const long long rows = ((long long) args.batch * (mc > 0 ? mc : 1)) << (args.n - args.lo);
             if (rows >= (1LL << 31)) return cudaErrorNotSupported;
         }
-        if (!make_map<S>(&map_in, args.in, args.n, args.lo, args.batch, mc)) return cudaErrorNotSupported;
+        bool opb = false;
+        if constexpr (RNS) opb = args.poly_order != nullptr;
+        if (!make_map<S>(&map_in, args.in, args.n, args.lo, args.batch, mc, opb)) return cudaErrorNotSupported;
         if (args.in == args.out)
             map_out = map_in;
-        else if (!make_map<S>(&map_out, args.out, args.n, args.lo, args.batch, mc))
+        else if (!make_map<S>(&map_out, args.out, args.n, args.lo, args.batch, mc, opb))
             return cudaErrorNotSupported;
         long long grid = (long long) sms * blocks_per_sm;
         if (grid > args.work) grid = args.work;
@@ -1139,8 +1182,9 @@ namespace gpuntt_b200
     // both the lazy-policy and the exact-policy kernel of every pass are enqueued and a device flag picks one.
     // flag_ws: one int of device scratch.  *launched = 0 when not covered.
     template <typename T>
-    cudaError_t fast_merge_rns(const T* in, T* out, const T* table, const T* mod_dev, const T* ninv_dev, const int* mod_order, int mod_count,
-                               int n_power, int plus, bool inverse, int batch, int* flag_ws, cudaStream_t st, int* launched,
+    cudaError_t fast_merge_rns(const T* in, T* out, const T* table, const T* mod_dev, const T* ninv_dev, const int* mod_order,
+                               const int* poly_order, int mod_count, int n_power, int plus, bool inverse, int batch, int* flag_ws,
+                               cudaStream_t st, int* launched,
                                void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t))
     {
         *launched = 0;
@@ -1161,6 +1205,7 @@ namespace gpuntt_b200
         a.mod_dev = mod_dev;
         a.ninv_dev = ninv_dev;
         a.mod_order = mod_order;
+        a.poly_order = poly_order;
         a.policy_flag = nullptr;
         int kind = 1;
         if (bits == 64)
@@ -1227,10 +1272,12 @@ namespace gpuntt_b200
         *launched = pl.npass;
         return cudaSuccess;
     }
-    template cudaError_t fast_merge_rns<uint64_t>(const uint64_t*, uint64_t*, const uint64_t*, const uint64_t*, const uint64_t*, const int*, int, int,
-                                                  int, bool, int, int*, cudaStream_t, int*, void (*)(int, cudaStream_t), void (*)(cudaStream_t));
-    template cudaError_t fast_merge_rns<uint32_t>(const uint32_t*, uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, const int*, int, int,
-                                                  int, bool, int, int*, cudaStream_t, int*, void (*)(int, cudaStream_t), void (*)(cudaStream_t));
+    template cudaError_t fast_merge_rns<uint64_t>(const uint64_t*, uint64_t*, const uint64_t*, const uint64_t*, const uint64_t*, const int*, const int*,
+                                                  int, int, int, bool, int, int*, cudaStream_t, int*, void (*)(int, cudaStream_t),
+                                                  void (*)(cudaStream_t));
+    template cudaError_t fast_merge_rns<uint32_t>(const uint32_t*, uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, const int*, const int*,
+                                                  int, int, int, bool, int, int*, cudaStream_t, int*, void (*)(int, cudaStream_t),
+                                                  void (*)(cudaStream_t));
 
     // (w, w') pairs of the 4-step twiddle matrix, once per call (the batch shares it)
     // t_lo > 0: entry i comes from the transposed index ((i mod 2^t_lo) << t_hi) | (i >> t_lo) (4-step inverse: the data

@@ -612,8 +612,9 @@ namespace gpuntt_b200
     // merge_fast.cu
     int fast_describe(int n_power, int element_bits, char* buf, size_t len);
     template <typename T>
-    cudaError_t fast_merge_rns(const T* in, T* out, const T* table, const T* mod_dev, const T* ninv_dev, const int* mod_order, int mod_count,
-                               int n_power, int plus, bool inverse, int batch, int* flag_ws, cudaStream_t st, int* launched,
+    cudaError_t fast_merge_rns(const T* in, T* out, const T* table, const T* mod_dev, const T* ninv_dev, const int* mod_order,
+                               const int* poly_order, int mod_count, int n_power, int plus, bool inverse, int batch, int* flag_ws,
+                               cudaStream_t st, int* launched,
                                void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t));
     cudaError_t fast_fourstep_inverse(const uint64_t* rows_in, uint64_t* work, uint64_t* dst, const uint64_t* n1_table,
                                       const uint64_t* n2_table, const uint64_t* w_table, void* w_pairs_ws, uint64_t p, uint64_t ninv,
@@ -843,7 +844,7 @@ namespace gpuntt_b200
             if (fe != cudaSuccess) return cuda_fail(fe, "fast_pass_kernel launch");
             if (launched > 0) return GPUNTT_B200_OK;
         }
-        if (rns && !d->is_signed && !g_force_generic.load() && d->ntt_layout == GPUNTT_B200_PER_POLYNOMIAL && !d->poly_order_dev)
+        if (rns && !d->is_signed && !g_force_generic.load() && d->ntt_layout == GPUNTT_B200_PER_POLYNOMIAL)
         {
             void* flag = nullptr;
             cudaError_t fe = get_workspace(d->stream, 7, sizeof(int), &flag);
@@ -851,8 +852,8 @@ namespace gpuntt_b200
             int launched = 0;
             fe = fast_merge_rns<T>(reinterpret_cast<const T*>(d->in), reinterpret_cast<T*>(d->out),
                                    reinterpret_cast<const T*>(d->root_of_unity_table), reinterpret_cast<const T*>(d->modulus_dev),
-                                   reinterpret_cast<const T*>(d->mod_inverse_dev), d->modulus_order_dev, d->mod_count, n, plus ? 1 : 0, inv,
-                                   d->batch_size,
+                                   reinterpret_cast<const T*>(d->mod_inverse_dev), d->modulus_order_dev, d->poly_order_dev, d->mod_count, n,
+                                   plus ? 1 : 0, inv, d->batch_size,
                                    reinterpret_cast<int*>(flag), st, &launched, prof_begin, prof_end);
             if (fe != cudaSuccess) return cuda_fail(fe, "fast_pass_kernel (RNS) launch");
             if (launched > 0) return GPUNTT_B200_OK;

@@ -442,6 +442,9 @@ def test_rns_ordered_entry_points(bits, logn, batch, mod_count):
                    poly_order_dev=porder_d.data_ptr())
     torch.cuda.synchronize()
     assert (to_host(d, bits).reshape(slots, n) == buf).all()
+    if batch % mod_count == 0 and logn >= (12 if bits == 64 else 14):
+        # two-pass ring, whole slots: the tuned RNS kernels (policy kernel + lazy/exact kernel per pass for 64-bit)
+        assert capi.lib().gpuntt_b200_last_launch_count() == (5 if bits == 64 else 2)
 
 
 @pytest.mark.parametrize("bits", [64, 32])
