@@ -176,6 +176,12 @@ template <typename T> static int fourstep_execute_t(const gpuntt_b200_4step_desc
             src = out;
         }
         bool columns_done = false;
+        // when the row phase takes the tuned kernels as well, the column epilogue leaves its products below 2p (one
+        // correction instead of two) and the rows' multiply-free first stages start from that bound
+        const bool lazy_rows = sizeof(T) == 8 && !rns && !g_force_generic.load() && fast_supported(lg2, 64) &&
+                               (uint64_t) d->modulus_value >= kF60ModulusMin && (uint64_t) d->modulus_value < kF60ModulusLimit &&
+                               (long long) batch * n1 <= 0x7fffffffLL && (((long long) batch * n1) << (lg2 - 8)) < (1LL << 31) &&
+                               (reinterpret_cast<uintptr_t>(fused ? (const void*) ws : (const void*) out) & 15) == 0; // = what fast_merge checks
         if constexpr (sizeof(T) == 8)
         {
             // tuned strided kernel with the W product as its epilogue (single modulus, F60 moduli)
@@ -187,7 +193,8 @@ template <typename T> static int fourstep_execute_t(const gpuntt_b200_4step_desc
                 int launched = 0;
                 we = fast_fourstep_columns(reinterpret_cast<const uint64_t*>(src), reinterpret_cast<uint64_t*>(work),
                                            reinterpret_cast<const uint64_t*>(d->n1_table), reinterpret_cast<const uint64_t*>(d->w_table), pairs,
-                                           (uint64_t) d->modulus_value, n, lg1, lg2, batch, st, &launched, prof_begin, prof_end);
+                                           (uint64_t) d->modulus_value, n, lg1, lg2, batch, st, &launched, prof_begin, prof_end,
+                                           lazy_rows ? 1 : 0);
                 if (we != cudaSuccess) return cuda_fail(we, "fast 4-step column pass launch");
                 columns_done = launched > 0;
             }
@@ -211,7 +218,21 @@ template <typename T> static int fourstep_execute_t(const gpuntt_b200_4step_desc
             rc = run_core<T>(cc);
             if (rc != GPUNTT_B200_OK) return rc;
         }
-        rc = row_transforms(work, work, lg2, (long long) batch * n1, d->n2_table, lg1, false);
+        bool rows_done = false;
+        if constexpr (sizeof(T) == 8)
+        {
+            if (columns_done && lazy_rows)
+            {
+                int launched = 0;
+                cudaError_t re = fast_merge<uint64_t>(reinterpret_cast<const uint64_t*>(work), reinterpret_cast<uint64_t*>(work),
+                                                      reinterpret_cast<const uint64_t*>(d->n2_table), (uint64_t) d->modulus_value, 0, lg2, 0,
+                                                      false, (int) ((long long) batch * n1), st, &launched, prof_begin, prof_end, 2);
+                if (re != cudaSuccess) return cuda_fail(re, "fast_pass_kernel launch");
+                rows_done = launched > 0;
+                if (!rows_done) return fail(GPUNTT_B200_ERR_CUDA, "4-step row phase: tuned kernels declined after a lazy column phase");
+            }
+        }
+        if (!rows_done) rc = row_transforms(work, work, lg2, (long long) batch * n1, d->n2_table, lg1, false);
         if (rc != GPUNTT_B200_OK) return rc;
         if (fused)
         {

@@ -188,6 +188,8 @@ namespace gpuntt_b200
         uint64_t mu; // 64-bit: floor(2^(63 + pbits) / p), 32-bit: floor(2^64 / p) -- companions without a division
         int pbits; // bit length of p
         int n, lo, plus, first, last, batch, rr;
+        int in_bound; // forward first pass of a cyclic transform: inputs are below in_bound * p (0/1: canonical)
+        int w_lazy;   // WMUL forward kernels: leave the products below 2p (one correction) instead of canonical
         int n_tw; // transform size (log2) for twiddle indexing when it differs from the layout size n (0: n)
         int cta_per_seg, seg_extra; // cta_per_seg > 0: every CTA works inside ONE twiddle segment; the first seg_extra segments get
                                     // cta_per_seg + 1 CTAs, the others cta_per_seg (set by launch_fast)
@@ -222,7 +224,8 @@ namespace gpuntt_b200
     __device__ __forceinline__ void fast_round(unsigned char* buf, const Twiddle<typename S::T>* __restrict__ tws,
                                                const typename ModOf<S>::type& M, int ctid,
                                                const Twiddle<typename S::T>& ninv,
-                                               const Twiddle<typename S::T>* __restrict__ wtile = nullptr, int lo = 0)
+                                               const Twiddle<typename S::T>* __restrict__ wtile = nullptr, int lo = 0, int in_bound = 1,
+                                               bool w_lazy = false)
     {
         using T = typename S::T;
         constexpr int E = 1 << R;
@@ -301,7 +304,10 @@ namespace gpuntt_b200
                         {
                             const Twiddle<T> tw{v[j].x, v[j].y};
                             const T r = M.mul(e[h + j], tw); // any 64-bit value in, [0,3p) out
-                            e[h + j] = canonical ? csub(csub(r, M.p + M.p), M.p) : r;
+                            if constexpr (S::INV)
+                                e[h + j] = r; // the Gentleman-Sande butterflies take [0,4p)
+                            else
+                                e[h + j] = canonical ? csub(csub(r, M.p + M.p), M.p) : csub(r, M.p + M.p);
                         }
                     }
                 }
@@ -322,7 +328,7 @@ namespace gpuntt_b200
                             // {1, 2, 6, 12}[it] * p, the twiddle-1 butterflies of stages 0..2 are bare add/subtract
                             if (TRIV && it < 3 && x == 0)
                             {
-                                const T K = M.triv_bound(it);
+                                const T K = M.triv_bound(it, in_bound);
 #pragma unroll
                                 for (int y = 0; y < (1 << ab); y++) M.add_sub(e[y], e[y | (1 << ab)], K);
                                 continue;
@@ -358,7 +364,7 @@ namespace gpuntt_b200
 #pragma unroll
                     for (int a = 0; a < E; a++) e[a] = M.canon_fwd(e[a]);
                 }
-                if constexpr (WMUL) w_product(true);
+                if constexpr (WMUL) w_product(!w_lazy);
             }
             else
             {
@@ -734,16 +740,17 @@ namespace gpuntt_b200
                         if constexpr (S::STRIDED && S::POL == 2 && S::G1 == 1)
                         {
                             if (triv)
-                                fast_round<S, S::R1, S::LB1, S::G1, FIN1, true, W1>(buf, tw1, M, tid, ninv, wtile, a.lo);
+                                fast_round<S, S::R1, S::LB1, S::G1, FIN1, true, W1>(buf, tw1, M, tid, ninv, wtile, a.lo,
+                                                                                     a.in_bound > 1 ? a.in_bound : 1, a.w_lazy != 0);
                             else
-                                fast_round<S, S::R1, S::LB1, S::G1, FIN1, false, W1>(buf, tw1, M, tid, ninv, wtile, a.lo);
+                                fast_round<S, S::R1, S::LB1, S::G1, FIN1, false, W1>(buf, tw1, M, tid, ninv, wtile, a.lo, 1, a.w_lazy != 0);
                         }
                         else
                             fast_round<S, S::R1, S::LB1, S::G1, FIN1>(buf, tw1, M, tid, ninv);
                         if constexpr (S::R2 > 0)
                         {
                             consumer_sync();
-                            fast_round<S, S::R2, S::LB2, S::G2, FIN2, false, W2>(buf, tw2, M, tid, ninv, wtile, a.lo);
+                            fast_round<S, S::R2, S::LB2, S::G2, FIN2, false, W2>(buf, tw2, M, tid, ninv, wtile, a.lo, 1, a.w_lazy != 0);
                         }
                     }
                     else
@@ -1021,7 +1028,7 @@ namespace gpuntt_b200
     template <typename T>
     cudaError_t fast_merge(const T* in, T* out, const T* table, T p, T ninv, int n_power, int plus, bool inverse,
                            int batch, cudaStream_t st, int* launched, void (*prof_begin)(int, cudaStream_t),
-                           void (*prof_end)(cudaStream_t))
+                           void (*prof_end)(cudaStream_t), int in_bound)
     {
         *launched = 0;
         if (!fast_supported(n_power, (int) sizeof(T) * 8)) return cudaSuccess;
@@ -1051,6 +1058,7 @@ namespace gpuntt_b200
             a.n = n_power;
             a.plus = plus;
             a.batch = batch;
+            a.in_bound = in_bound;
             using Cf = Shape<T, false, 2, false, 4, 4, 12, GPUNTT_FAST_P1_NPLOG>;
             using Ci = Shape<T, true, 1, false, 4, 4, 12, 1>;
             using Cfx = Shape<T, false, 0, false, 4, 4, 12, 1>;
@@ -1297,7 +1305,7 @@ namespace gpuntt_b200
     // entries), canonical outputs.  Single modulus, 64-bit, F60 moduli; *launched = 0 when not covered.
     cudaError_t fast_fourstep_columns(const uint64_t* in, uint64_t* out, const uint64_t* n1_table, const uint64_t* w_table,
                                       void* w_pairs_ws, uint64_t p, int n_power, int lg1, int lg2, int batch, cudaStream_t st,
-                                      int* launched, void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t))
+                                      int* launched, void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t), int w_lazy)
     {
         using T = uint64_t;
         *launched = 0;
@@ -1322,6 +1330,7 @@ namespace gpuntt_b200
         a.last = 0;
         a.batch = batch;
         a.w_pairs = w_pairs_ws;
+        a.w_lazy = w_lazy; // products below 2p (the tuned row phase starts from that bound) or canonical
         a.work = (long long) batch << (lg2 - (12 - lg1));
         a.rr = 1; // column-chunk-major round robin: the polynomials of a chunk share the pair fetch through the L2
         const long long N = 1LL << n_power;
@@ -1465,8 +1474,8 @@ namespace gpuntt_b200
     }
 
     template cudaError_t fast_merge<uint64_t>(const uint64_t*, uint64_t*, const uint64_t*, uint64_t, uint64_t, int, int, bool,
-                                              int, cudaStream_t, int*, void (*)(int, cudaStream_t), void (*)(cudaStream_t));
+                                              int, cudaStream_t, int*, void (*)(int, cudaStream_t), void (*)(cudaStream_t), int);
     template cudaError_t fast_merge<uint32_t>(const uint32_t*, uint32_t*, const uint32_t*, uint32_t, uint32_t, int, int, bool,
-                                              int, cudaStream_t, int*, void (*)(int, cudaStream_t), void (*)(cudaStream_t));
+                                              int, cudaStream_t, int*, void (*)(int, cudaStream_t), void (*)(cudaStream_t), int);
 
 } // namespace gpuntt_b200

@@ -622,11 +622,12 @@ namespace gpuntt_b200
                                       void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t));
     cudaError_t fast_fourstep_columns(const uint64_t* in, uint64_t* out, const uint64_t* n1_table, const uint64_t* w_table,
                                       void* w_pairs_ws, uint64_t p, int n_power, int lg1, int lg2, int batch, cudaStream_t st,
-                                      int* launched, void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t));
+                                      int* launched, void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t), int w_lazy);
     template <typename T>
     cudaError_t fast_merge(const T* in, T* out, const T* table, T p, T ninv, int n_power, int plus, bool inverse,
                            int batch, cudaStream_t st, int* launched, void (*prof_begin)(int, cudaStream_t),
-                           void (*prof_end)(cudaStream_t));
+                           void (*prof_end)(cudaStream_t), int in_bound = 1);
+    bool fast_supported(int n_power, int element_bits);
 
     static int fail(int code, const std::string& msg)
     {

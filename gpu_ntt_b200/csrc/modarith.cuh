@@ -257,7 +257,11 @@ namespace gpuntt_b200
             X = s;
         }
         // bound (multiple of p) of the values before stage it of a first cyclic round with canonical inputs
-        __device__ __forceinline__ T triv_bound(int it) const { return (it == 0 ? 1 : it == 1 ? 2 : 6) * p; }
+        // in_bound: the inputs are below in_bound * p (1: canonical; 2: the 4-step column phase leaves values below 2p)
+        __device__ __forceinline__ T triv_bound(int it, int in_bound = 1) const
+        {
+            return (T) (it == 0 ? in_bound : it == 1 ? 2 * in_bound : (in_bound == 1 ? 6 : 8)) * p;
+        }
         // [0, 13p) -> [0, p)
         __device__ __forceinline__ T canon_fwd(T x) const
         {
@@ -298,7 +302,7 @@ namespace gpuntt_b200
             X = s;
         }
         // bound (multiple of p) of the values before stage it of a first cyclic round with canonical inputs
-        __device__ __forceinline__ T triv_bound(int it) const { return (it == 0 ? 1 : it == 1 ? 2 : 4) * p; }
+        __device__ __forceinline__ T triv_bound(int it, int = 1) const { return (it == 0 ? 1 : it == 1 ? 2 : 4) * p; }
         __device__ __forceinline__ T canon_fwd(T x) const // [0, 8p) -> [0, p)
         {
             const T q = __umulhi(x, red_m); // in {floor(x/p) - 1, floor(x/p)}
