@@ -26,3 +26,8 @@ for tool in memcheck racecheck; do
   timeout 900 compute-sanitizer --tool $tool --kernel-regex kns=fast_pass python /tmp/san_case.py > gpurun_out/sanitizer_$tool.txt 2>&1
   echo "== $tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|ok |Error|hazard" gpurun_out/sanitizer_$tool.txt | head -20
 done
+# the RNS, ordered and 4-step entry points on the tuned kernels (small parametrisations of the parity tests)
+timeout 1200 compute-sanitizer --tool memcheck --kernel-regex kns=fast_pass python -m pytest tests/test_merge_gpu.py tests/test_4step_gpu.py -m gpu -x -q \
+    -k "test_rns_form_tuned_kernels and (64-12 or 64-13 or 32-14) or test_rns_ordered_entry_points and 12-8-4 or test_4step_fused_and_reference_contracts and (12-3 or 13-1 or 16-2) and 64" \
+    > gpurun_out/sanitizer_memcheck_entry_points.txt 2>&1
+echo "== memcheck over RNS / ordered / 4-step tests rc=$?"; grep -E "ERROR SUMMARY|passed|failed|Error" gpurun_out/sanitizer_memcheck_entry_points.txt | head
