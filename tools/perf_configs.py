@@ -162,9 +162,9 @@ def main():
     fourstep_case("C4 4-step inverse fused", 24, 16, max(2, it // 4), capi.FOURSTEP_FUSED, inverse=True)
     fourstep_case("4-step fused logN=20", 20, 64, max(2, it // 4), capi.FOURSTEP_FUSED)
     if not args.quick:
-        for logn in (12, 13, 14, 15, 17, 18, 20, 22, 24):
+        for logn in (8, 10, 11, 12, 13, 14, 15, 17, 18, 20, 22, 24):
             merge_case(f"u64 logN={logn}", logn, max(1, (1 << 26) >> logn), 64, X_N_minus, it)
-        for logn in (12, 16):
+        for logn in (10, 12, 16):
             merge_case(f"u32 logN={logn}", logn, max(1, (1 << 27) >> logn), 32, X_N_minus, it)
 
 
