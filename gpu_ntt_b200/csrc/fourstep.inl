@@ -330,6 +330,34 @@ static int fourstep_execute(const gpuntt_b200_4step_desc* d)
     if (d->mod_count > 0 && d->direction == GPUNTT_B200_INVERSE && !d->mod_inverse_dev)
         return fail(GPUNTT_B200_ERR_ARGUMENT, "RNS inverse needs mod_inverse_dev");
     if (d->mod_count == 0 && d->modulus_value < 5) return fail(GPUNTT_B200_ERR_ARGUMENT, "modulus_value too small");
+    // The reference's own 4-step examples call the RNS overload with ONE modulus held on the device
+    // (test_4step_ntt.cu:126-154).  The tuned kernels take the modulus as a launch argument and pick their arithmetic
+    // policy from it on the host, so that one Modulus (and n^-1) is read back here -- 24 + 8 bytes, after the work
+    // already enqueued on the stream -- and the call continues as the single-modulus form.  Under stream capture no
+    // read-back is possible and the device-modulus kernels run instead.
+    gpuntt_b200_4step_desc single;
+    if (d->mod_count == 1 && d->element_bits == 64 && !g_force_generic.load())
+    {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing((cudaStream_t) d->stream, &cap);
+        if (cap == cudaStreamCaptureStatusNone)
+        {
+            uint64_t host_mod[3] = {0, 0, 0}, host_ninv = 0;
+            cudaError_t e = cudaMemcpyAsync(host_mod, d->modulus_dev, sizeof(host_mod), cudaMemcpyDeviceToHost, (cudaStream_t) d->stream);
+            if (e == cudaSuccess && d->direction == GPUNTT_B200_INVERSE)
+                e = cudaMemcpyAsync(&host_ninv, d->mod_inverse_dev, sizeof(host_ninv), cudaMemcpyDeviceToHost, (cudaStream_t) d->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t) d->stream);
+            if (e != cudaSuccess) return cuda_fail(e, "4-step modulus read-back");
+            if (host_mod[0] < 5) return fail(GPUNTT_B200_ERR_ARGUMENT, "modulus_value too small");
+            single = *d;
+            single.mod_count = 0;
+            single.modulus_dev = nullptr;
+            single.mod_inverse_dev = nullptr;
+            single.modulus_value = host_mod[0];
+            single.mod_inverse_value = host_ninv;
+            d = &single;
+        }
+    }
     if (d->element_bits == 64) return fourstep_execute_t<uint64_t>(d);
     return fourstep_execute_t<uint32_t>(d);
 }
