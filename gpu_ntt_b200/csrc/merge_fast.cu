@@ -134,14 +134,17 @@ namespace gpuntt_b200
     // above the F60 range: correction on every stage), 2 F60 / L32 (forward).
     // NT: contiguous passes of transforms SHORTER than a tile row group (the 4-step inverse row phase, N = n1 <= 256): twiddles
     // depend on the low NT index bits only and a tile holds several whole transforms.
-    template <typename T_, bool INV_, int POL_, bool STRIDED_, int R1_, int R2_, int K_, int NPLOG_, int NT_ = 0> struct Shape
+    // R3: a third register round below the other two (contiguous NT passes only): whole transforms of 2^9 .. 2^12 elements in
+    // ONE pass (the small rings, fast_small below).
+    template <typename T_, bool INV_, int POL_, bool STRIDED_, int R1_, int R2_, int K_, int NPLOG_, int NT_ = 0, int R3_ = 0> struct Shape
     {
         using T = T_;
         static constexpr int POL = POL_;
         static constexpr bool INV = INV_, FAST = POL_ != 0, STRIDED = STRIDED_;
         static_assert(POL_ == 0 || POL_ == 1 || (POL_ == 2 && !INV_), "policy 2 is forward-only");
-        static constexpr int R1 = R1_, R2 = R2_, K = K_, NPLOG = NPLOG_;
-        static constexpr int D = R1 + R2;
+        static constexpr int R1 = R1_, R2 = R2_, R3 = R3_, K = K_, NPLOG = NPLOG_;
+        static constexpr int D = R1 + R2 + R3;
+        static_assert(R3_ == 0 || (!STRIDED_ && NT_ > 0 && R2_ > 0), "three rounds: contiguous whole-transform passes only");
         static constexpr int C = STRIDED ? (K - D) : 0;
         static constexpr int KC = K - NPLOG;          // contiguous elements per polynomial in a tile
         static constexpr int NT = NT_;
@@ -149,10 +152,11 @@ namespace gpuntt_b200
         static constexpr int CB = (sizeof(T) == 8) ? 4 : 5; // log2 elements per 128-byte row
         static constexpr int ROWS = (1 << K) >> CB;
         static constexpr int TILE_SMEM = ROWS * 128;
-        static constexpr int LB1 = C + R2, LB2 = C;   // lowest local bit of the high / low round
+        static constexpr int LB1 = C + R2 + R3, LB2 = C + R3, LB3 = C;   // lowest local bit of the high / low / third round
         static constexpr int G1 = 1 << (KTW - LB1 - R1), G2 = 1 << (KTW - LB2 - R2); // twiddle groups
-        static constexpr int TW1 = ((1 << R1) - 1) * G1, TW2 = ((1 << R2) - 1) * G2;
-        static constexpr int TW_SMEM = (TW1 + TW2) * (int) sizeof(Twiddle<T>);
+        static constexpr int G3 = R3 > 0 ? (1 << (KTW - LB3 - R3)) : 1;
+        static constexpr int TW1 = ((1 << R1) - 1) * G1, TW2 = ((1 << R2) - 1) * G2, TW3 = ((1 << R3) - 1) * G3;
+        static constexpr int TW_SMEM = (TW1 + TW2 + TW3) * (int) sizeof(Twiddle<T>);
         static constexpr int SMEM = 2 * TILE_SMEM + TW_SMEM + 128 + 1024; // barriers, segment constants + slack to align the tiles to 1 KiB
         static_assert(LB2 == 0 || LB2 >= CB, "low round must start at bit 0 or on a row boundary");
         static_assert(LB1 >= CB, "high round must start on a row boundary");
@@ -433,6 +437,7 @@ namespace gpuntt_b200
         unsigned char* bufs = smem;                                                    // 2 tile buffers
         Twiddle<T>* tw1 = reinterpret_cast<Twiddle<T>*>(smem + 2 * S::TILE_SMEM);       // high round, slot-major
         Twiddle<T>* tw2 = tw1 + S::TW1;                                                 // low round
+        Twiddle<T>* tw3 = tw2 + S::TW2;                                                 // third round (small rings)
         uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * S::TILE_SMEM + S::TW_SMEM); // full[2], done[2]
 
         const int tid = threadIdx.x;
@@ -617,11 +622,12 @@ namespace gpuntt_b200
                 // (w, w') pairs for both rounds, slot-major: entry (slot, group) at slot*G + group
                 const int j0 = S::STRIDED ? (range << S::D) : (S::NT ? 0 : (range << S::KC)); // index (>> lo) of the tile's first row
                 const int ntw = a.n_tw ? a.n_tw : n;
-                for (int i = tid; i < S::TW1 + S::TW2; i += kFastThreads)
+                for (int i = tid; i < S::TW1 + S::TW2 + S::TW3; i += kFastThreads)
                 {
-                    const bool hi = i < S::TW1;
-                    const int ii = hi ? i : i - S::TW1;
-                    const int R = hi ? S::R1 : S::R2, LB = hi ? S::LB1 : S::LB2, G = hi ? S::G1 : S::G2;
+                    const bool hi = i < S::TW1, third = S::R3 > 0 && i >= S::TW1 + S::TW2;
+                    const int ii = hi ? i : (third ? i - S::TW1 - S::TW2 : i - S::TW1);
+                    const int R = hi ? S::R1 : (third ? S::R3 : S::R2), LB = hi ? S::LB1 : (third ? S::LB3 : S::LB2),
+                              G = hi ? S::G1 : (third ? S::G3 : S::G2);
                     const int slot = ii / G, group = ii % G;
                     // slot -> (ab, x): slot = 2^(R-1-ab) - 1 + x
                     const int lvl = 31 - __clz(slot + 1); // = R-1-ab
@@ -632,9 +638,9 @@ namespace gpuntt_b200
                     const long long idx = ((long long) a.plus << s) + (J >> (rb0 + ab + 1)) + x;
                     const T wv = seg_table[idx];
                     if constexpr (sizeof(T) == 8)
-                        (hi ? tw1 : tw2)[ii] = Twiddle<T>{wv, shoup_companion_mu(wv, seg_p, seg_mu, seg_pbits)};
+                        (hi ? tw1 : (third ? tw3 : tw2))[ii] = Twiddle<T>{wv, shoup_companion_mu(wv, seg_p, seg_mu, seg_pbits)};
                     else
-                        (hi ? tw1 : tw2)[ii] = Twiddle<T>{wv, shoup_companion_mu32(wv, seg_p, seg_mu)};
+                        (hi ? tw1 : (third ? tw3 : tw2))[ii] = Twiddle<T>{wv, shoup_companion_mu32(wv, seg_p, seg_mu)};
                 }
             }
             __syncthreads();
@@ -735,7 +741,7 @@ namespace gpuntt_b200
 #ifdef GPUNTT_EXPERIMENT_NOCANON // timing experiment only (lazy outputs): what the final canonicalisation costs
                         constexpr bool FIN1 = false, FIN2 = false;
 #else
-                        constexpr bool FIN1 = !S::STRIDED && S::R2 == 0, FIN2 = !S::STRIDED;
+                        constexpr bool FIN1 = !S::STRIDED && S::R2 == 0, FIN2 = !S::STRIDED && S::R3 == 0;
 #endif
                         if constexpr (S::STRIDED && S::POL == 2 && S::G1 == 1)
                         {
@@ -752,9 +758,19 @@ namespace gpuntt_b200
                             consumer_sync();
                             fast_round<S, S::R2, S::LB2, S::G2, FIN2, false, W2>(buf, tw2, M, tid, ninv, wtile, a.lo, 1, a.w_lazy != 0);
                         }
+                        if constexpr (S::R3 > 0)
+                        {
+                            consumer_sync();
+                            fast_round<S, S::R3, S::LB3, S::G3, true>(buf, tw3, M, tid, ninv);
+                        }
                     }
                     else
                     {
+                        if constexpr (S::R3 > 0)
+                        {
+                            fast_round<S, S::R3, S::LB3, S::G3, false>(buf, tw3, M, tid, ninv);
+                            consumer_sync();
+                        }
                         if constexpr (S::R2 > 0)
                         {
                             fast_round<S, S::R2, S::LB2, S::G2, false, false, W2>(buf, tw2, M, tid, ninv, wtile, a.lo);
@@ -766,6 +782,14 @@ namespace gpuntt_b200
                                 fast_round<S, S::R1, S::LB1, S::G1, true, false, W1>(buf, tw1, M, tid, ninv, wtile, a.lo);
                             else
                                 fast_round<S, S::R1, S::LB1, S::G1, false, false, W1>(buf, tw1, M, tid, ninv, wtile, a.lo);
+                        }
+                        else if constexpr (S::NT > 0)
+                        {
+                            // whole transforms in the tile: the top round is the last one of a single-pass inverse (n^-1 there)
+                            if (a.last)
+                                fast_round<S, S::R1, S::LB1, S::G1, true>(buf, tw1, M, tid, ninv);
+                            else
+                                fast_round<S, S::R1, S::LB1, S::G1, false>(buf, tw1, M, tid, ninv);
                         }
                         else
                             fast_round<S, S::R1, S::LB1, S::G1, false>(buf, tw1, M, tid, ninv);
@@ -1023,6 +1047,82 @@ namespace gpuntt_b200
         }
     }
 
+    // Small rings (replaces ForwardCoreLowRing / InverseCoreLowRing and the one-launch plans, ntt.cu:11-433 of the
+    // reference): 2^7 .. 2^11 (64-bit) / 2^8 .. 2^12 (32-bit).  The [batch][N] array is walked as chunks of one tile row
+    // group (2048 / 4096 elements); a tile holds whole transforms, so ONE pass with two or three register rounds does
+    // every stage, canonicalises (forward) or applies n^-1 (inverse), and the data makes one HBM round trip.
+    // Needs batch * N to be a whole number of chunks; anything else stays on the generic kernel.
+    bool fast_small_supported(int n_power, int element_bits)
+    {
+        return element_bits == 64 ? (n_power >= 7 && n_power <= 11) : (n_power >= 8 && n_power <= 12);
+    }
+    template <typename T, bool INV, int POL> static cudaError_t launch_small(int n_power, const FastArgs<T>& s, cudaStream_t st)
+    {
+        if constexpr (sizeof(T) == 8)
+        {
+            switch (n_power)
+            {
+                case 7: return launch_fast<Shape<T, INV, POL, false, 3, 4, 12, 1, 7>>(s, st);
+                case 8: return launch_fast<Shape<T, INV, POL, false, 4, 4, 12, 1, 8>>(s, st);
+                case 9: return launch_fast<Shape<T, INV, POL, false, 2, 3, 12, 1, 9, 4>>(s, st);
+                case 10: return launch_fast<Shape<T, INV, POL, false, 3, 3, 12, 1, 10, 4>>(s, st);
+                case 11: return launch_fast<Shape<T, INV, POL, false, 3, 4, 12, 1, 11, 4>>(s, st);
+                default: return cudaErrorNotSupported;
+            }
+        }
+        else
+        {
+            switch (n_power)
+            {
+                case 8: return launch_fast<Shape<T, INV, POL, false, 3, 5, 13, 1, 8>>(s, st);
+                case 9: return launch_fast<Shape<T, INV, POL, false, 4, 5, 13, 1, 9>>(s, st);
+                case 10: return launch_fast<Shape<T, INV, POL, false, 5, 5, 13, 1, 10>>(s, st);
+                case 11: return launch_fast<Shape<T, INV, POL, false, 3, 3, 13, 1, 11, 5>>(s, st);
+                case 12: return launch_fast<Shape<T, INV, POL, false, 3, 4, 13, 1, 12, 5>>(s, st);
+                default: return cudaErrorNotSupported;
+            }
+        }
+    }
+    // a: table / p / ninv / mu / pbits / plus filled in by fast_merge
+    template <typename T>
+    static cudaError_t fast_small(const FastArgs<T>& a, const T* in, T* out, int n_power, bool inverse, int batch, cudaStream_t st, int* launched,
+                                  void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t))
+    {
+        constexpr int KC = sizeof(T) == 8 ? 11 : 12; // chunk = one row group of a two-group tile
+        const long long elems = (long long) batch << n_power;
+        if (elems & ((1LL << KC) - 1)) return cudaSuccess;
+        const long long chunks = elems >> KC;
+        if (chunks > 0x7fffffffLL) return cudaSuccess;
+        FastArgs<T> s = a;
+        s.in = in;
+        s.out = out;
+        s.n = KC;
+        s.n_tw = n_power;
+        s.lo = 0;
+        s.first = 1;
+        s.last = 1;
+        s.batch = (int) chunks;
+        s.work = (chunks + 1) >> 1;
+        // arithmetic policy: 64-bit forward F60, inverse lazy; 32-bit forward lazy (p <= 2^29), inverse exact
+        bool covered;
+        if constexpr (sizeof(T) == 8)
+            covered = inverse ? ((uint64_t) a.p < kFastModulusLimit) : ((uint64_t) a.p >= kF60ModulusMin && (uint64_t) a.p < kF60ModulusLimit);
+        else
+            covered = inverse || (uint32_t) a.p < kL32ModulusLimit;
+        if (!covered) return cudaSuccess;
+        cudaError_t e;
+        prof_begin(1, st);
+        if constexpr (sizeof(T) == 8)
+            e = inverse ? launch_small<T, true, 1>(n_power, s, st) : launch_small<T, false, 2>(n_power, s, st);
+        else
+            e = inverse ? launch_small<T, true, 0>(n_power, s, st) : launch_small<T, false, 2>(n_power, s, st);
+        prof_end(st);
+        if (e == cudaErrorNotSupported) return cudaSuccess; // no tensor maps: generic path
+        if (e != cudaSuccess) return e;
+        *launched = 1;
+        return cudaSuccess;
+    }
+
     // Returns cudaSuccess and sets *launched to the number of kernels, or *launched = 0 if this
     // transform is not covered (the caller then uses the generic path).
     template <typename T>
@@ -1031,8 +1131,31 @@ namespace gpuntt_b200
                            void (*prof_end)(cudaStream_t), int in_bound)
     {
         *launched = 0;
-        if (!fast_supported(n_power, (int) sizeof(T) * 8)) return cudaSuccess;
         if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return cudaSuccess;
+        if (fast_small_supported(n_power, (int) sizeof(T) * 8))
+        {
+            if (sizeof(T) == 4 && ((uint32_t) p >= (1u << 30) || (uint32_t) p < 3)) return cudaSuccess;
+            FastArgs<T> a{};
+            a.table = table;
+            a.p = p;
+            a.ninv_w = ninv;
+            a.ninv_wq = inverse ? shoup_companion(ninv, p) : 0;
+            if constexpr (sizeof(T) == 8)
+            {
+                a.pbits = 64 - __builtin_clzll((unsigned long long) p);
+                const unsigned __int128 m = (((unsigned __int128) 1) << (63 + a.pbits)) / (unsigned __int128) p;
+                a.mu = (m >> 64) ? ~0ull : (uint64_t) m;
+            }
+            else
+            {
+                a.pbits = 32 - __builtin_clz((unsigned) p);
+                a.mu = ~0ull / (uint64_t) p;
+            }
+            a.plus = plus;
+            a.in_bound = 1;
+            return fast_small<T>(a, in, out, n_power, inverse, batch, st, launched, prof_begin, prof_end);
+        }
+        if (!fast_supported(n_power, (int) sizeof(T) * 8)) return cudaSuccess;
         // TMA coordinates are signed 32-bit: the matrix-row index of the finest strided pass must fit
         if (((long long) batch << (n_power - (sizeof(T) == 8 ? 8 : 10))) >= (1LL << 31)) return cudaSuccess;
         if constexpr (sizeof(T) == 8)

@@ -535,3 +535,40 @@ def test_cuda_graph_capture_and_replay(bits, logn, batch):
     torch.cuda.synchronize()
     assert (to_host(fwd, bits).ravel() == O.merge_ntt(y, P).ravel()).all()
     assert (to_host(back, bits).ravel() == y).all()
+
+
+@pytest.mark.parametrize("bits", [64, 32])
+@pytest.mark.parametrize("poly", [O.X_N_minus, O.X_N_plus])
+@pytest.mark.parametrize("logn", [7, 8, 9, 10, 11, 12])
+def test_small_rings_single_pass_tuned_kernels(bits, poly, logn):
+    """Rings of 2^7..2^11 (64-bit) / 2^8..2^12 (32-bit) whose batch fills whole 2048/4096-element chunks run as ONE launch of
+    the tuned kernel (whole transforms inside a tile, two or three register rounds; replaces the reference's LowRing
+    kernels and one-launch plans, ntt.cu:11-433).  Batches: one chunk (half-empty tile), an odd number of chunks, and enough
+    chunks that every CTA of the persistent grid gets several tiles.  The same calls on the generic kernel agree."""
+    small = (7 <= logn <= 11) if bits == 64 else (8 <= logn <= 12)
+    if not small:
+        pytest.skip("not a small-ring size for this width")
+    chunk = 2048 if bits == 64 else 4096
+    P = O.merge_params(logn, poly, bits)
+    for chunks in (1, 5, 1500):
+        batch = (chunks * chunk) >> logn
+        x = O.example_input(P.modulus, batch << logn, seed=logn + chunks)
+        want = O.merge_ntt(x, P)
+        for inplace in (True, False):
+            got = run_fwd(x, P, bits, poly, inplace=inplace)
+            assert capi.lib().gpuntt_b200_last_launch_count() == 1, "forward did not take the single-pass tuned kernel"
+            assert (got == want).all(), (chunks, inplace)
+            back = run_inv(want, P, bits, poly, inplace=inplace)
+            assert capi.lib().gpuntt_b200_last_launch_count() == 1, "inverse did not take the single-pass tuned kernel"
+            assert (back == x).all(), (chunks, inplace)
+        capi.lib().gpuntt_b200_force_generic_path(1)
+        try:
+            assert (run_fwd(x, P, bits, poly) == want).all()
+            assert (run_inv(want, P, bits, poly) == x).all()
+        finally:
+            capi.lib().gpuntt_b200_force_generic_path(0)
+    # a batch that does not fill whole chunks stays on the generic kernel and is still exact
+    batch = ((3 * chunk) >> logn) + 1
+    if (batch << logn) % chunk:
+        x = O.example_input(P.modulus, batch << logn, seed=99)
+        assert (run_fwd(x, P, bits, poly) == O.merge_ntt(x, P)).all()

@@ -9,7 +9,7 @@
 // so the two binaries differ in nothing but the library behind the API.  Each case checks polynomial 0 and the last
 // polynomial against the library's own NTTCPU (bit-exact) before it is timed with CUDA events.
 //
-//   api_bench <label> [c2|c2inv|c3|c4|sweep ...]     one JSON object per line
+//   api_bench <label> [c2|c2inv|c3|c4|sweep|small|fhe ...]     one JSON object per line
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -71,9 +71,11 @@ template <typename T> static std::vector<T> random_poly(size_t n, T p, unsigned 
 }
 
 // Merge-NTT, single modulus, in place (the call BASELINE.json's metric is quoted on).
-template <typename T> static void merge_case(const char* name, int logn, int batch, bool inverse, bool round_trip, int iters)
+template <typename T>
+static void merge_case(const char* name, int logn, int batch, bool inverse, bool round_trip, int iters,
+                       ReductionPolynomial ring = ReductionPolynomial::X_N_minus, int mod_count = 0)
 {
-    NTTParameters<T> P(logn, ReductionPolynomial::X_N_minus);
+    NTTParameters<T> P(logn, ring);
     NTTCPU<T> cpu(P);
     const size_t n = (size_t) 1 << logn;
     std::vector<T> a = random_poly<T>(n, P.modulus.value, 0), b = random_poly<T>(n, P.modulus.value, 1);
@@ -92,12 +94,47 @@ template <typename T> static void merge_case(const char* name, int logn, int bat
     CK(cudaMemcpy(dft, ft.data(), sizeof(T) * ft.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dit, it.data(), sizeof(T) * it.size(), cudaMemcpyHostToDevice));
     ntt_configuration<T> cf = {.n_power = logn, .ntt_type = FORWARD, .ntt_layout = PerPolynomial,
-                               .reduction_poly = ReductionPolynomial::X_N_minus, .zero_padding = false, .stream = 0};
+                               .reduction_poly = ring, .zero_padding = false, .stream = 0};
     ntt_configuration<T> ci = {.n_power = logn, .ntt_type = INVERSE, .ntt_layout = PerPolynomial,
-                               .reduction_poly = ReductionPolynomial::X_N_minus, .zero_padding = false,
+                               .reduction_poly = ring, .zero_padding = false,
                                .mod_inverse = P.n_inv, .stream = 0};
-    auto fwd = [&]() { GPU_NTT_Inplace(d, dft, P.modulus, cf, batch); };
-    auto inv = [&]() { GPU_INTT_Inplace(d, dit, P.modulus, ci, batch); };
+    // RNS overloads (mod_count > 0): mod_count slots that all hold the pooled prime of this ring size (the timing does not
+    // depend on the moduli being distinct; polynomial b uses slot b % mod_count, ntt.cu:613-619), tables 1 << n_power apart
+    Modulus<T>* dmod = nullptr;
+    Ninverse<T>* dninv = nullptr;
+    Root<T>*rft = nullptr, *rit = nullptr;
+    if (mod_count > 0)
+    {
+        std::vector<Modulus<T>> hm(mod_count, P.modulus);
+        std::vector<Ninverse<T>> hn(mod_count, P.n_inv);
+        CK(cudaMalloc(&dmod, sizeof(Modulus<T>) * mod_count));
+        CK(cudaMalloc(&dninv, sizeof(Ninverse<T>) * mod_count));
+        CK(cudaMemcpy(dmod, hm.data(), sizeof(Modulus<T>) * mod_count, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dninv, hn.data(), sizeof(Ninverse<T>) * mod_count, cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&rft, sizeof(T) * n * mod_count));
+        CK(cudaMalloc(&rit, sizeof(T) * n * mod_count));
+        for (int m = 0; m < mod_count; m++)
+        {
+            CK(cudaMemcpy(rft + n * m, ft.data(), sizeof(T) * ft.size(), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(rit + n * m, it.data(), sizeof(T) * it.size(), cudaMemcpyHostToDevice));
+        }
+    }
+    ntt_rns_configuration<T> rf = {.n_power = logn, .ntt_type = FORWARD, .ntt_layout = PerPolynomial,
+                                   .reduction_poly = ring, .zero_padding = false, .stream = 0};
+    ntt_rns_configuration<T> ri = {.n_power = logn, .ntt_type = INVERSE, .ntt_layout = PerPolynomial,
+                                   .reduction_poly = ring, .zero_padding = false, .mod_inverse = dninv, .stream = 0};
+    auto fwd = [&]() {
+        if (mod_count > 0)
+            GPU_NTT_Inplace(d, rft, dmod, rf, batch, mod_count);
+        else
+            GPU_NTT_Inplace(d, dft, P.modulus, cf, batch);
+    };
+    auto inv = [&]() {
+        if (mod_count > 0)
+            GPU_INTT_Inplace(d, rit, dmod, ri, batch, mod_count);
+        else
+            GPU_INTT_Inplace(d, dit, P.modulus, ci, batch);
+    };
     // parity against the library's own CPU transform
     bool ok = true;
     std::vector<T> h(n);
@@ -126,14 +163,18 @@ template <typename T> static void merge_case(const char* name, int logn, int bat
     double ms = round_trip ? time_ms([&]() { fwd(); inv(); }, iters) : (inverse ? time_ms(inv, iters) : time_ms(fwd, iters));
     double ntts = (double) batch * (round_trip ? 2 : 1);
     double gbs = 2.0 * n * sizeof(T) * ntts / (ms * 1e-3) / 1e9;
-    printf("{\"lib\": \"%s\", \"case\": \"%s\", \"bits\": %d, \"logn\": %d, \"batch\": %d, \"op\": \"%s\", \"parity_vs_NTTCPU\": %s, "
-           "\"ms\": %.4f, \"ntt_per_s\": %.1f, \"alg_GBps\": %.1f}\n",
-           g_label, name, (int) sizeof(T) * 8, logn, batch, round_trip ? "fwd+inv" : (inverse ? "inv" : "fwd"), ok ? "true" : "false",
+    printf("{\"lib\": \"%s\", \"case\": \"%s\", \"bits\": %d, \"logn\": %d, \"batch\": %d, \"ring\": \"%s\", \"mod_count\": %d, \"op\": \"%s\", "
+           "\"parity_vs_NTTCPU\": %s, \"ms\": %.4f, \"ntt_per_s\": %.1f, \"alg_GBps\": %.1f}\n",
+           g_label, name, (int) sizeof(T) * 8, logn, batch, ring == ReductionPolynomial::X_N_minus ? "X^N-1" : "X^N+1", mod_count, round_trip ? "fwd+inv" : (inverse ? "inv" : "fwd"), ok ? "true" : "false",
            ms, ntts / (ms * 1e-3), gbs);
     fflush(stdout);
     cudaFree(d);
     cudaFree(dft);
     cudaFree(dit);
+    cudaFree(dmod);
+    cudaFree(dninv);
+    cudaFree(rft);
+    cudaFree(rit);
 }
 
 // 4-step, reference contract: transpose, GPU_4STEP_NTT, transpose (example/ntt_4step/test_4step_ntt.cu:147-154).
@@ -199,7 +240,7 @@ int main(int argc, char** argv)
 {
     if (argc < 2)
     {
-        fprintf(stderr, "usage: %s <label> [c2|c2inv|c3|c4|sweep ...]\n", argv[0]);
+        fprintf(stderr, "usage: %s <label> [c2|c2inv|c3|c4|sweep|small|fhe ...]\n", argv[0]);
         return 1;
     }
     g_label = argv[1];
@@ -226,6 +267,29 @@ int main(int argc, char** argv)
                 merge_case<Data64>("sweep64", l, 1 << (26 - l), false, false, 10);
             for (int l = 12; l <= 24; l += 4)
                 merge_case<Data32>("sweep32", l, 1 << (27 - l), false, false, 10);
+        }
+        else if (c == "small")
+        {
+            for (int l = 8; l <= 11; l++)
+                merge_case<Data64>("small64", l, 32768, false, false, 10);
+            for (int l = 8; l <= 13; l++)
+                merge_case<Data32>("small32", l, 32768, false, false, 10);
+        }
+        else if (c == "fhe")
+        {
+            // what RNS-FHE callers issue: negacyclic ring, RNS overloads, forward and inverse
+            for (int l = 12; l <= 17; l++)
+            {
+                merge_case<Data64>("fhe64-rns4", l, 1 << (26 - l), false, false, 10, ReductionPolynomial::X_N_plus, 4);
+                merge_case<Data64>("fhe64-rns4", l, 1 << (26 - l), true, false, 10, ReductionPolynomial::X_N_plus, 4);
+            }
+            merge_case<Data64>("fhe64-single", 16, 1024, false, false, 10, ReductionPolynomial::X_N_plus, 0);
+            merge_case<Data64>("fhe64-single", 16, 1024, true, false, 10, ReductionPolynomial::X_N_plus, 0);
+            merge_case<Data32>("fhe32-rns4", 14, 8192, false, false, 10, ReductionPolynomial::X_N_plus, 4);
+            merge_case<Data32>("fhe32-rns4", 14, 8192, true, false, 10, ReductionPolynomial::X_N_plus, 4);
+            merge_case<Data64>("fhe64-rns4-batch64", 16, 64, false, false, 10, ReductionPolynomial::X_N_plus, 4);
+            merge_case<Data64>("fhe64-rns4-batch64", 15, 64, false, false, 10, ReductionPolynomial::X_N_plus, 4);
+            merge_case<Data64>("fhe64-rns4-batch64", 13, 64, false, false, 10, ReductionPolynomial::X_N_plus, 4);
         }
         else
             fprintf(stderr, "unknown case %s\n", c.c_str());
