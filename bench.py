@@ -69,6 +69,27 @@ def cpu_reference_rate(count, threads=None, seed=0):
     return count / (time.perf_counter() - t0), threads, "port"
 
 
+def reference_gpu_same_box():
+    """The reference's OWN GPU kernels on this GPU, for the same workload: tools/bin/api_bench_reference is
+    tools/api_bench.cu (a caller of the public GPU-NTT API) linked against the reference's GPU sources compiled for
+    sm_100 (`make -C oracle refgpu`, built where /root/reference exists; the binary travels with the snapshot).
+    Informational -- BASELINE.md section 4 item 4; the graded reference arm is the CPU one.  None when not built."""
+    exe = os.path.join(ROOT, "tools", "bin", "api_bench_reference")
+    if not os.path.exists(exe):
+        return None
+    try:
+        r = subprocess.run([exe, "reference", "c2"], capture_output=True, text=True, timeout=120)
+        for line in r.stdout.splitlines():
+            if line.startswith("{"):
+                d = json.loads(line)
+                return {"value": d["ntt_per_s"], "unit": UNIT, "ms_per_step": d["ms"], "parity_vs_NTTCPU": d["parity_vs_NTTCPU"],
+                        "what": "GPU_NTT_Inplace<Data64> of the reference's ntt.cu built for sm_100, same N/batch/prime, "
+                                "CUDA events, data resident in HBM (tools/api_bench.cu)"}
+    except Exception as e:  # noqa: BLE001 -- informational leg only
+        return {"error": str(e)[:200]}
+    return None
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -290,6 +311,7 @@ def run_b200_arm(args):
         out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
                                "sample": f"{args.cpu_sample} polynomials of the same workload (N=2^16, Data64, seed 0), "
                                          f"NTTCPU::ntt sharded over {threads} host threads"}
+        out["reference_gpu_same_box"] = reference_gpu_same_box()
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

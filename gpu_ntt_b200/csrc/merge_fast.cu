@@ -1007,9 +1007,22 @@ namespace gpuntt_b200
         return pl;
     }
 
+    // single-pass small rings (fast_small below)
+    bool fast_small_supported(int n_power, int element_bits)
+    {
+        return element_bits == 64 ? (n_power >= 7 && n_power <= 11) : (n_power >= 8 && n_power <= 12);
+    }
+
     // text form of the tuned plan for gpuntt_b200_describe_plan; returns the number of launches (0: not covered)
     int fast_describe(int n_power, int element_bits, char* buf, size_t len)
     {
+        if (fast_small_supported(n_power, element_bits))
+        {
+            snprintf(buf, len, "pass0{tile=2^%d contiguous, whole transforms of 2^%d in a tile, stages=%d in %d register rounds, TMA persistent; "
+                               "batches that do not fill whole %d-element chunks: generic kernel} ",
+                     element_bits == 64 ? 12 : 13, n_power, n_power, n_power > (element_bits == 64 ? 8 : 10) ? 3 : 2, element_bits == 64 ? 2048 : 4096);
+            return 1;
+        }
         if (!fast_supported(n_power, element_bits)) return 0;
         const FastPlan pl = make_fast_plan(n_power, element_bits);
         size_t off = 0;
@@ -1052,10 +1065,6 @@ namespace gpuntt_b200
     // group (2048 / 4096 elements); a tile holds whole transforms, so ONE pass with two or three register rounds does
     // every stage, canonicalises (forward) or applies n^-1 (inverse), and the data makes one HBM round trip.
     // Needs batch * N to be a whole number of chunks; anything else stays on the generic kernel.
-    bool fast_small_supported(int n_power, int element_bits)
-    {
-        return element_bits == 64 ? (n_power >= 7 && n_power <= 11) : (n_power >= 8 && n_power <= 12);
-    }
     template <typename T, bool INV, int POL> static cudaError_t launch_small(int n_power, const FastArgs<T>& s, cudaStream_t st)
     {
         if constexpr (sizeof(T) == 8)
