@@ -29,6 +29,7 @@
 #include <cstdio>
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <type_traits>
 
 #include "gpuntt_b200.h"
 #include "merge_ntt.cuh"
@@ -426,10 +427,8 @@ namespace gpuntt_b200
         int pbits, mi;
     };
 
-    template <typename S, bool WMUL = false, bool RNS = false>
-    __global__ void __launch_bounds__(kFastThreads, (!S::INV && S::POL == 2) ? (S::STRIDED ? GPUNTT_FAST_P0_BLOCKS : GPUNTT_FAST_P1_BLOCKS) : 2)
-        fast_pass_kernel(const FastArgs<typename S::T> a, const __grid_constant__ CUtensorMap map_in,
-                         const __grid_constant__ CUtensorMap map_out)
+    template <typename S, bool WMUL, bool RNS>
+    __device__ __forceinline__ void fast_pass_body(const FastArgs<typename S::T>& a, const CUtensorMap& map_in, const CUtensorMap& map_out)
     {
         using T = typename S::T;
         extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -597,8 +596,7 @@ namespace gpuntt_b200
                     if constexpr (sizeof(T) == 8)
                     {
                         c.pbits = 64 - __clzll((long long) c.p);
-                        const unsigned __int128 m = (((unsigned __int128) 1) << (63 + c.pbits)) / (unsigned __int128) c.p;
-                        c.mu = (m >> 64) ? ~0ull : (uint64_t) m;
+                        c.mu = (c.p & (c.p - 1)) ? recip_mu64(c.p, c.pbits) : ~0ull; // (a power of two is no modulus; keep the old clamp)
                     }
                     else
                     {
@@ -606,7 +604,10 @@ namespace gpuntt_b200
                         c.mu = ~0ull / (uint64_t) c.p;
                     }
                     c.ninv_w = S::INV ? a.ninv_dev[mi] : T(0);
-                    c.ninv_wq = S::INV ? shoup_companion(c.ninv_w, c.p) : T(0);
+                    if constexpr (sizeof(T) == 8)
+                        c.ninv_wq = S::INV ? shoup_companion_mu(c.ninv_w, c.p, c.mu, c.pbits) : T(0);
+                    else
+                        c.ninv_wq = S::INV ? shoup_companion(c.ninv_w, c.p) : T(0);
                     *segc = c;
                 }
                 __syncthreads();
@@ -808,6 +809,36 @@ namespace gpuntt_b200
         }
     }
 
+    template <typename S, bool WMUL = false, bool RNS = false>
+    __global__ void __launch_bounds__(kFastThreads, (!S::INV && S::POL == 2) ? (S::STRIDED ? GPUNTT_FAST_P0_BLOCKS : GPUNTT_FAST_P1_BLOCKS) : 2)
+        fast_pass_kernel(const FastArgs<typename S::T> a, const __grid_constant__ CUtensorMap map_in,
+                         const __grid_constant__ CUtensorMap map_out)
+    {
+        fast_pass_body<S, WMUL, RNS>(a, map_in, map_out);
+    }
+
+    // RNS calls on 64-bit data: the moduli live on the device, so the choice between the lazy-policy body (SL) and the
+    // exact-policy body (SX) of a pass is made HERE, by every warp, from the modulus array itself -- one launch per pass
+    // and no pre-kernel (a call used to be a flag kernel plus two launches per pass, one of which returned at once:
+    // 5 launches, 32-34 us for a small batch against 18-23 us on the reference's two kernels).
+    template <typename SL, typename SX>
+    __global__ void __launch_bounds__(kFastThreads, 2)
+        fast_pass_dual_kernel(const FastArgs<uint64_t> a, const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_out)
+    {
+        static_assert(SL::INV == SX::INV && SL::STRIDED == SX::STRIDED && SL::SMEM == SX::SMEM && SX::POL == 0 && SL::POL != 0, "same pass, two policies");
+        int bad = 0;
+        for (int i = threadIdx.x & 31; i < a.mod_count; i += 32)
+        {
+            const uint64_t p = a.mod_dev[3 * (a.mod_order ? a.mod_order[i] : i)];
+            const bool ok = SL::INV ? (p < kFastModulusLimit) : (p >= kF60ModulusMin && p < kF60ModulusLimit);
+            bad |= ok ? 0 : 1;
+        }
+        if (__any_sync(0xffffffffu, bad))
+            fast_pass_body<SX, false, true>(a, map_in, map_out);
+        else
+            fast_pass_body<SL, false, true>(a, map_in, map_out);
+    }
+
     // ------------------------------------------------------------------ host side
     static PFN_cuTensorMapEncodeTiled get_encode()
     {
@@ -890,14 +921,21 @@ namespace gpuntt_b200
     }
 
     // returns cudaErrorNotSupported when the tensor maps cannot be built (caller falls back)
-    template <typename S, bool WMUL = false, bool RNS = false> static cudaError_t launch_fast(const FastArgs<typename S::T>& args, cudaStream_t st)
+    // SX: exact-policy twin of S for the 64-bit RNS calls (fast_pass_dual_kernel picks on the device)
+    template <typename S, bool WMUL = false, bool RNS = false, typename SX = void>
+    static cudaError_t launch_fast(const FastArgs<typename S::T>& args, cudaStream_t st)
     {
         // per device (the shared-memory opt-in is a per-device function attribute); a race between first callers only
         // repeats idempotent work
         constexpr int kMaxDev = 64;
         static std::atomic<int> cached_bps[kMaxDev];
         static std::atomic<int> cached_sms[kMaxDev];
-        auto kern = fast_pass_kernel<S, WMUL, RNS>;
+        using KernT = void (*)(const FastArgs<typename S::T>, const CUtensorMap, const CUtensorMap);
+        KernT kern;
+        if constexpr (std::is_void<SX>::value)
+            kern = fast_pass_kernel<S, WMUL, RNS>;
+        else
+            kern = fast_pass_dual_kernel<S, SX>;
         int dev = 0;
         cudaError_t ge = cudaGetDevice(&dev);
         if (ge != cudaSuccess) return ge;
@@ -1288,21 +1326,6 @@ namespace gpuntt_b200
     }
 
     // ------------------------------------------------------------------ RNS form on the tuned kernels
-    // flag = 0 when every modulus allows the lazy policy of this direction, else 1 (one warp)
-    template <typename T>
-    __global__ void rns_policy_kernel(const T* __restrict__ mod_dev, const int* __restrict__ mod_order, int mod_count, int inverse, int* flag)
-    {
-        int bad = 0;
-        for (int i = threadIdx.x; i < mod_count; i += 32)
-        {
-            const uint64_t p = (uint64_t) mod_dev[3 * (mod_order ? mod_order[i] : i)];
-            const bool ok = inverse ? (p < kFastModulusLimit) : (p >= kF60ModulusMin && p < kF60ModulusLimit);
-            bad |= ok ? 0 : 1;
-        }
-        bad = __any_sync(0xffffffffu, bad);
-        if (threadIdx.x == 0) *flag = bad ? 1 : 0;
-    }
-
     template <typename T, bool INV, int POL> static cudaError_t launch_strided_rns(int d, const FastArgs<T>& args, cudaStream_t st)
     {
         constexpr int K = sizeof(T) == 8 ? 12 : 13;
@@ -1316,11 +1339,25 @@ namespace gpuntt_b200
             default: return cudaErrorNotSupported;
         }
     }
+    // 64-bit: lazy policy POL and the exact policy in one launch (the device picks)
+    template <bool INV, int POL> static cudaError_t launch_strided_rns_dual(int d, const FastArgs<uint64_t>& args, cudaStream_t st)
+    {
+        using T = uint64_t;
+        switch (d)
+        {
+            case 4: return launch_fast<Shape<T, INV, POL, true, 4, 0, 12, 0>, false, true, Shape<T, INV, 0, true, 4, 0, 12, 0>>(args, st);
+            case 5: return launch_fast<Shape<T, INV, POL, true, 3, 2, 12, 0>, false, true, Shape<T, INV, 0, true, 3, 2, 12, 0>>(args, st);
+            case 6: return launch_fast<Shape<T, INV, POL, true, 3, 3, 12, 0>, false, true, Shape<T, INV, 0, true, 3, 3, 12, 0>>(args, st);
+            case 7: return launch_fast<Shape<T, INV, POL, true, 4, 3, 12, 0>, false, true, Shape<T, INV, 0, true, 4, 3, 12, 0>>(args, st);
+            case 8: return launch_fast<Shape<T, INV, POL, true, 4, 4, 12, 0>, false, true, Shape<T, INV, 0, true, 4, 4, 12, 0>>(args, st);
+            default: return cudaErrorNotSupported;
+        }
+    }
 
     // GPU_NTT / GPU_INTT RNS overloads (ntt.cu:2560-3058) for the two-pass ring sizes (64-bit 2^12..2^16, 32-bit
-    // 2^14..2^18), batch a multiple of mod_count, no order indirection.  The moduli are device data, so for 64-bit
-    // both the lazy-policy and the exact-policy kernel of every pass are enqueued and a device flag picks one.
-    // flag_ws: one int of device scratch.  *launched = 0 when not covered.
+    // 2^14..2^18), batch a multiple of mod_count.  The moduli are device data, so for 64-bit every pass is ONE launch of
+    // fast_pass_dual_kernel, which holds the lazy-policy and the exact-policy body and picks from the modulus array.
+    // flag_ws: unused (kept for the call signature).  *launched = 0 when not covered.
     template <typename T>
     cudaError_t fast_merge_rns(const T* in, T* out, const T* table, const T* mod_dev, const T* ninv_dev, const int* mod_order,
                                const int* poly_order, int mod_count, int n_power, int plus, bool inverse, int batch, int* flag_ws,
@@ -1348,15 +1385,7 @@ namespace gpuntt_b200
         a.poly_order = poly_order;
         a.policy_flag = nullptr;
         int kind = 1;
-        if (bits == 64)
-        {
-            prof_begin(0, st);
-            rns_policy_kernel<T><<<1, 32, 0, st>>>(mod_dev, mod_order, mod_count, inverse ? 1 : 0, flag_ws);
-            prof_end(st);
-            cudaError_t pe = cudaGetLastError();
-            if (pe != cudaSuccess) return pe;
-            a.policy_flag = flag_ws;
-        }
+        (void) flag_ws; // (the policy flag of the two-launch scheme; the dual kernels read the moduli themselves)
         for (int k = 0; k < pl.npass; k++)
         {
             const int i = inverse ? pl.npass - 1 - k : k;
@@ -1367,44 +1396,28 @@ namespace gpuntt_b200
             s.first = (k == 0);
             s.last = (k == pl.npass - 1);
             cudaError_t e = cudaSuccess;
-            for (int variant = 0; variant < (bits == 64 ? 2 : 1) && e == cudaSuccess; variant++)
+            prof_begin(kind, st);
+            if (pl.strided[i])
             {
-                const bool lazy = bits == 64 && variant == 0;
-                s.want_policy = lazy ? 0 : 1;
-                prof_begin(kind, st);
-                if (pl.strided[i])
-                {
-                    const int c = K - pl.d[i];
-                    s.work = ((long long) mod_count * s.batch) << (pl.lo[i] - c); // one range per slot in a two-pass plan
-                    if constexpr (bits == 64)
-                    {
-                        if (lazy)
-                            e = inverse ? launch_strided_rns<T, true, 1>(pl.d[i], s, st) : launch_strided_rns<T, false, 2>(pl.d[i], s, st);
-                        else
-                            e = inverse ? launch_strided_rns<T, true, 0>(pl.d[i], s, st) : launch_strided_rns<T, false, 0>(pl.d[i], s, st);
-                    }
-                    else
-                        e = inverse ? launch_strided_rns<T, true, 0>(pl.d[i], s, st) : launch_strided_rns<T, false, 0>(pl.d[i], s, st);
-                }
+                const int c = K - pl.d[i];
+                s.work = ((long long) mod_count * s.batch) << (pl.lo[i] - c); // one range per slot in a two-pass plan
+                if constexpr (bits == 64)
+                    e = inverse ? launch_strided_rns_dual<true, 1>(pl.d[i], s, st) : launch_strided_rns_dual<false, 2>(pl.d[i], s, st);
                 else
-                {
-                    const long long tpr = (s.batch + 1) >> 1;
-                    s.work = ((long long) mod_count * tpr) << (n_power - (K - 1));
-                    if constexpr (bits == 64)
-                    {
-                        if (lazy)
-                            e = inverse ? launch_fast<Shape<T, true, 1, false, 4, 4, 12, 1>, false, true>(s, st)
-                                        : launch_fast<Shape<T, false, 2, false, 4, 4, 12, 1>, false, true>(s, st);
-                        else
-                            e = inverse ? launch_fast<Shape<T, true, 0, false, 4, 4, 12, 1>, false, true>(s, st)
-                                        : launch_fast<Shape<T, false, 0, false, 4, 4, 12, 1>, false, true>(s, st);
-                    }
-                    else
-                        e = inverse ? launch_fast<Shape<T, true, 0, false, 5, 5, 13, 1>, false, true>(s, st)
-                                    : launch_fast<Shape<T, false, 0, false, 5, 5, 13, 1>, false, true>(s, st);
-                }
-                prof_end(st);
+                    e = inverse ? launch_strided_rns<T, true, 0>(pl.d[i], s, st) : launch_strided_rns<T, false, 0>(pl.d[i], s, st);
             }
+            else
+            {
+                const long long tpr = (s.batch + 1) >> 1;
+                s.work = ((long long) mod_count * tpr) << (n_power - (K - 1));
+                if constexpr (bits == 64)
+                    e = inverse ? launch_fast<Shape<T, true, 1, false, 4, 4, 12, 1>, false, true, Shape<T, true, 0, false, 4, 4, 12, 1>>(s, st)
+                                : launch_fast<Shape<T, false, 2, false, 4, 4, 12, 1>, false, true, Shape<T, false, 0, false, 4, 4, 12, 1>>(s, st);
+                else
+                    e = inverse ? launch_fast<Shape<T, true, 0, false, 5, 5, 13, 1>, false, true>(s, st)
+                                : launch_fast<Shape<T, false, 0, false, 5, 5, 13, 1>, false, true>(s, st);
+            }
+            prof_end(st);
             kind++;
             if (e == cudaErrorNotSupported && k == 0) return cudaSuccess;
             if (e != cudaSuccess) return e;

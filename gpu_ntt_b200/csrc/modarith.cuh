@@ -344,6 +344,40 @@ namespace gpuntt_b200
         return (uint32_t) q;
     }
 
+    // floor((u1 * 2^64 + u0) / v) for u1 < v: schoolbook division in base 2^32 (two 64-bit divisions and their
+    // corrections) -- the 128-bit division the compiler would emit for unsigned __int128 costs about a microsecond on
+    // one thread, which the RNS kernels pay per segment on their critical path.
+    __host__ __device__ __forceinline__ uint64_t div_128_by_64(uint64_t u1, uint64_t u0, uint64_t v)
+    {
+        const uint64_t b = 1ull << 32;
+        int s = 0;
+        while (!((v << s) >> 63)) s++; // v != 0
+        v <<= s;
+        const uint64_t vn1 = v >> 32, vn0 = v & 0xffffffffull;
+        const uint64_t un32 = s ? ((u1 << s) | (u0 >> (64 - s))) : u1;
+        const uint64_t un10 = u0 << s;
+        const uint64_t un1 = un10 >> 32, un0 = un10 & 0xffffffffull;
+        uint64_t q1 = un32 / vn1, rhat = un32 - q1 * vn1;
+        while (q1 >= b || q1 * vn0 > b * rhat + un1)
+        {
+            q1--;
+            rhat += vn1;
+            if (rhat >= b) break;
+        }
+        const uint64_t un21 = un32 * b + un1 - q1 * v;
+        uint64_t q0 = un21 / vn1;
+        rhat = un21 - q0 * vn1;
+        while (q0 >= b || q0 * vn0 > b * rhat + un0)
+        {
+            q0--;
+            rhat += vn1;
+            if (rhat >= b) break;
+        }
+        return q1 * b + q0;
+    }
+    // mu = floor(2^(63 + bits) / p) for an odd p of bit length `bits` >= 2 (what shoup_companion_mu takes)
+    __host__ __device__ __forceinline__ uint64_t recip_mu64(uint64_t p, int bits) { return div_128_by_64(1ull << (bits - 1), 0, p); }
+
     // ------------------------------------------------------------------ plain Barrett product
     // a * b mod p for canonical a, b with the reference's Modulus constants (bit = bit length of p,
     // mu = floor(2^(2 bit + 1) / p), modular_arith.cuh:28-57): q = ((z >> (bit-2)) * mu) >> (bit+3) is at most

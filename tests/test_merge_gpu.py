@@ -182,13 +182,14 @@ def test_rns_form(bits, logn, batch, mod_count):
 ])
 def test_rns_form_tuned_kernels(bits, logn, batch, mod_count, tops):
     """RNS overloads on the tuned kernels (two-pass ring sizes, batch a multiple of mod_count): per-slot modulus,
-    table slice and N^-1 are read per segment on the device, and for 64-bit data a device flag picks the lazy or
-    the exact arithmetic kernels."""
+    table slice and N^-1 are read per segment on the device, and for 64-bit data every pass kernel holds the lazy and
+    the exact arithmetic body and picks one from the moduli it finds."""
     primes = [rns_primes(bits, logn, 1 + i, t)[i] for i, t in enumerate(tops)]
     assert len({p for p, _ in primes}) == mod_count
     _rns_roundtrip(bits, logn, batch, mod_count, primes)
-    # the inverse call was the last one: policy kernel + (lazy, exact) x 2 passes for 64-bit, 2 passes for 32-bit
-    assert capi.lib().gpuntt_b200_last_launch_count() == (5 if bits == 64 else 2)
+    # the inverse call was the last one: one launch per pass (64-bit: the dual kernel picks the lazy or the exact body
+    # from the modulus array on the device)
+    assert capi.lib().gpuntt_b200_last_launch_count() == 2
 
 
 def _rns_roundtrip(bits, logn, batch, mod_count, primes):
@@ -444,7 +445,7 @@ def test_rns_ordered_entry_points(bits, logn, batch, mod_count):
     assert (to_host(d, bits).reshape(slots, n) == buf).all()
     if batch % mod_count == 0 and logn >= (12 if bits == 64 else 14):
         # two-pass ring, whole slots: the tuned RNS kernels (policy kernel + lazy/exact kernel per pass for 64-bit)
-        assert capi.lib().gpuntt_b200_last_launch_count() == (5 if bits == 64 else 2)
+        assert capi.lib().gpuntt_b200_last_launch_count() == 2
 
 
 @pytest.mark.parametrize("bits", [64, 32])

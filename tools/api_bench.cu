@@ -9,7 +9,7 @@
 // so the two binaries differ in nothing but the library behind the API.  Each case checks polynomial 0 and the last
 // polynomial against the library's own NTTCPU (bit-exact) before it is timed with CUDA events.
 //
-//   api_bench <label> [c2|c2inv|c3|c4|sweep|small|fhe ...]     one JSON object per line
+//   api_bench <label> [c2|c2inv|c3|c4|sweep|small|fhe|latency ...]     one JSON object per line
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -240,7 +240,7 @@ int main(int argc, char** argv)
 {
     if (argc < 2)
     {
-        fprintf(stderr, "usage: %s <label> [c2|c2inv|c3|c4|sweep|small|fhe ...]\n", argv[0]);
+        fprintf(stderr, "usage: %s <label> [c2|c2inv|c3|c4|sweep|small|fhe|latency ...]\n", argv[0]);
         return 1;
     }
     g_label = argv[1];
@@ -274,6 +274,17 @@ int main(int argc, char** argv)
                 merge_case<Data64>("small64", l, 32768, false, false, 10);
             for (int l = 8; l <= 13; l++)
                 merge_case<Data32>("small32", l, 32768, false, false, 10);
+        }
+        else if (c == "latency")
+        {
+            // launch-bound regime: what an RNS-FHE caller issues per ciphertext operation (tens of polynomials per call)
+            for (int l = 12; l <= 16; l++)
+                for (int b : {8, 32, 128})
+                {
+                    merge_case<Data64>("latency-rns4", l, b, false, false, 50, ReductionPolynomial::X_N_plus, 4);
+                    merge_case<Data64>("latency-rns4", l, b, true, false, 50, ReductionPolynomial::X_N_plus, 4);
+                    merge_case<Data64>("latency-single", l, b, false, false, 50, ReductionPolynomial::X_N_plus, 0);
+                }
         }
         else if (c == "fhe")
         {
