@@ -1370,7 +1370,8 @@ namespace gpuntt_b200
         if (!fast_supported(n_power, bits) || mod_count < 1 || batch % mod_count != 0) return cudaSuccess;
         if (((long long) batch << (n_power - (bits == 64 ? 8 : 10))) >= (1LL << 31)) return cudaSuccess;
         const FastPlan pl = make_fast_plan(n_power, bits);
-        if (pl.npass != 2 || pl.d[0] < 4) return cudaSuccess;
+        for (int i = 0; i + 1 < pl.npass; i++)
+            if (pl.d[i] < 4 || pl.d[i] > 8) return cudaSuccess; // strided RNS shapes exist for 4..8 stages
         if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return cudaSuccess;
         FastArgs<T> a{};
         a.table = table;
@@ -1400,7 +1401,8 @@ namespace gpuntt_b200
             if (pl.strided[i])
             {
                 const int c = K - pl.d[i];
-                s.work = ((long long) mod_count * s.batch) << (pl.lo[i] - c); // one range per slot in a two-pass plan
+                // (slot, range) segments: 2^(n - lo - d) ranges per slot (one in a two-pass plan)
+                s.work = (((long long) mod_count * s.batch) << (pl.lo[i] - c)) << (n_power - pl.lo[i] - pl.d[i]);
                 if constexpr (bits == 64)
                     e = inverse ? launch_strided_rns_dual<true, 1>(pl.d[i], s, st) : launch_strided_rns_dual<false, 2>(pl.d[i], s, st);
                 else

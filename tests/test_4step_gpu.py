@@ -151,3 +151,46 @@ def test_4step_errors():
     assert ei.value.status == capi.ERR_N_POWER
     with pytest.raises(capi.GpuNttError):
         capi.fourstep_ntt(t.view(1, -1), t, t, t, 576460752303415297, 12, io_contract=capi.FOURSTEP_REFERENCE)  # in == out
+
+
+def test_4step_rns_overload_one_modulus_takes_the_tuned_kernels_and_can_be_captured():
+    """With exactly one device modulus the RNS overload reads that Modulus back (32 bytes) and continues as the
+    single-modulus form -- same launches, same kernels; under stream capture no read-back is possible and the
+    device-modulus kernels run instead.  Both must equal the oracle."""
+    bits, logn, batch = 64, 16, 2
+    P = O.fourstep_params(logn, O.X_N_minus, bits)
+    x = O.example_input(P.modulus, batch * P.n, seed=11).reshape(batch, P.n)
+    want = O.fourstep_ntt(x, P)
+    t1, t2, W = tables(P, bits, False)
+    bit, mu = O.modulus(P.modulus, bits)
+    mods = to_dev(np.array([P.modulus, bit, mu], dtype=np.uint64), bits)
+    d = to_dev(x, bits).view(batch, P.n)
+    out = torch.empty_like(d)
+    capi.fourstep_ntt(d, t1, t2, W, P.modulus, logn, out=out)
+    torch.cuda.synchronize()
+    single_launches = capi.lib().gpuntt_b200_last_launch_count()
+    assert (to_host(out, bits).reshape(batch, -1) == want).all()
+    out.zero_()
+    capi.fourstep_ntt(d, t1, t2, W, 0, logn, out=out, mod_count=1, modulus_dev=mods.data_ptr())
+    torch.cuda.synchronize()
+    assert capi.lib().gpuntt_b200_last_launch_count() == single_launches
+    assert (to_host(out, bits).reshape(batch, -1) == want).all()
+    # capture on an explicit stream whose cached scratch (generic-kernel twiddle companions, 4-step workspace) exists
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    capi.lib().gpuntt_b200_force_generic_path(1)
+    try:
+        with torch.cuda.stream(side):
+            capi.fourstep_ntt(d, t1, t2, W, 0, logn, out=out, mod_count=1, modulus_dev=mods.data_ptr())
+    finally:
+        capi.lib().gpuntt_b200_force_generic_path(0)
+    side.synchronize()
+    assert (to_host(out, bits).reshape(batch, -1) == want).all()
+    g = torch.cuda.CUDAGraph()
+    out.zero_()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g, stream=side):
+        capi.fourstep_ntt(d, t1, t2, W, 0, logn, out=out, mod_count=1, modulus_dev=mods.data_ptr())
+    g.replay()
+    torch.cuda.synchronize()
+    assert (to_host(out, bits).reshape(batch, -1) == want).all()
