@@ -69,6 +69,25 @@ def cpu_reference_rate(count, threads=None, seed=0):
     return count / (time.perf_counter() - t0), threads, "port"
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout under
+    torchrun), so keep a private handle on the real stdout and point fd 1 at stderr for everything else."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit_line(text):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(text + "\n")
+    out.flush()
+
+
 def reference_gpu_same_box():
     """The reference's OWN GPU kernels on this GPU, for the same workload: tools/bin/api_bench_reference is
     tools/api_bench.cu (a caller of the public GPU-NTT API) linked against the reference's GPU sources compiled for
@@ -106,7 +125,7 @@ def run_reference_arm(args):
         total_t += per_step / rate
     value = per_step * args.steps / total_t
     sample = f"{per_step} of the {BATCH} polynomials per step, NTTCPU<Data64>::ntt N=2^16 on {threads} host threads"
-    print(json.dumps({
+    emit_line(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
@@ -313,7 +332,7 @@ def run_b200_arm(args):
                                          f"NTTCPU::ntt sharded over {threads} host threads"}
         out["reference_gpu_same_box"] = reference_gpu_same_box()
     if rank == 0:
-        print(json.dumps(out))
+        emit_line(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -328,6 +347,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="kernel-timed region only (for runs under ncu)")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:
