@@ -99,12 +99,22 @@ def lib():
         L.gpuntt_b200_version.restype = i
         L.gpuntt_b200_force_generic_path.restype = None
         L.gpuntt_b200_force_generic_path.argtypes = [i]
+        L.gpuntt_b200_tune.restype = None
+        L.gpuntt_b200_tune.argtypes = [i, i]
         L.gpuntt_b200_set_profiling.restype = None
         L.gpuntt_b200_set_profiling.argtypes = [i]
         L.gpuntt_b200_profile_read.restype = i
         L.gpuntt_b200_profile_read.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int), i]
         _lib = L
     return _lib
+
+
+TUNE_FUSED_PASSES, TUNE_FUSED_LAG = 1, 2
+
+
+def tune(knob: int, value: int) -> None:
+    """gpuntt_b200_tune: A/B knobs (results never depend on them)."""
+    lib().gpuntt_b200_tune(knob, value)
 
 
 def check(status: int) -> None:

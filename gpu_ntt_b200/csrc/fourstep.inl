@@ -226,7 +226,8 @@ template <typename T> static int fourstep_execute_t(const gpuntt_b200_4step_desc
                 int launched = 0;
                 cudaError_t re = fast_merge<uint64_t>(reinterpret_cast<const uint64_t*>(work), reinterpret_cast<uint64_t*>(work),
                                                       reinterpret_cast<const uint64_t*>(d->n2_table), (uint64_t) d->modulus_value, 0, lg2, 0,
-                                                      false, (int) ((long long) batch * n1), st, &launched, prof_begin, prof_end, 2);
+                                                      false, (int) ((long long) batch * n1), st, &launched, prof_begin, prof_end, 2,
+                                                      fused_counters(d->stream, (long long) batch * n1));
                 if (re != cudaSuccess) return cuda_fail(re, "fast_pass_kernel launch");
                 rows_done = launched > 0;
                 if (!rows_done) return fail(GPUNTT_B200_ERR_CUDA, "4-step row phase: tuned kernels declined after a lazy column phase");

@@ -1,0 +1,196 @@
+// gpu_ntt_b200/csrc/merge_fast_4step.cu -- 4-step phases on the tuned kernels:
+//   fast_fourstep_columns  forward column phase with the twiddle-matrix product as epilogue
+//   fast_fourstep_inverse  inverse (row phase + strided passes with the product as prologue)
+// Kernels and the launch helper live in fast_kernels.cuh.
+#include "fast_kernels.cuh"
+
+namespace gpuntt_b200
+{
+
+    // (w, w') pairs of the 4-step twiddle matrix, once per call (the batch shares it)
+    // t_lo > 0: entry i comes from the transposed index ((i mod 2^t_lo) << t_hi) | (i >> t_lo) (4-step inverse: the data
+    // is the n2 x n1 matrix, the reference's inverse twiddle matrix is laid out n1 x n2)
+    __global__ void __launch_bounds__(256) w_pairs_kernel(const uint64_t* __restrict__ w, Twiddle<uint64_t>* __restrict__ out, long long count,
+                                                          uint64_t p, uint64_t mu, int pbits, int t_lo, int t_hi)
+    {
+        const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= count) return;
+        const long long src = t_lo ? (((i & ((1LL << t_lo) - 1)) << t_hi) | (i >> t_lo)) : i;
+        const uint64_t v = w[src];
+        out[i] = Twiddle<uint64_t>{v, shoup_companion_mu(v, p, mu, pbits)};
+    }
+
+    // Forward 4-step column phase on the tuned strided kernel: the first lg1 stages of a size-2^n transform with the
+    // n1 table (rows 2^lg2 elements apart), then every element times W[offset] (pairs built into w_pairs_ws, N
+    // entries), canonical outputs.  Single modulus, 64-bit, F60 moduli; *launched = 0 when not covered.
+    cudaError_t fast_fourstep_columns(const uint64_t* in, uint64_t* out, const uint64_t* n1_table, const uint64_t* w_table,
+                                      void* w_pairs_ws, uint64_t p, int n_power, int lg1, int lg2, int batch, cudaStream_t st,
+                                      int* launched, void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t), int w_lazy)
+    {
+        using T = uint64_t;
+        *launched = 0;
+        if (lg1 < 5 || lg1 > 8 || lg2 < 12 - lg1 || n_power != lg1 + lg2) return cudaSuccess;
+        if (((long long) batch << lg1) >= (1LL << 31)) return cudaSuccess;
+        if (!(p >= kF60ModulusMin && p < kF60ModulusLimit)) return cudaSuccess;
+        if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return cudaSuccess;
+        FastArgs<T> a{};
+        a.in = in;
+        a.out = out;
+        a.table = n1_table;
+        a.p = p;
+        a.pbits = 64 - __builtin_clzll((unsigned long long) p);
+        {
+            const unsigned __int128 m = (((unsigned __int128) 1) << (63 + a.pbits)) / (unsigned __int128) p;
+            a.mu = (m >> 64) ? ~0ull : (uint64_t) m;
+        }
+        a.n = n_power;
+        a.lo = lg2;
+        a.plus = 0;
+        a.first = 1;
+        a.last = 0;
+        a.batch = batch;
+        a.w_pairs = w_pairs_ws;
+        a.w_lazy = w_lazy; // products below 2p (the tuned row phase starts from that bound) or canonical
+        a.work = (long long) batch << (lg2 - (12 - lg1));
+        a.rr = 1; // column-chunk-major round robin: the polynomials of a chunk share the pair fetch through the L2
+        const long long N = 1LL << n_power;
+        prof_begin(0, st);
+        w_pairs_kernel<<<(unsigned) ((N + 255) / 256), 256, 0, st>>>(w_table, reinterpret_cast<Twiddle<T>*>(w_pairs_ws), N, p, a.mu, a.pbits, 0, 0);
+        prof_end(st);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        prof_begin(1, st);
+        switch (lg1)
+        {
+            case 5: e = launch_fast<Shape<T, false, 2, true, 3, 2, 12, 0>, true>(a, st); break;
+            case 6: e = launch_fast<Shape<T, false, 2, true, 3, 3, 12, 0>, true>(a, st); break;
+            case 7: e = launch_fast<Shape<T, false, 2, true, 4, 3, 12, 0>, true>(a, st); break;
+            default: e = launch_fast<Shape<T, false, 2, true, 4, 4, 12, 0>, true>(a, st); break;
+        }
+        prof_end(st);
+        if (e == cudaErrorNotSupported) return cudaSuccess; // (the pair table was written for nothing)
+        if (e != cudaSuccess) return e;
+        *launched = 2;
+        return cudaSuccess;
+    }
+
+    // Inverse 4-step on the tuned kernels.  `rows_in` holds the n2 x n1 matrix (n2 rows of n1 contiguous elements):
+    //   1. contiguous inverse pass: a size-n1 Gentleman-Sande transform on every row (n1 table, no n^-1), rows_in -> work;
+    //   2. strided inverse passes over the top lg2 index bits with the n2 table: the first multiplies by the inverse twiddle
+    //      matrix as it loads (pairs in data layout, built from the transposed index), the last applies n^-1 and canonicalises;
+    //      work -> dst.
+    // Single modulus, 64-bit, p below the lazy inverse limit, shapes whose pass splits fit the tile; *launched = 0 otherwise.
+    cudaError_t fast_fourstep_inverse(const uint64_t* rows_in, uint64_t* work, uint64_t* dst, const uint64_t* n1_table,
+                                      const uint64_t* n2_table, const uint64_t* w_table, void* w_pairs_ws, uint64_t p, uint64_t ninv,
+                                      int n_power, int lg1, int lg2, int batch, cudaStream_t st, int* launched,
+                                      void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t))
+    {
+        using T = uint64_t;
+        *launched = 0;
+        if (lg1 < 5 || lg1 > 8 || n_power != lg1 + lg2 || n_power < 12) return cudaSuccess;
+        if (((long long) batch << lg2) >= (1LL << 31)) return cudaSuccess;
+        if (!(p < kFastModulusLimit) || p < 5) return cudaSuccess;
+        if ((reinterpret_cast<uintptr_t>(rows_in) | reinterpret_cast<uintptr_t>(work) | reinterpret_cast<uintptr_t>(dst)) & 15) return cudaSuccess;
+        // split of the lg2 strided stages (executed low bits first)
+        int da, db;
+        if (lg2 <= 8)
+        {
+            da = lg2;
+            db = 0;
+            if (da < 4 || 12 - da > lg1) return cudaSuccess;
+        }
+        else
+        {
+            da = lg2 - 8;
+            if (da < 12 - lg1) da = 12 - lg1;
+            if (da < 4) da = 4;
+            db = lg2 - da;
+            if (da > 8 || db < 4 || db > 8) return cudaSuccess;
+        }
+        FastArgs<T> a{};
+        a.p = p;
+        a.ninv_w = ninv;
+        a.ninv_wq = shoup_companion(ninv, p);
+        a.pbits = 64 - __builtin_clzll((unsigned long long) p);
+        {
+            const unsigned __int128 m = (((unsigned __int128) 1) << (63 + a.pbits)) / (unsigned __int128) p;
+            a.mu = (m >> 64) ? ~0ull : (uint64_t) m;
+        }
+        a.plus = 0;
+        const long long N = 1LL << n_power;
+        cudaError_t e;
+        prof_begin(0, st);
+        w_pairs_kernel<<<(unsigned) ((N + 255) / 256), 256, 0, st>>>(w_table, reinterpret_cast<Twiddle<T>*>(w_pairs_ws), N, p, a.mu, a.pbits, lg1, lg2);
+        prof_end(st);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        int kind = 1;
+        {
+            // row phase: the array as (batch * N / 2048) chunks of 2048 elements, transforms of 2^lg1 inside
+            FastArgs<T> s = a;
+            s.in = rows_in;
+            s.out = work;
+            s.table = n1_table;
+            s.n = 11;
+            s.n_tw = lg1;
+            s.lo = 0;
+            s.first = 1;
+            s.last = 0;
+            const long long chunks = ((long long) batch << n_power) >> 11;
+            if (chunks > 0x7fffffffLL) return cudaSuccess;
+            s.batch = (int) chunks;
+            s.work = (chunks + 1) >> 1;
+            prof_begin(kind++, st);
+            switch (lg1)
+            {
+                case 5: e = launch_fast<Shape<T, true, 1, false, 1, 4, 12, 1, 5>>(s, st); break;
+                case 6: e = launch_fast<Shape<T, true, 1, false, 2, 4, 12, 1, 6>>(s, st); break;
+                case 7: e = launch_fast<Shape<T, true, 1, false, 3, 4, 12, 1, 7>>(s, st); break;
+                default: e = launch_fast<Shape<T, true, 1, false, 4, 4, 12, 1, 8>>(s, st); break;
+            }
+            prof_end(st);
+            if (e == cudaErrorNotSupported) return cudaSuccess;
+            if (e != cudaSuccess) return e;
+        }
+        auto strided = [&](int d, int lo, bool wmul, bool last, const T* src, T* out) -> cudaError_t
+        {
+            FastArgs<T> s = a;
+            s.in = src;
+            s.out = out;
+            s.table = n2_table;
+            s.n = n_power;
+            s.lo = lo;
+            s.first = 0;
+            s.last = last ? 1 : 0;
+            s.batch = batch;
+            s.w_pairs = w_pairs_ws;
+            s.work = ((long long) batch << (lo - (12 - d))) << (n_power - lo - d);
+            s.rr = (!wmul && n_power == lo + d && lo > 10) ? 1 : 0;
+            prof_begin(kind++, st);
+            cudaError_t r;
+            if (wmul)
+                switch (d)
+                {
+                    case 4: r = launch_fast<Shape<T, true, 1, true, 4, 0, 12, 0>, true>(s, st); break;
+                    case 5: r = launch_fast<Shape<T, true, 1, true, 3, 2, 12, 0>, true>(s, st); break;
+                    case 6: r = launch_fast<Shape<T, true, 1, true, 3, 3, 12, 0>, true>(s, st); break;
+                    case 7: r = launch_fast<Shape<T, true, 1, true, 4, 3, 12, 0>, true>(s, st); break;
+                    default: r = launch_fast<Shape<T, true, 1, true, 4, 4, 12, 0>, true>(s, st); break;
+                }
+            else
+                r = launch_strided<T, true, 1>(d, s, st);
+            prof_end(st);
+            return r;
+        };
+        if (db == 0)
+            e = strided(da, lg1, true, true, work, dst);
+        else
+        {
+            e = strided(da, lg1, true, false, work, dst);
+            if (e == cudaSuccess) e = strided(db, lg1 + da, false, true, dst, dst);
+        }
+        if (e != cudaSuccess) return e; // (cudaErrorNotSupported cannot appear here: the row pass already built a tensor map)
+        *launched = kind;
+        return cudaSuccess;
+    }
+
+} // namespace gpuntt_b200

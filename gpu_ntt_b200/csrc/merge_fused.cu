@@ -1,0 +1,519 @@
+// gpu_ntt_b200/csrc/merge_fused.cu -- two-pass Merge-NTT plans in ONE launch, the passes chained through the L2.
+//
+// The reference runs a 2^12..2^16-point transform as two kernels (plans [logN-9, 9], ntt.cuh:628-636 of the
+// reference; launches at ntt.cu:2104-2141), so every coefficient crosses HBM twice.  The tuned kernels of
+// fast_kernels.cuh kept that structure (strided pass + contiguous pass, two launches).  Here both passes live in one
+// persistent kernel:
+//   * every CTA owns a share of the FIRST pass's tiles and a share of the SECOND pass's tiles and walks them in one
+//     merged order; a second-pass tile is only loaded once the first pass has finished every polynomial it touches
+//     (one counter word per polynomial in global memory: producers add 1 per stored tile with release semantics, the
+//     TMA-issuing thread polls with acquire loads -- never blocking its own stores, see below);
+//   * the second pass trails the first by a few tile times (`lag` polynomials), so what it reads was written to
+//     the L2 microseconds earlier and is still there (a wave of 2 x 148 tiles is ~10 MiB against 126 MB of L2), and
+//     in-place transforms overwrite the same dirty lines before they are evicted: the data crosses HBM ONCE
+//     (read by the first pass, written back after the second);
+//   * a call is one launch instead of two.
+// Deadlock freedom: every tile has a virtual time (first pass: its polynomial; second pass: its last polynomial +
+// lag, lag >= polynomials per contiguous tile); every CTA processes its tiles in increasing time and a tile only
+// depends on tiles of strictly smaller time.  A tile that has been loaded is always computed, stored and signalled:
+// the producer thread polls "dependency satisfied?" and "consumers done?" in one loop and never spins on a dependency
+// while a finished tile waits for its store.  The grid never exceeds the number of co-resident CTAs.
+// The counters are self-cleaning (the last second-pass tile that observes a polynomial resets its word), so the
+// workspace is all-zero between calls and no memset is enqueued.
+#include "fast_kernels.cuh"
+
+namespace gpuntt_b200
+{
+
+    template <typename T> struct FusedArgs
+    {
+        FastArgs<T> s, c;     // the strided pass / the contiguous pass (in, out, work, rr, cta_per_seg unused)
+        unsigned* counters;   // one word per polynomial: low 16 bits = first-pass tiles stored, high 16 = second-pass observers
+        int fwd;              // 1: strided pass first (forward transform), 0: contiguous pass first (inverse)
+        int lag;              // see above
+        int g_str;            // CTAs [0, g_str) take the strided tiles, round robin
+        int c_off, con_k, con_extra; // CTAs from c_off on take the contiguous tiles: the first con_extra ranges have con_k + 1
+                                     // CTAs, the others con_k; CTA j of a range takes tile groups j, j + k, ...
+        int tpp_log;          // log2 strided tiles per polynomial
+        int nranges;          // contiguous ranges per polynomial
+        int ngroups;          // contiguous tile groups = ceil(batch / polynomials per tile)
+    };
+
+    __device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity)
+    {
+        uint32_t ok;
+        asm volatile("{\n\t"
+                     ".reg .pred P;\n\t"
+                     "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, P;\n\t"
+                     "}"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+        return ok;
+    }
+    __device__ __forceinline__ unsigned ld_acquire(const unsigned* p)
+    {
+        unsigned v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v)
+    {
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    }
+    __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+    // A CTA's position in its two tile streams.  next() yields the tiles in the merged (virtual time) order.
+    struct FusedCursor
+    {
+        long long s_next, s_end; // strided tile ids (poly << tpp_log | column chunk), step s_step
+        int s_step;
+        int q_next, q_end, q_step; // contiguous tile groups
+    };
+    struct FusedTile
+    {
+        int kind;      // 0 strided, 1 contiguous, -1 none
+        long long id;  // strided tile id / contiguous group
+    };
+
+    template <int NPLOG> __device__ __forceinline__ FusedTile fused_peek(const FusedCursor& k, int fwd, int lag, int tpp_log, int batch)
+    {
+        const bool hasS = k.s_next < k.s_end, hasC = k.q_next < k.q_end;
+        FusedTile t;
+        t.kind = -1;
+        t.id = 0;
+        if (!hasS && !hasC) return t;
+        const long long polyS = k.s_next >> tpp_log;
+        long long pmaxC = (((long long) k.q_next + 1) << NPLOG) - 1;
+        if (pmaxC > batch - 1) pmaxC = batch - 1;
+        bool pickC;
+        if (fwd)
+            pickC = hasC && (!hasS || pmaxC + lag <= polyS); // contiguous is the second pass: time pmaxC + lag
+        else
+            pickC = hasC && (!hasS || pmaxC <= polyS + lag); // strided is the second pass: time polyS + lag
+        t.kind = pickC ? 1 : 0;
+        t.id = pickC ? (long long) k.q_next : k.s_next;
+        return t;
+    }
+    __device__ __forceinline__ void fused_advance(FusedCursor& k, const FusedTile& t)
+    {
+        if (t.kind == 1)
+            k.q_next += k.q_step;
+        else
+            k.s_next += k.s_step;
+    }
+
+    template <typename SS, typename SC>
+    __global__ void __launch_bounds__(kFastThreads, 2)
+        fused2_kernel(const FusedArgs<typename SS::T> f, const __grid_constant__ CUtensorMap mapA_in, const __grid_constant__ CUtensorMap mapA_out,
+                      const __grid_constant__ CUtensorMap mapB)
+    {
+        using T = typename SS::T;
+        static_assert(SS::STRIDED && !SC::STRIDED && SS::TILE_SMEM == SC::TILE_SMEM && SS::INV == SC::INV, "one strided and one contiguous pass");
+        static_assert(SC::NT == 0 && SC::R3 == 0, "merge passes only");
+        constexpr int TILE = SS::TILE_SMEM;
+        extern __shared__ __align__(128) unsigned char smem_raw[];
+        unsigned char* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+        unsigned char* bufs = smem;
+        Twiddle<T>* twS = reinterpret_cast<Twiddle<T>*>(smem + 2 * TILE);
+        Twiddle<T>* twC = twS + (SS::TW1 + SS::TW2);
+        uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * TILE + SS::TW_SMEM + SC::TW_SMEM); // full[2], done[2]
+
+        const int tid = threadIdx.x;
+        const int batch = f.s.batch, n = f.s.n;
+        const int fwd = f.fwd, lag = f.lag, tpp_log = f.tpp_log;
+
+        // ---- this CTA's shares
+        FusedCursor cur;
+        cur.s_step = f.g_str;
+        cur.s_next = (int) blockIdx.x < f.g_str ? (long long) blockIdx.x : 0;
+        cur.s_end = (int) blockIdx.x < f.g_str ? ((long long) batch << tpp_log) : 0;
+        int range = 0;
+        cur.q_next = 0;
+        cur.q_end = 0;
+        cur.q_step = 1;
+        if ((int) blockIdx.x >= f.c_off)
+        {
+            const int cb = (int) blockIdx.x - f.c_off;
+            const int big = f.con_extra * (f.con_k + 1);
+            int kk, j;
+            if (cb < big)
+            {
+                kk = f.con_k + 1;
+                range = cb / kk;
+                j = cb % kk;
+            }
+            else
+            {
+                kk = f.con_k;
+                range = f.con_extra + (cb - big) / kk;
+                j = (cb - big) % kk;
+            }
+            if (range < f.nranges)
+            {
+                cur.q_next = j;
+                cur.q_end = f.ngroups;
+                cur.q_step = kk;
+            }
+        }
+        const bool doS = cur.s_next < cur.s_end, doC = cur.q_next < cur.q_end;
+
+        if (tid == kConsumers)
+        {
+            tma_prefetch_desc(&mapA_in);
+            tma_prefetch_desc(&mapA_out);
+            tma_prefetch_desc(&mapB);
+        }
+        if (tid == 0)
+        {
+            mbar_init(smem_u32(&bars[0]), 1);
+            mbar_init(smem_u32(&bars[1]), 1);
+            mbar_init(smem_u32(&bars[2]), kConsumers);
+            mbar_init(smem_u32(&bars[3]), kConsumers);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            fence_async();
+        }
+        __syncthreads();
+
+        if (tid >= kConsumers)
+        {
+            // =================== producer: one thread runs the whole load / store / signal state machine ===================
+            if (tid == kConsumers)
+            {
+                FusedCursor ldc = cur;
+                FusedTile slot[2];
+                unsigned t_load = 0, t_store = 0;
+                bool more = doS || doC;
+                while (more || t_store < t_load)
+                {
+                    bool progressed = false;
+                    if (more && t_load < t_store + 2)
+                    {
+                        const FusedTile t = fused_peek<SC::NPLOG>(ldc, fwd, lag, tpp_log, batch);
+                        if (t.kind < 0)
+                            more = false;
+                        else
+                        {
+                            const bool second = fwd ? (t.kind == 1) : (t.kind == 0);
+                            bool ok = true;
+                            long long p0 = 0, p1 = 0; // polynomials this tile depends on: [p0, p1)
+                            unsigned need = 0;
+                            if (second)
+                            {
+                                if (t.kind == 1)
+                                {
+                                    p0 = t.id << SC::NPLOG;
+                                    p1 = p0 + (1 << SC::NPLOG);
+                                    if (p1 > batch) p1 = batch;
+                                    need = 1u << tpp_log;
+                                }
+                                else
+                                {
+                                    p0 = t.id >> tpp_log;
+                                    p1 = p0 + 1;
+                                    need = (unsigned) f.nranges;
+                                }
+                                for (long long p = p0; p < p1 && ok; p++) ok = (ld_acquire(f.counters + p) & 0xffffu) == need;
+                            }
+                            if (ok)
+                            {
+                                if (second) fence_proxy_async_all(); // the bulk read below is ordered after the acquire loads
+                                const int b = (int) (t_load & 1);
+                                const uint32_t bar = smem_u32(&bars[b]);
+                                const uint32_t dst = smem_u32(bufs + b * TILE);
+                                mbar_expect_tx(bar, TILE);
+                                const CUtensorMap* mp = second ? &mapB : &mapA_in;
+                                if (t.kind == 0)
+                                {
+                                    const long long poly = t.id >> tpp_log, cc = t.id & ((1LL << tpp_log) - 1);
+                                    tma_load_3d(dst, mp, 0, (int) (cc << (SS::C - SS::CB)), (int) (poly << (n - f.s.lo)), bar);
+                                }
+                                else
+                                    tma_load_3d(dst, mp, 0, range << (SC::KC - SC::CB), (int) (t.id << SC::NPLOG), bar);
+                                if (second)
+                                {
+                                    // self-cleaning counters: the last observer of a polynomial zeroes its word
+                                    const unsigned observers = t.kind == 1 ? (unsigned) f.nranges : (1u << tpp_log);
+                                    for (long long p = p0; p < p1; p++)
+                                    {
+                                        const unsigned old = atomicAdd(f.counters + p, 0x10000u);
+                                        if ((old >> 16) == observers - 1) atomicExch(f.counters + p, 0u);
+                                    }
+                                }
+                                slot[b] = t;
+                                fused_advance(ldc, t);
+                                t_load++;
+                                progressed = true;
+                            }
+                        }
+                    }
+                    if (t_store < t_load)
+                    {
+                        const int b = (int) (t_store & 1);
+                        if (mbar_test(smem_u32(&bars[2 + b]), (t_store >> 1) & 1))
+                        {
+                            const FusedTile t = slot[b];
+                            const bool second = fwd ? (t.kind == 1) : (t.kind == 0);
+                            const uint32_t src = smem_u32(bufs + b * TILE);
+                            const CUtensorMap* mp = second ? &mapB : &mapA_out;
+                            if (t.kind == 0)
+                            {
+                                const long long poly = t.id >> tpp_log, cc = t.id & ((1LL << tpp_log) - 1);
+                                tma_store_3d(mp, 0, (int) (cc << (SS::C - SS::CB)), (int) (poly << (n - f.s.lo)), src);
+                            }
+                            else
+                                tma_store_3d(mp, 0, range << (SC::KC - SC::CB), (int) (t.id << SC::NPLOG), src);
+                            bulk_commit();
+                            if (!second)
+                            {
+                                // first-pass tile: its polynomials advance once the bulk store is COMPLETE (not merely read)
+                                bulk_wait0();
+                                fence_proxy_async_all();
+                                if (t.kind == 0)
+                                    red_release_add(f.counters + (t.id >> tpp_log), 1u);
+                                else
+                                {
+                                    long long p0 = t.id << SC::NPLOG, p1 = p0 + (1 << SC::NPLOG);
+                                    if (p1 > batch) p1 = batch;
+                                    for (long long p = p0; p < p1; p++) red_release_add(f.counters + p, 1u);
+                                }
+                            }
+                            else
+                                bulk_wait_read0(); // the buffer may be overwritten again
+                            t_store++;
+                            progressed = true;
+                        }
+                    }
+                    if (!progressed) __nanosleep(32);
+                }
+                bulk_wait0();
+            }
+        }
+        else
+        {
+            // =================== consumer warps ===================
+            typename ModOf<SS>::type MS(f.s.p);
+            typename ModOf<SC>::type MC(f.c.p);
+            const Twiddle<T> ninv{f.s.ninv_w, f.s.ninv_wq};
+            const bool triv = !SS::INV && !f.s.plus && f.s.first && (f.s.lo + SS::D == n) && f.s.table[0] == T(1);
+            if (doS) build_twiddles<SS>(twS, f.s.table, 0, n, f.s.n_tw, f.s.lo, f.s.plus, f.s.p, f.s.mu, f.s.pbits, tid, kConsumers);
+            if (doC) build_twiddles<SC>(twC, f.c.table, range, n, f.c.n_tw, 0, f.c.plus, f.c.p, f.c.mu, f.c.pbits, tid, kConsumers);
+            consumer_sync();
+            FusedCursor cc = cur;
+            unsigned t_idx = 0;
+            for (;;)
+            {
+                const FusedTile t = fused_peek<SC::NPLOG>(cc, fwd, lag, tpp_log, batch);
+                if (t.kind < 0) break;
+                fused_advance(cc, t);
+                const int b = (int) (t_idx & 1);
+                unsigned char* buf = bufs + b * TILE;
+                mbar_wait(smem_u32(&bars[b]), (t_idx >> 1) & 1); // tile landed
+                if (t.kind == 0)
+                    tile_rounds<SS, false>(buf, twS, twS + SS::TW1, twS + SS::TW1 + SS::TW2, MS, tid, ninv, nullptr, f.s, triv);
+                else
+                    tile_rounds<SC, false>(buf, twC, twC + SC::TW1, twC + SC::TW1 + SC::TW2, MC, tid, ninv, nullptr, f.c, false);
+                fence_async(); // make the generic-proxy writes visible to the bulk store
+                mbar_arrive(smem_u32(&bars[2 + b]));
+                t_idx++;
+            }
+        }
+    }
+
+    static std::atomic<int> g_fused_lag_steps{2};
+    void fused_set_lag_steps(int v) { g_fused_lag_steps.store(v < 0 ? 0 : v); }
+
+    // in / out / table / p / ninv / mu / pbits / n / plus / batch / in_bound of `a` are filled in; lo_s = row stride (log2) of the
+    // strided pass.  Returns cudaErrorNotSupported when this call cannot take the fused kernel (the caller launches the
+    // two passes separately).
+    template <typename SS, typename SC>
+    static cudaError_t launch_fused(const FastArgs<typename SS::T>& a, int lo_s, bool inverse, unsigned* counters, cudaStream_t st,
+                                    void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t))
+    {
+        using T = typename SS::T;
+        constexpr int kMaxDev = 64;
+        static std::atomic<int> cached_bps[kMaxDev];
+        static std::atomic<int> cached_sms[kMaxDev];
+        constexpr int SMEM = 2 * SS::TILE_SMEM + SS::TW_SMEM + SC::TW_SMEM + 128 + 1024;
+        auto kern = fused2_kernel<SS, SC>;
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 0 || dev >= kMaxDev) return cudaErrorNotSupported;
+        int bps = cached_bps[dev].load(std::memory_order_acquire), sms = cached_sms[dev].load(std::memory_order_acquire);
+        if (bps <= 0 || sms <= 0)
+        {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+            if (e != cudaSuccess) return e;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            int b = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kFastThreads, SMEM);
+            if (e != cudaSuccess) return e;
+            if (b < 1) return cudaErrorNotSupported; // (the flag protocol needs every CTA resident)
+            bps = b;
+            cached_sms[dev].store(sms, std::memory_order_release);
+            cached_bps[dev].store(bps, std::memory_order_release);
+        }
+        const int n = a.n, batch = a.batch;
+        if (lo_s + SS::D != n || lo_s < SS::C) return cudaErrorNotSupported; // one strided range (two-pass plans)
+        const int tpp_log = lo_s - SS::C;
+        const int nranges = 1 << (n - SC::KC);
+        if (n < SC::KC || tpp_log > 14 || nranges > 16384) return cudaErrorNotSupported;
+        const long long slots = (long long) sms * bps;
+        if (nranges > slots) return cudaErrorNotSupported;
+        const long long rows = (long long) batch << (n - lo_s);
+        if (rows >= (1LL << 31)) return cudaErrorNotSupported;
+
+        FusedArgs<T> f{};
+        f.s = a;
+        f.s.lo = lo_s;
+        f.s.first = inverse ? 0 : 1;
+        f.s.last = inverse ? 1 : 0;
+        f.c = a;
+        f.c.lo = 0;
+        f.c.first = inverse ? 1 : 0;
+        f.c.last = inverse ? 0 : 1;
+        f.c.in_bound = 1;
+        f.counters = counters;
+        f.fwd = inverse ? 0 : 1;
+        f.tpp_log = tpp_log;
+        f.nranges = nranges;
+        f.ngroups = (batch + (1 << SC::NPLOG) - 1) >> SC::NPLOG;
+        const long long n_str = (long long) batch << tpp_log;
+        long long grid;
+        const long long con_each = (slots - n_str) / nranges; // CTAs per range left over when every strided tile has its own CTA
+        if (n_str <= slots / 2 && con_each >= 1)
+        {
+            // small batch: separate CTAs per pass (the contiguous CTAs build their twiddles while the strided ones compute)
+            long long k = con_each < f.ngroups ? con_each : f.ngroups;
+            f.g_str = (int) n_str;
+            f.c_off = (int) n_str;
+            f.con_k = (int) k;
+            f.con_extra = 0;
+            grid = n_str + k * nranges;
+            f.lag = 1 << SC::NPLOG;
+        }
+        else
+        {
+            grid = slots;
+            f.g_str = (int) grid;
+            f.c_off = 0;
+            f.con_k = (int) (grid / nranges);
+            f.con_extra = (int) (grid % nranges);
+            // polynomials the whole grid moves through one pass per tile time
+            const long long per_step = (grid << (SS::K)) >> n;
+            long long lag = g_fused_lag_steps.load() * (per_step > 0 ? per_step : 1);
+            if (lag < (1 << SC::NPLOG)) lag = 1 << SC::NPLOG;
+            if (lag > 0x3fffffff) lag = 0x3fffffff;
+            f.lag = (int) lag;
+        }
+        alignas(64) CUtensorMap mA_in, mA_out, mB;
+        if (!inverse)
+        {
+            if (!make_map<SS>(&mA_in, a.in, n, lo_s, batch)) return cudaErrorNotSupported;
+            if (a.in == a.out)
+                mA_out = mA_in;
+            else if (!make_map<SS>(&mA_out, a.out, n, lo_s, batch))
+                return cudaErrorNotSupported;
+            if (!make_map<SC>(&mB, a.out, n, 0, batch)) return cudaErrorNotSupported;
+        }
+        else
+        {
+            if (!make_map<SC>(&mA_in, a.in, n, 0, batch)) return cudaErrorNotSupported;
+            if (a.in == a.out)
+                mA_out = mA_in;
+            else if (!make_map<SC>(&mA_out, a.out, n, 0, batch))
+                return cudaErrorNotSupported;
+            if (!make_map<SS>(&mB, a.out, n, lo_s, batch)) return cudaErrorNotSupported;
+        }
+        prof_begin(1, st);
+        kern<<<(unsigned) grid, kFastThreads, SMEM, st>>>(f, mA_in, mA_out, mB);
+        prof_end(st);
+        return cudaGetLastError();
+    }
+
+    // Two-pass plans in one launch.  Returns cudaErrorNotSupported when the shape / modulus is not covered.
+    template <typename T>
+    cudaError_t fused_merge(const FastArgs<T>& a, const FastPlan& pl, bool inverse, bool f60_or_l32, bool lazy_inv, unsigned* counters,
+                            cudaStream_t st, void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t))
+    {
+        if (pl.npass != 2 || !pl.strided[0] || pl.strided[1]) return cudaErrorNotSupported;
+        const int d = pl.d[0], lo = pl.lo[0];
+        if constexpr (sizeof(T) == 8)
+        {
+            using Cf = Shape<T, false, 2, false, 4, 4, 12, 1>;
+            using Ci = Shape<T, true, 1, false, 4, 4, 12, 1>;
+            if (!inverse)
+            {
+                if (!f60_or_l32) return cudaErrorNotSupported;
+                switch (d)
+                {
+                    case 4: return launch_fused<Shape<T, false, 2, true, 4, 0, 12, 0>, Cf>(a, lo, false, counters, st, prof_begin, prof_end);
+                    case 5: return launch_fused<Shape<T, false, 2, true, 3, 2, 12, 0>, Cf>(a, lo, false, counters, st, prof_begin, prof_end);
+                    case 6: return launch_fused<Shape<T, false, 2, true, 3, 3, 12, 0>, Cf>(a, lo, false, counters, st, prof_begin, prof_end);
+                    case 7: return launch_fused<Shape<T, false, 2, true, 4, 3, 12, 0>, Cf>(a, lo, false, counters, st, prof_begin, prof_end);
+                    case 8: return launch_fused<Shape<T, false, 2, true, 4, 4, 12, 0>, Cf>(a, lo, false, counters, st, prof_begin, prof_end);
+                    default: return cudaErrorNotSupported;
+                }
+            }
+            if (!lazy_inv) return cudaErrorNotSupported;
+            switch (d)
+            {
+                case 4: return launch_fused<Shape<T, true, 1, true, 4, 0, 12, 0>, Ci>(a, lo, true, counters, st, prof_begin, prof_end);
+                case 5: return launch_fused<Shape<T, true, 1, true, 3, 2, 12, 0>, Ci>(a, lo, true, counters, st, prof_begin, prof_end);
+                case 6: return launch_fused<Shape<T, true, 1, true, 3, 3, 12, 0>, Ci>(a, lo, true, counters, st, prof_begin, prof_end);
+                case 7: return launch_fused<Shape<T, true, 1, true, 4, 3, 12, 0>, Ci>(a, lo, true, counters, st, prof_begin, prof_end);
+                case 8: return launch_fused<Shape<T, true, 1, true, 4, 4, 12, 0>, Ci>(a, lo, true, counters, st, prof_begin, prof_end);
+                default: return cudaErrorNotSupported;
+            }
+        }
+        else
+        {
+            using Cl = Shape<T, false, 2, false, 5, 5, 13, 1>;
+            using Cf = Shape<T, false, 0, false, 5, 5, 13, 1>;
+            using Ci = Shape<T, true, 0, false, 5, 5, 13, 1>;
+            if (!inverse && f60_or_l32)
+            {
+                switch (d)
+                {
+                    case 3: return launch_fused<Shape<T, false, 2, true, 3, 0, 13, 0>, Cl>(a, lo, false, counters, st, prof_begin, prof_end);
+                    case 4: return launch_fused<Shape<T, false, 2, true, 4, 0, 13, 0>, Cl>(a, lo, false, counters, st, prof_begin, prof_end);
+                    case 5: return launch_fused<Shape<T, false, 2, true, 5, 0, 13, 0>, Cl>(a, lo, false, counters, st, prof_begin, prof_end);
+                    case 6: return launch_fused<Shape<T, false, 2, true, 3, 3, 13, 0>, Cl>(a, lo, false, counters, st, prof_begin, prof_end);
+                    case 7: return launch_fused<Shape<T, false, 2, true, 4, 3, 13, 0>, Cl>(a, lo, false, counters, st, prof_begin, prof_end);
+                    case 8: return launch_fused<Shape<T, false, 2, true, 4, 4, 13, 0>, Cl>(a, lo, false, counters, st, prof_begin, prof_end);
+                    default: return cudaErrorNotSupported;
+                }
+            }
+            if (!inverse)
+            {
+                switch (d)
+                {
+                    case 3: return launch_fused<Shape<T, false, 0, true, 3, 0, 13, 0>, Cf>(a, lo, false, counters, st, prof_begin, prof_end);
+                    case 4: return launch_fused<Shape<T, false, 0, true, 4, 0, 13, 0>, Cf>(a, lo, false, counters, st, prof_begin, prof_end);
+                    case 5: return launch_fused<Shape<T, false, 0, true, 5, 0, 13, 0>, Cf>(a, lo, false, counters, st, prof_begin, prof_end);
+                    case 6: return launch_fused<Shape<T, false, 0, true, 3, 3, 13, 0>, Cf>(a, lo, false, counters, st, prof_begin, prof_end);
+                    case 7: return launch_fused<Shape<T, false, 0, true, 4, 3, 13, 0>, Cf>(a, lo, false, counters, st, prof_begin, prof_end);
+                    case 8: return launch_fused<Shape<T, false, 0, true, 4, 4, 13, 0>, Cf>(a, lo, false, counters, st, prof_begin, prof_end);
+                    default: return cudaErrorNotSupported;
+                }
+            }
+            switch (d)
+            {
+                case 3: return launch_fused<Shape<T, true, 0, true, 3, 0, 13, 0>, Ci>(a, lo, true, counters, st, prof_begin, prof_end);
+                case 4: return launch_fused<Shape<T, true, 0, true, 4, 0, 13, 0>, Ci>(a, lo, true, counters, st, prof_begin, prof_end);
+                case 5: return launch_fused<Shape<T, true, 0, true, 5, 0, 13, 0>, Ci>(a, lo, true, counters, st, prof_begin, prof_end);
+                case 6: return launch_fused<Shape<T, true, 0, true, 3, 3, 13, 0>, Ci>(a, lo, true, counters, st, prof_begin, prof_end);
+                case 7: return launch_fused<Shape<T, true, 0, true, 4, 3, 13, 0>, Ci>(a, lo, true, counters, st, prof_begin, prof_end);
+                case 8: return launch_fused<Shape<T, true, 0, true, 4, 4, 13, 0>, Ci>(a, lo, true, counters, st, prof_begin, prof_end);
+                default: return cudaErrorNotSupported;
+            }
+        }
+    }
+    template cudaError_t fused_merge<uint64_t>(const FastArgs<uint64_t>&, const FastPlan&, bool, bool, bool, unsigned*, cudaStream_t,
+                                               void (*)(int, cudaStream_t), void (*)(cudaStream_t));
+    template cudaError_t fused_merge<uint32_t>(const FastArgs<uint32_t>&, const FastPlan&, bool, bool, bool, unsigned*, cudaStream_t,
+                                               void (*)(int, cudaStream_t), void (*)(cudaStream_t));
+
+} // namespace gpuntt_b200

@@ -626,7 +626,8 @@ namespace gpuntt_b200
     template <typename T>
     cudaError_t fast_merge(const T* in, T* out, const T* table, T p, T ninv, int n_power, int plus, bool inverse,
                            int batch, cudaStream_t st, int* launched, void (*prof_begin)(int, cudaStream_t),
-                           void (*prof_end)(cudaStream_t), int in_bound = 1);
+                           void (*prof_end)(cudaStream_t), int in_bound = 1, unsigned* counters = nullptr);
+    void fused_set_lag_steps(int v); // merge_fused.cu
     bool fast_supported(int n_power, int element_bits);
 
     static int fail(int code, const std::string& msg)
@@ -674,6 +675,43 @@ namespace gpuntt_b200
         }
         *out = w.ptr;
         return cudaSuccess;
+    }
+
+    // Per-polynomial progress counters of the single-launch two-pass kernels (merge_fused.cu): all-zero between calls
+    // (the kernels clean up after themselves), so they are zeroed once, when the buffer is allocated -- on the caller's
+    // stream, i.e. before the first kernel that uses them.  nullptr: run the passes as separate launches.
+    static std::atomic<int> g_fused_enabled{1};
+    static unsigned* fused_counters(void* stream, long long polys)
+    {
+        if (!g_fused_enabled.load() || polys <= 0) return nullptr;
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+        const size_t bytes = (size_t) polys * sizeof(unsigned);
+        std::lock_guard<std::mutex> lk(g_ws_mutex);
+        Workspace& w = g_ws[std::make_tuple(dev, stream, 8)];
+        if (w.bytes < bytes)
+        {
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            cudaStreamIsCapturing((cudaStream_t) stream, &cap);
+            if (cap != cudaStreamCaptureStatusNone) return nullptr; // no allocation inside a capture: separate launches
+            if (w.ptr)
+            {
+                if (cudaStreamSynchronize((cudaStream_t) stream) != cudaSuccess) return nullptr;
+                cudaFree(w.ptr);
+                w.ptr = nullptr;
+                w.bytes = 0;
+            }
+            size_t want = bytes < (1u << 16) ? (1u << 16) : bytes * 2;
+            if (cudaMalloc(&w.ptr, want) != cudaSuccess)
+            {
+                cudaGetLastError();
+                w.ptr = nullptr;
+                return nullptr;
+            }
+            w.bytes = want;
+            if (cudaMemsetAsync(w.ptr, 0, want, (cudaStream_t) stream) != cudaSuccess) return nullptr;
+        }
+        return reinterpret_cast<unsigned*>(w.ptr);
     }
 
     template <typename K> static cudaError_t allow_smem(K kernel, size_t bytes)
@@ -841,7 +879,7 @@ namespace gpuntt_b200
             cudaError_t fe = fast_merge<T>(reinterpret_cast<const T*>(d->in), reinterpret_cast<T*>(d->out),
                                            reinterpret_cast<const T*>(d->root_of_unity_table), (T) d->modulus_value,
                                            (T) d->mod_inverse_value, n, plus ? 1 : 0, inv, d->batch_size, st, &launched,
-                                           prof_begin, prof_end);
+                                           prof_begin, prof_end, 1, fused_counters(d->stream, d->batch_size));
             if (fe != cudaSuccess) return cuda_fail(fe, "fast_pass_kernel launch");
             if (launched > 0) return GPUNTT_B200_OK;
         }
@@ -1167,6 +1205,15 @@ extern "C"
 
     void gpuntt_b200_set_profiling(int on) { g_profiling.store(on ? 1 : 0); }
     void gpuntt_b200_force_generic_path(int on) { g_force_generic.store(on ? 1 : 0); }
+    void gpuntt_b200_tune(int knob, int value)
+    {
+        switch (knob)
+        {
+            case GPUNTT_B200_TUNE_FUSED_PASSES: g_fused_enabled.store(value ? 1 : 0); break;
+            case GPUNTT_B200_TUNE_FUSED_LAG: fused_set_lag_steps(value); break;
+            default: break;
+        }
+    }
 
     int gpuntt_b200_profile_read(float* ms_out, int* kind_out, int max_records)
     {

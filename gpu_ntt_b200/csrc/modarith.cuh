@@ -249,6 +249,13 @@ namespace gpuntt_b200
             Y = X + k - t;
             X = Xn;
         }
+        // x - 8p when hi32(x) > hi32(8p): [0, 16p + 2^32) -> [0, 8p + 2^32)
+        __device__ __forceinline__ T csub8_hi(T x) const
+        {
+            uint32_t xh;
+            asm("{\n\t.reg .u32 lo;\n\tmov.b64 {lo, %0}, %1;\n\t}" : "=r"(xh) : "l"(x));
+            return xh > e1 ? x + neg_eight_p : x;
+        }
         // twiddle-1 butterfly on values below K (K a multiple of p): X' = X + Y, Y' = X - Y + K, both below 2K
         __device__ __forceinline__ void add_sub(T& X, T& Y, T K) const
         {
@@ -303,6 +310,7 @@ namespace gpuntt_b200
         }
         // bound (multiple of p) of the values before stage it of a first cyclic round with canonical inputs
         __device__ __forceinline__ T triv_bound(int it, int = 1) const { return (it == 0 ? 1 : it == 1 ? 2 : 4) * p; }
+        __device__ __forceinline__ T csub8_hi(T x) const { return x; } // (in_bound > 1 never reaches the 32-bit kernels)
         __device__ __forceinline__ T canon_fwd(T x) const // [0, 8p) -> [0, p)
         {
             const T q = __umulhi(x, red_m); // in {floor(x/p) - 1, floor(x/p)}

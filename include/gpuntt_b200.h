@@ -182,6 +182,14 @@ int gpuntt_b200_profile_read(float* ms_out, int* kind_out, int max_records);
  * takes the generic pass kernel, so both implementations can be checked against the oracle. */
 void gpuntt_b200_force_generic_path(int on);
 
+/* Tuning / A-B testing knobs (process-wide; results never depend on them):
+ *   FUSED_PASSES  1 (default): two-pass plans run as ONE launch with the passes chained through the L2
+ *                 (merge_fused.cu); 0: one launch per pass.
+ *   FUSED_LAG     how many tile times the second pass trails the first inside the fused kernel (default 2). */
+#define GPUNTT_B200_TUNE_FUSED_PASSES 1
+#define GPUNTT_B200_TUNE_FUSED_LAG 2
+void gpuntt_b200_tune(int knob, int value);
+
 /* Human-readable message for the last non-OK status returned on this thread. */
 const char* gpuntt_b200_last_error(void);
 
