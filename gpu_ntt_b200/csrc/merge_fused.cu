@@ -183,11 +183,39 @@ namespace gpuntt_b200
             {
                 FusedCursor ldc = cur;
                 FusedTile slot[2];
+                FusedTile pend;       // first-pass tile whose store has been issued but not yet signalled
+                pend.kind = -1;
+                pend.id = 0;
                 unsigned t_load = 0, t_store = 0;
                 bool more = doS || doC;
-                while (more || t_store < t_load)
+                while (more || t_store < t_load || pend.kind >= 0)
                 {
                     bool progressed = false;
+                    // ---- (1) store a finished tile
+                    if (t_store < t_load)
+                    {
+                        const int b = (int) (t_store & 1);
+                        if (mbar_test(smem_u32(&bars[2 + b]), (t_store >> 1) & 1))
+                        {
+                            const FusedTile t = slot[b];
+                            const bool second = fwd ? (t.kind == 1) : (t.kind == 0);
+                            const uint32_t src = smem_u32(bufs + b * TILE);
+                            const CUtensorMap* mp = second ? &mapB : &mapA_out;
+                            if (t.kind == 0)
+                            {
+                                const long long poly = t.id >> tpp_log, cc = t.id & ((1LL << tpp_log) - 1);
+                                tma_store_3d(mp, 0, (int) (cc << (SS::C - SS::CB)), (int) (poly << (n - f.s.lo)), src);
+                            }
+                            else
+                                tma_store_3d(mp, 0, range << (SC::KC - SC::CB), (int) (t.id << SC::NPLOG), src);
+                            bulk_commit();
+                            bulk_wait_read0(); // the buffer may be overwritten again
+                            if (!second) pend = t;
+                            t_store++;
+                            progressed = true;
+                        }
+                    }
+                    // ---- (2) load the next tile of the merged order once its buffer is free and its dependencies are met
                     if (more && t_load < t_store + 2)
                     {
                         const FusedTile t = fused_peek<SC::NPLOG>(ldc, fwd, lag, tpp_log, batch);
@@ -248,42 +276,22 @@ namespace gpuntt_b200
                             }
                         }
                     }
-                    if (t_store < t_load)
+                    // ---- (3) signal the first-pass tile stored above: its polynomials advance once the bulk store is COMPLETE
+                    //          (not merely read); the next load is already in flight while this waits
+                    if (pend.kind >= 0)
                     {
-                        const int b = (int) (t_store & 1);
-                        if (mbar_test(smem_u32(&bars[2 + b]), (t_store >> 1) & 1))
+                        bulk_wait0();
+                        fence_proxy_async_all();
+                        if (pend.kind == 0)
+                            red_release_add(f.counters + (pend.id >> tpp_log), 1u);
+                        else
                         {
-                            const FusedTile t = slot[b];
-                            const bool second = fwd ? (t.kind == 1) : (t.kind == 0);
-                            const uint32_t src = smem_u32(bufs + b * TILE);
-                            const CUtensorMap* mp = second ? &mapB : &mapA_out;
-                            if (t.kind == 0)
-                            {
-                                const long long poly = t.id >> tpp_log, cc = t.id & ((1LL << tpp_log) - 1);
-                                tma_store_3d(mp, 0, (int) (cc << (SS::C - SS::CB)), (int) (poly << (n - f.s.lo)), src);
-                            }
-                            else
-                                tma_store_3d(mp, 0, range << (SC::KC - SC::CB), (int) (t.id << SC::NPLOG), src);
-                            bulk_commit();
-                            if (!second)
-                            {
-                                // first-pass tile: its polynomials advance once the bulk store is COMPLETE (not merely read)
-                                bulk_wait0();
-                                fence_proxy_async_all();
-                                if (t.kind == 0)
-                                    red_release_add(f.counters + (t.id >> tpp_log), 1u);
-                                else
-                                {
-                                    long long p0 = t.id << SC::NPLOG, p1 = p0 + (1 << SC::NPLOG);
-                                    if (p1 > batch) p1 = batch;
-                                    for (long long p = p0; p < p1; p++) red_release_add(f.counters + p, 1u);
-                                }
-                            }
-                            else
-                                bulk_wait_read0(); // the buffer may be overwritten again
-                            t_store++;
-                            progressed = true;
+                            long long p0 = pend.id << SC::NPLOG, p1 = p0 + (1 << SC::NPLOG);
+                            if (p1 > batch) p1 = batch;
+                            for (long long p = p0; p < p1; p++) red_release_add(f.counters + p, 1u);
                         }
+                        pend.kind = -1;
+                        progressed = true;
                     }
                     if (!progressed) __nanosleep(32);
                 }

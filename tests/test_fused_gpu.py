@@ -106,11 +106,8 @@ def test_fused_concurrent_streams():
     ds = [to_dev(x, 64) for x in xs]
     streams = [torch.cuda.Stream(), torch.cuda.Stream()]
     torch.cuda.synchronize()
-    for rep in range(3):
-        for d, s in zip(ds, streams):
-            if rep:
-                continue
-            capi.ntt(d.view(300, -1), tab, P.modulus, 15, O.X_N_plus, stream=s)
+    for d, s in zip(ds, streams):
+        capi.ntt(d.view(300, -1), tab, P.modulus, 15, O.X_N_plus, stream=s)
     torch.cuda.synchronize()
     for d, w in zip(ds, wants):
         assert (to_host(d, 64) == w).all()
