@@ -119,9 +119,10 @@ namespace gpuntt_b200
     __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
     __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #ifdef GPUNTT_EXPERIMENT_NOSYNC // timing experiment only (wrong results): upper bound of what a barrier-free round structure could gain
-    __device__ __forceinline__ void consumer_sync() {}
+    __device__ __forceinline__ void consumer_sync(int = 1) {}
 #else
-    __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
+    // named barrier of one consumer group (256 threads); the fused kernels run two groups per CTA (ids 1 and 2)
+    __device__ __forceinline__ void consumer_sync(int id = 1) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kConsumers) : "memory"); }
 #endif
 
     // ------------------------------------------------------------------ compile-time pass shape
@@ -470,7 +471,7 @@ namespace gpuntt_b200
     __device__ __forceinline__ void tile_rounds(unsigned char* buf, const Twiddle<typename S::T>* tw1, const Twiddle<typename S::T>* tw2,
                                                 const Twiddle<typename S::T>* tw3, const typename ModOf<S>::type& M, int tid,
                                                 const Twiddle<typename S::T>& ninv, const Twiddle<typename S::T>* wtile,
-                                                const FastArgs<typename S::T>& a, bool triv)
+                                                const FastArgs<typename S::T>& a, bool triv, int bar = 1)
     {
         constexpr bool W1 = WMUL && S::R2 == 0, W2 = WMUL && S::R2 > 0;
         if constexpr (!S::INV)
@@ -492,12 +493,12 @@ namespace gpuntt_b200
                 fast_round<S, S::R1, S::LB1, S::G1, FIN1>(buf, tw1, M, tid, ninv);
             if constexpr (S::R2 > 0)
             {
-                consumer_sync();
+                consumer_sync(bar);
                 fast_round<S, S::R2, S::LB2, S::G2, FIN2, false, W2>(buf, tw2, M, tid, ninv, wtile, a.lo, 1, a.w_lazy != 0);
             }
             if constexpr (S::R3 > 0)
             {
-                consumer_sync();
+                consumer_sync(bar);
                 fast_round<S, S::R3, S::LB3, S::G3, true>(buf, tw3, M, tid, ninv);
             }
         }
@@ -506,12 +507,12 @@ namespace gpuntt_b200
             if constexpr (S::R3 > 0)
             {
                 fast_round<S, S::R3, S::LB3, S::G3, false>(buf, tw3, M, tid, ninv);
-                consumer_sync();
+                consumer_sync(bar);
             }
             if constexpr (S::R2 > 0)
             {
                 fast_round<S, S::R2, S::LB2, S::G2, false, false, W2>(buf, tw2, M, tid, ninv, wtile, a.lo);
-                consumer_sync();
+                consumer_sync(bar);
             }
             if constexpr (S::STRIDED)
             {

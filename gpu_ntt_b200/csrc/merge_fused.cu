@@ -104,8 +104,33 @@ namespace gpuntt_b200
             k.s_next += k.s_step;
     }
 
+    // One CTA per SM: two consumer groups of 8 warps (each takes the next tile of the CTA's merged order as soon as it is
+    // free, so short strided tiles and long contiguous tiles balance out), one producer thread, kFusedBufs tile buffers --
+    // loads run up to kFusedBufs tiles ahead of the arithmetic, which is what hides the dependency checks, the HBM latency
+    // of the first-pass tiles and the store-completion waits of the signalling (with two CTAs x two buffers per SM the
+    // consumers spent a third of their time waiting for tiles: profiles/r2_fused_v1_ncu_summary.txt).
+    constexpr int kFusedGroups = 2;
+    constexpr int kFusedConsumers = kFusedGroups * kConsumers;
+    constexpr int kFusedThreads = kFusedConsumers + 32;
+    constexpr int kFusedBufs = 5;
+
+    struct FusedCtl
+    {
+        uint64_t full[kFusedBufs], done[kFusedBufs];
+        int kind[kFusedBufs]; // what the producer loaded into each buffer
+        int next_t;           // next tile index to be claimed by a consumer group
+        int bcast[kFusedGroups][2];
+    };
+
+    template <typename SS, typename SC> struct FusedSmem
+    {
+        static constexpr int TILE = SS::TILE_SMEM;
+        static constexpr int TW = SS::TW_SMEM + SC::TW_SMEM;
+        static constexpr int BYTES = kFusedBufs * TILE + TW + (int) sizeof(FusedCtl) + 1024; // + slack to align the tiles to 1 KiB
+    };
+
     template <typename SS, typename SC>
-    __global__ void __launch_bounds__(kFastThreads, 2)
+    __global__ void __launch_bounds__(kFusedThreads, 1)
         fused2_kernel(const FusedArgs<typename SS::T> f, const __grid_constant__ CUtensorMap mapA_in, const __grid_constant__ CUtensorMap mapA_out,
                       const __grid_constant__ CUtensorMap mapB)
     {
@@ -113,12 +138,13 @@ namespace gpuntt_b200
         static_assert(SS::STRIDED && !SC::STRIDED && SS::TILE_SMEM == SC::TILE_SMEM && SS::INV == SC::INV, "one strided and one contiguous pass");
         static_assert(SC::NT == 0 && SC::R3 == 0, "merge passes only");
         constexpr int TILE = SS::TILE_SMEM;
+        constexpr int NB = kFusedBufs;
         extern __shared__ __align__(128) unsigned char smem_raw[];
         unsigned char* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
         unsigned char* bufs = smem;
-        Twiddle<T>* twS = reinterpret_cast<Twiddle<T>*>(smem + 2 * TILE);
+        Twiddle<T>* twS = reinterpret_cast<Twiddle<T>*>(smem + NB * TILE);
         Twiddle<T>* twC = twS + (SS::TW1 + SS::TW2);
-        uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * TILE + SS::TW_SMEM + SC::TW_SMEM); // full[2], done[2]
+        FusedCtl* ctl = reinterpret_cast<FusedCtl*>(smem + NB * TILE + SS::TW_SMEM + SC::TW_SMEM);
 
         const int tid = threadIdx.x;
         const int batch = f.s.batch, n = f.s.n;
@@ -158,8 +184,9 @@ namespace gpuntt_b200
             }
         }
         const bool doS = cur.s_next < cur.s_end, doC = cur.q_next < cur.q_end;
+        const int total = (doS ? (int) ((cur.s_end - 1 - cur.s_next) / cur.s_step + 1) : 0) + (doC ? (cur.q_end - 1 - cur.q_next) / cur.q_step + 1 : 0);
 
-        if (tid == kConsumers)
+        if (tid == kFusedConsumers)
         {
             tma_prefetch_desc(&mapA_in);
             tma_prefetch_desc(&mapA_out);
@@ -167,35 +194,37 @@ namespace gpuntt_b200
         }
         if (tid == 0)
         {
-            mbar_init(smem_u32(&bars[0]), 1);
-            mbar_init(smem_u32(&bars[1]), 1);
-            mbar_init(smem_u32(&bars[2]), kConsumers);
-            mbar_init(smem_u32(&bars[3]), kConsumers);
+            for (int b = 0; b < NB; b++)
+            {
+                mbar_init(smem_u32(&ctl->full[b]), 1);
+                mbar_init(smem_u32(&ctl->done[b]), kConsumers);
+            }
+            ctl->next_t = 0;
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             fence_async();
         }
         __syncthreads();
 
-        if (tid >= kConsumers)
+        if (tid >= kFusedConsumers)
         {
             // =================== producer: one thread runs the whole load / store / signal state machine ===================
-            if (tid == kConsumers)
+            if (tid == kFusedConsumers)
             {
                 FusedCursor ldc = cur;
-                FusedTile slot[2];
-                FusedTile pend;       // first-pass tile whose store has been issued but not yet signalled
-                pend.kind = -1;
-                pend.id = 0;
-                unsigned t_load = 0, t_store = 0;
-                bool more = doS || doC;
-                while (more || t_store < t_load || pend.kind >= 0)
+                FusedTile slot[NB];
+                FusedTile pq[4]; // first-pass tiles whose store has been issued but not yet signalled (FIFO)
+                unsigned pq_seq[4];
+                int pq_head = 0, pq_n = 0;
+                unsigned commits = 0; // bulk groups committed so far
+                int t_load = 0, t_store = 0;
+                while (t_store < total || pq_n > 0)
                 {
                     bool progressed = false;
-                    // ---- (1) store a finished tile
+                    // ---- (1) store the next finished tile (in order)
                     if (t_store < t_load)
                     {
-                        const int b = (int) (t_store & 1);
-                        if (mbar_test(smem_u32(&bars[2 + b]), (t_store >> 1) & 1))
+                        const int b = t_store % NB;
+                        if (mbar_test(smem_u32(&ctl->done[b]), (unsigned) (t_store / NB) & 1u))
                         {
                             const FusedTile t = slot[b];
                             const bool second = fwd ? (t.kind == 1) : (t.kind == 0);
@@ -209,88 +238,99 @@ namespace gpuntt_b200
                             else
                                 tma_store_3d(mp, 0, range << (SC::KC - SC::CB), (int) (t.id << SC::NPLOG), src);
                             bulk_commit();
+                            commits++;
                             bulk_wait_read0(); // the buffer may be overwritten again
-                            if (!second) pend = t;
+                            if (!second)
+                            {
+                                const int e = (pq_head + pq_n) & 3;
+                                pq[e] = t;
+                                pq_seq[e] = commits;
+                                pq_n++;
+                            }
                             t_store++;
                             progressed = true;
                         }
                     }
-                    // ---- (2) load the next tile of the merged order once its buffer is free and its dependencies are met
-                    if (more && t_load < t_store + 2)
+                    // ---- (2) load the next tile of the merged order once a buffer is free and its dependencies are met
+                    if (t_load < total && t_load < t_store + NB)
                     {
                         const FusedTile t = fused_peek<SC::NPLOG>(ldc, fwd, lag, tpp_log, batch);
-                        if (t.kind < 0)
-                            more = false;
-                        else
+                        const bool second = fwd ? (t.kind == 1) : (t.kind == 0);
+                        bool ok = true;
+                        long long p0 = 0, p1 = 0; // polynomials this tile depends on: [p0, p1)
+                        unsigned need = 0;
+                        if (second)
                         {
-                            const bool second = fwd ? (t.kind == 1) : (t.kind == 0);
-                            bool ok = true;
-                            long long p0 = 0, p1 = 0; // polynomials this tile depends on: [p0, p1)
-                            unsigned need = 0;
+                            if (t.kind == 1)
+                            {
+                                p0 = t.id << SC::NPLOG;
+                                p1 = p0 + (1 << SC::NPLOG);
+                                if (p1 > batch) p1 = batch;
+                                need = 1u << tpp_log;
+                            }
+                            else
+                            {
+                                p0 = t.id >> tpp_log;
+                                p1 = p0 + 1;
+                                need = (unsigned) f.nranges;
+                            }
+                            for (long long p = p0; p < p1 && ok; p++) ok = (ld_acquire(f.counters + p) & 0xffffu) == need;
+                        }
+                        if (ok)
+                        {
+                            if (second) fence_proxy_async_all(); // the bulk read below is ordered after the acquire loads
+                            const int b = t_load % NB;
+                            const uint32_t bar = smem_u32(&ctl->full[b]);
+                            const uint32_t dst = smem_u32(bufs + b * TILE);
+                            ctl->kind[b] = t.kind; // (released by the arrive below, acquired by the consumers' wait)
+                            mbar_expect_tx(bar, TILE);
+                            const CUtensorMap* mp = second ? &mapB : &mapA_in;
+                            if (t.kind == 0)
+                            {
+                                const long long poly = t.id >> tpp_log, cc = t.id & ((1LL << tpp_log) - 1);
+                                tma_load_3d(dst, mp, 0, (int) (cc << (SS::C - SS::CB)), (int) (poly << (n - f.s.lo)), bar);
+                            }
+                            else
+                                tma_load_3d(dst, mp, 0, range << (SC::KC - SC::CB), (int) (t.id << SC::NPLOG), bar);
                             if (second)
                             {
-                                if (t.kind == 1)
+                                // self-cleaning counters: the last observer of a polynomial zeroes its word
+                                const unsigned observers = t.kind == 1 ? (unsigned) f.nranges : (1u << tpp_log);
+                                for (long long p = p0; p < p1; p++)
                                 {
-                                    p0 = t.id << SC::NPLOG;
-                                    p1 = p0 + (1 << SC::NPLOG);
-                                    if (p1 > batch) p1 = batch;
-                                    need = 1u << tpp_log;
+                                    const unsigned old = atomicAdd(f.counters + p, 0x10000u);
+                                    if ((old >> 16) == observers - 1) atomicExch(f.counters + p, 0u);
                                 }
-                                else
-                                {
-                                    p0 = t.id >> tpp_log;
-                                    p1 = p0 + 1;
-                                    need = (unsigned) f.nranges;
-                                }
-                                for (long long p = p0; p < p1 && ok; p++) ok = (ld_acquire(f.counters + p) & 0xffffu) == need;
                             }
-                            if (ok)
-                            {
-                                if (second) fence_proxy_async_all(); // the bulk read below is ordered after the acquire loads
-                                const int b = (int) (t_load & 1);
-                                const uint32_t bar = smem_u32(&bars[b]);
-                                const uint32_t dst = smem_u32(bufs + b * TILE);
-                                mbar_expect_tx(bar, TILE);
-                                const CUtensorMap* mp = second ? &mapB : &mapA_in;
-                                if (t.kind == 0)
-                                {
-                                    const long long poly = t.id >> tpp_log, cc = t.id & ((1LL << tpp_log) - 1);
-                                    tma_load_3d(dst, mp, 0, (int) (cc << (SS::C - SS::CB)), (int) (poly << (n - f.s.lo)), bar);
-                                }
-                                else
-                                    tma_load_3d(dst, mp, 0, range << (SC::KC - SC::CB), (int) (t.id << SC::NPLOG), bar);
-                                if (second)
-                                {
-                                    // self-cleaning counters: the last observer of a polynomial zeroes its word
-                                    const unsigned observers = t.kind == 1 ? (unsigned) f.nranges : (1u << tpp_log);
-                                    for (long long p = p0; p < p1; p++)
-                                    {
-                                        const unsigned old = atomicAdd(f.counters + p, 0x10000u);
-                                        if ((old >> 16) == observers - 1) atomicExch(f.counters + p, 0u);
-                                    }
-                                }
-                                slot[b] = t;
-                                fused_advance(ldc, t);
-                                t_load++;
-                                progressed = true;
-                            }
+                            slot[b] = t;
+                            fused_advance(ldc, t);
+                            t_load++;
+                            progressed = true;
                         }
                     }
-                    // ---- (3) signal the first-pass tile stored above: its polynomials advance once the bulk store is COMPLETE
-                    //          (not merely read); the next load is already in flight while this waits
-                    if (pend.kind >= 0)
+                    // ---- (3) signal first-pass tiles: their polynomials advance once the bulk store is COMPLETE (not merely
+                    //          read).  Only when there is nothing else to do, or the queue runs full -- the wait blocks.
+                    if (pq_n > 0 && (!progressed || pq_n >= 3))
                     {
-                        bulk_wait0();
+                        const unsigned newer = commits - pq_seq[pq_head]; // groups committed after this tile's
+                        if (newer >= 2)
+                            asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
+                        else if (newer == 1)
+                            asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+                        else
+                            bulk_wait0();
                         fence_proxy_async_all();
-                        if (pend.kind == 0)
-                            red_release_add(f.counters + (pend.id >> tpp_log), 1u);
+                        const FusedTile t = pq[pq_head];
+                        if (t.kind == 0)
+                            red_release_add(f.counters + (t.id >> tpp_log), 1u);
                         else
                         {
-                            long long p0 = pend.id << SC::NPLOG, p1 = p0 + (1 << SC::NPLOG);
+                            long long p0 = t.id << SC::NPLOG, p1 = p0 + (1 << SC::NPLOG);
                             if (p1 > batch) p1 = batch;
                             for (long long p = p0; p < p1; p++) red_release_add(f.counters + p, 1u);
                         }
-                        pend.kind = -1;
+                        pq_head = (pq_head + 1) & 3;
+                        pq_n--;
                         progressed = true;
                     }
                     if (!progressed) __nanosleep(32);
@@ -300,36 +340,35 @@ namespace gpuntt_b200
         }
         else
         {
-            // =================== consumer warps ===================
+            // =================== consumer groups ===================
+            const int g = tid / kConsumers, ctid = tid % kConsumers;
             typename ModOf<SS>::type MS(f.s.p);
             typename ModOf<SC>::type MC(f.c.p);
             const Twiddle<T> ninv{f.s.ninv_w, f.s.ninv_wq};
             const bool triv = !SS::INV && !f.s.plus && f.s.first && (f.s.lo + SS::D == n) && f.s.table[0] == T(1);
-            if (doS) build_twiddles<SS>(twS, f.s.table, 0, n, f.s.n_tw, f.s.lo, f.s.plus, f.s.p, f.s.mu, f.s.pbits, tid, kConsumers);
-            if (doC) build_twiddles<SC>(twC, f.c.table, range, n, f.c.n_tw, 0, f.c.plus, f.c.p, f.c.mu, f.c.pbits, tid, kConsumers);
-            consumer_sync();
-            FusedCursor cc = cur;
-            unsigned t_idx = 0;
-            for (;;)
+            if (doS) build_twiddles<SS>(twS, f.s.table, 0, n, f.s.n_tw, f.s.lo, f.s.plus, f.s.p, f.s.mu, f.s.pbits, tid, kFusedConsumers);
+            if (doC) build_twiddles<SC>(twC, f.c.table, range, n, f.c.n_tw, 0, f.c.plus, f.c.p, f.c.mu, f.c.pbits, tid, kFusedConsumers);
+            asm volatile("bar.sync 3, %0;" ::"n"(kFusedConsumers) : "memory");
+            for (int it = 0;; it++)
             {
-                const FusedTile t = fused_peek<SC::NPLOG>(cc, fwd, lag, tpp_log, batch);
-                if (t.kind < 0) break;
-                fused_advance(cc, t);
-                const int b = (int) (t_idx & 1);
+                if (ctid == 0) ctl->bcast[g][it & 1] = atomicAdd(&ctl->next_t, 1);
+                consumer_sync(1 + g);
+                const int t = ctl->bcast[g][it & 1];
+                if (t >= total) break;
+                const int b = t % NB;
                 unsigned char* buf = bufs + b * TILE;
-                mbar_wait(smem_u32(&bars[b]), (t_idx >> 1) & 1); // tile landed
-                if (t.kind == 0)
-                    tile_rounds<SS, false>(buf, twS, twS + SS::TW1, twS + SS::TW1 + SS::TW2, MS, tid, ninv, nullptr, f.s, triv);
+                mbar_wait(smem_u32(&ctl->full[b]), (unsigned) (t / NB) & 1u); // tile landed
+                if (ctl->kind[b] == 0)
+                    tile_rounds<SS, false>(buf, twS, twS + SS::TW1, twS + SS::TW1 + SS::TW2, MS, ctid, ninv, nullptr, f.s, triv, 1 + g);
                 else
-                    tile_rounds<SC, false>(buf, twC, twC + SC::TW1, twC + SC::TW1 + SC::TW2, MC, tid, ninv, nullptr, f.c, false);
+                    tile_rounds<SC, false>(buf, twC, twC + SC::TW1, twC + SC::TW1 + SC::TW2, MC, ctid, ninv, nullptr, f.c, false, 1 + g);
                 fence_async(); // make the generic-proxy writes visible to the bulk store
-                mbar_arrive(smem_u32(&bars[2 + b]));
-                t_idx++;
+                mbar_arrive(smem_u32(&ctl->done[b]));
             }
         }
     }
 
-    static std::atomic<int> g_fused_lag_steps{2};
+    static std::atomic<int> g_fused_lag_steps{6};
     void fused_set_lag_steps(int v) { g_fused_lag_steps.store(v < 0 ? 0 : v); }
 
     // in / out / table / p / ninv / mu / pbits / n / plus / batch / in_bound of `a` are filled in; lo_s = row stride (log2) of the
@@ -343,7 +382,7 @@ namespace gpuntt_b200
         constexpr int kMaxDev = 64;
         static std::atomic<int> cached_bps[kMaxDev];
         static std::atomic<int> cached_sms[kMaxDev];
-        constexpr int SMEM = 2 * SS::TILE_SMEM + SS::TW_SMEM + SC::TW_SMEM + 128 + 1024;
+        constexpr int SMEM = FusedSmem<SS, SC>::BYTES;
         auto kern = fused2_kernel<SS, SC>;
         int dev = 0;
         cudaError_t e = cudaGetDevice(&dev);
@@ -356,10 +395,10 @@ namespace gpuntt_b200
             if (e != cudaSuccess) return e;
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             int b = 0;
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kFastThreads, SMEM);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kFusedThreads, SMEM);
             if (e != cudaSuccess) return e;
             if (b < 1) return cudaErrorNotSupported; // (the flag protocol needs every CTA resident)
-            bps = b;
+            bps = 1; // one CTA per SM by design
             cached_sms[dev].store(sms, std::memory_order_release);
             cached_bps[dev].store(bps, std::memory_order_release);
         }
@@ -436,7 +475,7 @@ namespace gpuntt_b200
             if (!make_map<SS>(&mB, a.out, n, lo_s, batch)) return cudaErrorNotSupported;
         }
         prof_begin(1, st);
-        kern<<<(unsigned) grid, kFastThreads, SMEM, st>>>(f, mA_in, mA_out, mB);
+        kern<<<(unsigned) grid, kFusedThreads, SMEM, st>>>(f, mA_in, mA_out, mB);
         prof_end(st);
         return cudaGetLastError();
     }

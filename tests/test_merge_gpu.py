@@ -295,7 +295,7 @@ def test_host_buffer_entry_point():
                        x.ctypes.data, out.ctypes.data, None, P.modulus, 0, None, None, None)
     capi.check(capi.lib().gpuntt_b200_merge_ntt_host(C.byref(d), P.fwd_br.ctypes.data, P.fwd_br.size))
     assert (out == O.merge_ntt(x, P)).all()
-    assert capi.lib().gpuntt_b200_last_launch_count() >= 2
+    assert capi.lib().gpuntt_b200_last_launch_count() >= 1
 
 
 def test_host_buffer_entry_point_chunked_pipeline():

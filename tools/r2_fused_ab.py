@@ -20,7 +20,7 @@ from gpu_ntt_b200.params import NTTParameters, X_N_minus  # noqa: E402
 from perf_configs import dev, peak, time_ms  # noqa: E402
 
 
-def case(logn, batch, bits, iters, inverse=False, fused=1, lag=2):
+def case(logn, batch, bits, iters, inverse=False, fused=1, lag=6):
     P = NTTParameters(logn, X_N_minus, bits)
     p = P.modulus
     tab = dev(P.gpu_root_of_unity_table_generator(P.inverse_root_of_unity_table if inverse else P.forward_root_of_unity_table), bits)
@@ -37,7 +37,7 @@ def case(logn, batch, bits, iters, inverse=False, fused=1, lag=2):
     ms = time_ms(fn, iters)
     launches = capi.lib().gpuntt_b200_last_launch_count()
     capi.tune(capi.TUNE_FUSED_PASSES, 1)
-    capi.tune(capi.TUNE_FUSED_LAG, 2)
+    capi.tune(capi.TUNE_FUSED_LAG, 6)
     gbs = 2 * (1 << logn) * (bits // 8) * batch / (ms * 1e-3) / 1e9
     print(json.dumps({"logn": logn, "batch": batch, "bits": bits, "op": "inv" if inverse else "fwd", "fused": fused, "lag": lag,
                       "launches": launches, "ms": round(ms, 4), "us": round(ms * 1e3, 2), "ntt_per_s": round(batch / (ms * 1e-3), 1),
@@ -57,7 +57,7 @@ def main():
         case(16, 1024, 64, it, inverse=True, fused=fused)
         case(14, 4096, 32, it, fused=fused)
         case(14, 4096, 32, it, inverse=True, fused=fused)
-    for lag in (0, 1, 3, 4, 8):
+    for lag in (1, 2, 3, 4, 8, 12):
         case(16, 1024, 64, it, lag=lag)
         case(14, 4096, 32, it, lag=lag)
     if args.quick:
