@@ -223,12 +223,19 @@ namespace gpuntt_b200
     // WMUL (forward strided passes only): after the stages every element is multiplied by the (w, w') pair at its
     // offset inside the polynomial -- the 4-step twiddle-matrix product (w_pairs: see fast_fourstep_columns) -- and
     // canonicalised.  wtile points at the pair of the tile's first element, lo is the pass's row stride (log2).
-    template <typename S, int R, int LB, int G, bool FINAL, bool TRIV = false, bool WMUL = false>
+    // TS (forward strided passes, the round on the LOWEST row bits): transposed store.  Every thread keeps its results in
+    // registers, the consumer group synchronises (all loads of the tile are done), and the results are written in the
+    // layout of the transposing TMA store box {16 rows, 2^C columns, 2^(D-4) row blocks}: the 128-byte line
+    // (row >> 4) * 2^C + column holds rows (row & ~15) .. +15 of that column, 16-byte chunks XOR (line & 7) like every
+    // SWIZZLE_128B tile -- so a thread's consecutive rows are one vector store per pair and the eight lanes of a quarter
+    // warp (eight columns) hit eight different bank groups.  This is how the 4-step column phase writes its output as the
+    // n2 x n1 matrix without a transpose kernel.
+    template <typename S, int R, int LB, int G, bool FINAL, bool TRIV = false, bool WMUL = false, bool TS = false>
     __device__ __forceinline__ void fast_round(unsigned char* buf, const Twiddle<typename S::T>* __restrict__ tws,
                                                const typename ModOf<S>::type& M, int ctid,
                                                const Twiddle<typename S::T>& ninv,
                                                const Twiddle<typename S::T>* __restrict__ wtile = nullptr, int lo = 0, int in_bound = 1,
-                                               bool w_lazy = false)
+                                               bool w_lazy = false, int bar = 1)
     {
         using T = typename S::T;
         constexpr int E = 1 << R;
@@ -241,8 +248,12 @@ namespace gpuntt_b200
         // CB <= LB < CB + 3: bits 7..9 of b come from a (l_base has zeros there) -> XOR constant per a.
         // LB == 0: the item is one or more whole 128-byte rows; chunks are 16-byte vectors.
         static_assert(LB == 0 || LB >= S::CB, "round must start at bit 0 or on a row boundary");
-#pragma unroll 1
-        for (int item = ctid; item < ITEMS; item += kConsumers)
+        constexpr int NI = TS ? (ITEMS / kConsumers) : 1;
+        static_assert(!TS || (S::STRIDED && !S::INV && LB == S::C && R >= 1 && S::D >= 5 && sizeof(T) == 8 && ITEMS % kConsumers == 0),
+                      "transposed store: lowest round of a forward strided 64-bit pass");
+        T keep[NI][TS ? E : 1];
+#pragma unroll(TS ? NI : 1)
+        for (int item = ctid, ii = 0; item < ITEMS; item += kConsumers, ii++)
         {
             const int l_base = ((item >> LB) << (LB + R)) | (item & ((1 << LB) - 1));
             const int group = (l_base >> (LB + R)) & (G - 1);
@@ -406,7 +417,12 @@ namespace gpuntt_b200
                 }
             }
 
-            if constexpr (LB == 0)
+            if constexpr (TS)
+            {
+#pragma unroll
+                for (int a = 0; a < E; a++) keep[ii][a] = e[a];
+            }
+            else if constexpr (LB == 0)
             {
 #pragma unroll
                 for (int a = 0; a < E; a += VN)
@@ -421,6 +437,25 @@ namespace gpuntt_b200
             {
 #pragma unroll
                 for (int a = 0; a < E; a++) *reinterpret_cast<T*>(addr(a)) = e[a];
+            }
+        }
+        if constexpr (TS)
+        {
+            consumer_sync(bar); // every thread of the group has read its elements: the buffer can take the new layout
+#pragma unroll
+            for (int ii = 0; ii < NI; ii++)
+            {
+                const int item = ctid + ii * kConsumers;
+                const int l_base = ((item >> LB) << (LB + R)) | (item & ((1 << LB) - 1));
+                const int col = l_base & ((1 << S::C) - 1), row0 = l_base >> S::C; // row0 has zeros in its low R bits
+#pragma unroll
+                for (int a = 0; a < E; a += 2)
+                {
+                    const int row = row0 | a;
+                    const int line = ((row >> 4) << S::C) + col;
+                    const int off = (line << 7) + (((((row & 15) >> 1) ^ (col & 7))) << 4);
+                    *reinterpret_cast<ulonglong2*>(buf + off) = make_ulonglong2(keep[ii][a], keep[ii][a + 1]);
+                }
             }
         }
     }
@@ -467,7 +502,7 @@ namespace gpuntt_b200
     // the transform (4-step row phase on the transposed layout) canonicalises as well.
     // 4-step twiddle-matrix product: forward = epilogue of the last round, inverse = prologue of the first executed
     // round; either way that is the low round when there are two.
-    template <typename S, bool WMUL, bool SFIN = false>
+    template <typename S, bool WMUL, bool SFIN = false, bool TS = false>
     __device__ __forceinline__ void tile_rounds(unsigned char* buf, const Twiddle<typename S::T>* tw1, const Twiddle<typename S::T>* tw2,
                                                 const Twiddle<typename S::T>* tw3, const typename ModOf<S>::type& M, int tid,
                                                 const Twiddle<typename S::T>& ninv, const Twiddle<typename S::T>* wtile,
@@ -481,20 +516,21 @@ namespace gpuntt_b200
 #else
             constexpr bool FIN1 = (SFIN || !S::STRIDED) && S::R2 == 0, FIN2 = (SFIN || !S::STRIDED) && S::R3 == 0;
 #endif
+            constexpr bool TS1 = TS && S::R2 == 0, TS2 = TS && S::R2 > 0;
             if constexpr (S::STRIDED && S::POL == 2 && S::G1 == 1)
             {
                 if (triv)
-                    fast_round<S, S::R1, S::LB1, S::G1, FIN1, true, W1>(buf, tw1, M, tid, ninv, wtile, a.lo,
-                                                                         a.in_bound > 1 ? a.in_bound : 1, a.w_lazy != 0);
+                    fast_round<S, S::R1, S::LB1, S::G1, FIN1, true, W1, TS1>(buf, tw1, M, tid, ninv, wtile, a.lo,
+                                                                              a.in_bound > 1 ? a.in_bound : 1, a.w_lazy != 0, bar);
                 else
-                    fast_round<S, S::R1, S::LB1, S::G1, FIN1, false, W1>(buf, tw1, M, tid, ninv, wtile, a.lo, 1, a.w_lazy != 0);
+                    fast_round<S, S::R1, S::LB1, S::G1, FIN1, false, W1, TS1>(buf, tw1, M, tid, ninv, wtile, a.lo, 1, a.w_lazy != 0, bar);
             }
             else
                 fast_round<S, S::R1, S::LB1, S::G1, FIN1>(buf, tw1, M, tid, ninv);
             if constexpr (S::R2 > 0)
             {
                 consumer_sync(bar);
-                fast_round<S, S::R2, S::LB2, S::G2, FIN2, false, W2>(buf, tw2, M, tid, ninv, wtile, a.lo, 1, a.w_lazy != 0);
+                fast_round<S, S::R2, S::LB2, S::G2, FIN2, false, W2, TS2>(buf, tw2, M, tid, ninv, wtile, a.lo, 1, a.w_lazy != 0, bar);
             }
             if constexpr (S::R3 > 0)
             {
@@ -546,7 +582,7 @@ namespace gpuntt_b200
         int pbits, mi;
     };
 
-    template <typename S, bool WMUL, bool RNS>
+    template <typename S, bool WMUL, bool RNS, bool SFIN = false, bool TS = false>
     __device__ __forceinline__ void fast_pass_body(const FastArgs<typename S::T>& a, const CUtensorMap& map_in, const CUtensorMap& map_out)
     {
         using T = typename S::T;
@@ -764,8 +800,11 @@ namespace gpuntt_b200
                             long long gp = RNS ? poly * a.mod_count + mslot : poly;
                             if constexpr (RNS)
                                 if (a.poly_order) gp = a.poly_order[gp];
-                            tma_store_3d(&map_out, 0, (int) (cc << (S::C - S::CB)),
-                                         (int) ((gp << (a.n - a.lo)) + ((long long) range << S::D)), src);
+                            if constexpr (TS) // transposing box {16 rows, 2^C columns, 2^(D-4) row blocks} of the n2 x n1 output matrix
+                                tma_store_3d(&map_out, 0, (int) ((gp << a.lo) + (cc << S::C)), 0, src);
+                            else
+                                tma_store_3d(&map_out, 0, (int) (cc << (S::C - S::CB)),
+                                             (int) ((gp << (a.n - a.lo)) + ((long long) range << S::D)), src);
                         }
                         else
                         {
@@ -831,7 +870,7 @@ namespace gpuntt_b200
                                 asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + (((long long) x << (LBW - S::C)) << a.lo)));
                         }
                     }
-                    tile_rounds<S, WMUL>(buf, tw1, tw2, tw3, M, tid, ninv, wtile, a, triv);
+                    tile_rounds<S, WMUL, SFIN, TS>(buf, tw1, tw2, tw3, M, tid, ninv, wtile, a, triv);
                     fence_async(); // make the generic-proxy writes visible to the bulk store
                     mbar_arrive(smem_u32(&bars[2 + b]));
                     if (b) uses1++; else uses0++;
@@ -846,12 +885,12 @@ namespace gpuntt_b200
         }
     }
 
-    template <typename S, bool WMUL = false, bool RNS = false>
+    template <typename S, bool WMUL = false, bool RNS = false, bool SFIN = false, bool TS = false>
     __global__ void __launch_bounds__(kFastThreads, (!S::INV && S::POL == 2) ? (S::STRIDED ? GPUNTT_FAST_P0_BLOCKS : GPUNTT_FAST_P1_BLOCKS) : 2)
         fast_pass_kernel(const FastArgs<typename S::T> a, const __grid_constant__ CUtensorMap map_in,
                          const __grid_constant__ CUtensorMap map_out)
     {
-        fast_pass_body<S, WMUL, RNS>(a, map_in, map_out);
+        fast_pass_body<S, WMUL, RNS, SFIN, TS>(a, map_in, map_out);
     }
 
     // RNS calls on 64-bit data: the moduli live on the device, so the choice between the lazy-policy body (SL) and the
@@ -957,9 +996,28 @@ namespace gpuntt_b200
         return r == CUDA_SUCCESS;
     }
 
+    // Output map of a transposing strided pass (fast_round TS): the pass reads the [rows = 2^D][2^lo] matrix of every
+    // polynomial (one range: lo + D == n) and writes its transpose, 2^lo rows of 2^D contiguous elements.  View
+    // {16 elements of a transposed row, every transposed row of every polynomial, 2^(D-4) blocks of 16 elements along
+    // that row}; box {16, 2^C, 2^(D-4)}.
+    template <typename S> static bool make_map_tstore(CUtensorMap* map, const void* base, int lo, int batch)
+    {
+        using T = typename S::T;
+        static_assert(sizeof(T) == 8 && S::STRIDED && S::D >= 5, "transposing store: 64-bit strided passes of 5..8 stages");
+        PFN_cuTensorMapEncodeTiled enc = get_encode();
+        if (!enc) return false;
+        cuuint64_t gdim[3] = {16, (cuuint64_t) batch << lo, 1ull << (S::D - 4)};
+        cuuint64_t gstride[2] = {(cuuint64_t) sizeof(T) << S::D, 128};
+        cuuint32_t box[3] = {16, 1u << S::C, 1u << (S::D - 4)}, estr[3] = {1, 1, 1};
+        CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        return r == CUDA_SUCCESS;
+    }
+
     // returns cudaErrorNotSupported when the tensor maps cannot be built (caller falls back)
     // SX: exact-policy twin of S for the 64-bit RNS calls (fast_pass_dual_kernel picks on the device)
-    template <typename S, bool WMUL = false, bool RNS = false, typename SX = void>
+    // SFIN: forward strided pass that ends the transform (canonical outputs); TS: transposing store (in != out)
+    template <typename S, bool WMUL = false, bool RNS = false, typename SX = void, bool SFIN = false, bool TS = false>
     static cudaError_t launch_fast(const FastArgs<typename S::T>& args, cudaStream_t st)
     {
         // per device (the shared-memory opt-in is a per-device function attribute); a race between first callers only
@@ -970,7 +1028,7 @@ namespace gpuntt_b200
         using KernT = void (*)(const FastArgs<typename S::T>, const CUtensorMap, const CUtensorMap);
         KernT kern;
         if constexpr (std::is_void<SX>::value)
-            kern = fast_pass_kernel<S, WMUL, RNS>;
+            kern = fast_pass_kernel<S, WMUL, RNS, SFIN, TS>;
         else
             kern = fast_pass_dual_kernel<S, SX>;
         int dev = 0;
@@ -1001,7 +1059,12 @@ namespace gpuntt_b200
         bool opb = false;
         if constexpr (RNS) opb = args.poly_order != nullptr;
         if (!make_map<S>(&map_in, args.in, args.n, args.lo, args.batch, mc, opb)) return cudaErrorNotSupported;
-        if (args.in == args.out)
+        if constexpr (TS)
+        {
+            if (args.in == args.out || args.lo + S::D != args.n) return cudaErrorNotSupported;
+            if (!make_map_tstore<S>(&map_out, args.out, args.lo, args.batch)) return cudaErrorNotSupported;
+        }
+        else if (args.in == args.out)
             map_out = map_in;
         else if (!make_map<S>(&map_out, args.out, args.n, args.lo, args.batch, mc, opb))
             return cudaErrorNotSupported;

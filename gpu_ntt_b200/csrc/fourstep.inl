@@ -164,6 +164,33 @@ template <typename T> static int fourstep_execute_t(const gpuntt_b200_4step_desc
 
     int rc = GPUNTT_B200_OK;
     cudaError_t e = cudaSuccess;
+    if constexpr (sizeof(T) == 8)
+    {
+        // Fused contract, forward, on the tuned kernels without any transpose: the column pass stores the n2 x n1 matrix
+        // (transposing TMA store), the row transforms run along it as strided passes and land in the final order.
+        if (!inv && fused && !rns && !g_force_generic.load() && g_fourstep_transposed.load() && fast_fourstep_rows_t_supported(lg1, lg2) &&
+            (uint64_t) d->modulus_value >= kF60ModulusMin && (uint64_t) d->modulus_value < kF60ModulusLimit)
+        {
+            void* pairs = nullptr;
+            cudaError_t we = get_workspace(d->stream, 6, (size_t) N * sizeof(Twiddle<T>), &pairs);
+            if (we != cudaSuccess) return cuda_fail(we, "4-step twiddle-pair workspace allocation");
+            int launched = 0;
+            we = fast_fourstep_columns(reinterpret_cast<const uint64_t*>(in), reinterpret_cast<uint64_t*>(ws),
+                                       reinterpret_cast<const uint64_t*>(d->n1_table), reinterpret_cast<const uint64_t*>(d->w_table), pairs,
+                                       (uint64_t) d->modulus_value, n, lg1, lg2, batch, st, &launched, prof_begin, prof_end, 1, 1);
+            if (we != cudaSuccess) return cuda_fail(we, "fast 4-step transposing column pass launch");
+            if (launched > 0)
+            {
+                int rl = 0;
+                we = fast_fourstep_rows_t(reinterpret_cast<const uint64_t*>(ws), reinterpret_cast<uint64_t*>(out),
+                                          reinterpret_cast<const uint64_t*>(d->n2_table), (uint64_t) d->modulus_value, n, lg1, lg2, batch, 2, st,
+                                          &rl, prof_begin, prof_end);
+                if (we != cudaSuccess) return cuda_fail(we, "fast 4-step row passes launch");
+                if (rl == 0) return fail(GPUNTT_B200_ERR_CUDA, "4-step row phase: tuned kernels declined after a transposing column phase");
+                return GPUNTT_B200_OK;
+            }
+        }
+    }
     if (!inv)
     {
         // natural-order matrix M (n1 x n2) in `src`; the reference contract hands us M^T

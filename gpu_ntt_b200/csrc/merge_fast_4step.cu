@@ -25,10 +25,12 @@ namespace gpuntt_b200
     // entries), canonical outputs.  Single modulus, 64-bit, F60 moduli; *launched = 0 when not covered.
     cudaError_t fast_fourstep_columns(const uint64_t* in, uint64_t* out, const uint64_t* n1_table, const uint64_t* w_table,
                                       void* w_pairs_ws, uint64_t p, int n_power, int lg1, int lg2, int batch, cudaStream_t st,
-                                      int* launched, void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t), int w_lazy)
+                                      int* launched, void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t), int w_lazy,
+                                      int transposed)
     {
         using T = uint64_t;
         *launched = 0;
+        if (transposed && in == out) return cudaSuccess;
         if (lg1 < 5 || lg1 > 8 || lg2 < 12 - lg1 || n_power != lg1 + lg2) return cudaSuccess;
         if (((long long) batch << lg1) >= (1LL << 31)) return cudaSuccess;
         if (!(p >= kF60ModulusMin && p < kF60ModulusLimit)) return cudaSuccess;
@@ -60,17 +62,114 @@ namespace gpuntt_b200
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         prof_begin(1, st);
-        switch (lg1)
-        {
-            case 5: e = launch_fast<Shape<T, false, 2, true, 3, 2, 12, 0>, true>(a, st); break;
-            case 6: e = launch_fast<Shape<T, false, 2, true, 3, 3, 12, 0>, true>(a, st); break;
-            case 7: e = launch_fast<Shape<T, false, 2, true, 4, 3, 12, 0>, true>(a, st); break;
-            default: e = launch_fast<Shape<T, false, 2, true, 4, 4, 12, 0>, true>(a, st); break;
-        }
+        if (transposed) // the pass writes the n2 x n1 matrix (every column transform becomes a contiguous row)
+            switch (lg1)
+            {
+                case 5: e = launch_fast<Shape<T, false, 2, true, 3, 2, 12, 0>, true, false, void, false, true>(a, st); break;
+                case 6: e = launch_fast<Shape<T, false, 2, true, 3, 3, 12, 0>, true, false, void, false, true>(a, st); break;
+                case 7: e = launch_fast<Shape<T, false, 2, true, 4, 3, 12, 0>, true, false, void, false, true>(a, st); break;
+                default: e = launch_fast<Shape<T, false, 2, true, 4, 4, 12, 0>, true, false, void, false, true>(a, st); break;
+            }
+        else
+            switch (lg1)
+            {
+                case 5: e = launch_fast<Shape<T, false, 2, true, 3, 2, 12, 0>, true>(a, st); break;
+                case 6: e = launch_fast<Shape<T, false, 2, true, 3, 3, 12, 0>, true>(a, st); break;
+                case 7: e = launch_fast<Shape<T, false, 2, true, 4, 3, 12, 0>, true>(a, st); break;
+                default: e = launch_fast<Shape<T, false, 2, true, 4, 4, 12, 0>, true>(a, st); break;
+            }
         prof_end(st);
         if (e == cudaErrorNotSupported) return cudaSuccess; // (the pair table was written for nothing)
         if (e != cudaSuccess) return e;
         *launched = 2;
+        return cudaSuccess;
+    }
+
+    // Forward 4-step row phase on the TRANSPOSED layout: `buf` holds, per polynomial, the n2 x n1 matrix the transposing
+    // column pass wrote (row j = the n1 outputs of column transform j, already multiplied by W).  The size-n2 transforms
+    // run along j, i.e. over index bits [lg1, n): one or two strided passes with the n2 table, the last one canonical.
+    // Their output order IS the reference's final order (out[j' * n1 + i'], ntt_4step_cpu.cu:33-109 of the reference),
+    // so no transpose kernel runs anywhere.  in_bound: the column products are below in_bound * p.
+    // split: lg2 = da + db, db in {7, 8} (the low pass needs 2^(12 - db) <= n1 adjacent elements), da in {0, 4..8}.
+    bool fast_fourstep_rows_t_supported(int lg1, int lg2)
+    {
+        if (lg1 < 5 || lg1 > 8) return false;
+        if (lg2 == 7 || lg2 == 8) return true;
+        const int db = lg2 - 8 >= 4 ? 8 : 7, da = lg2 - db;
+        return da >= 4 && da <= 8;
+    }
+    template <int D, bool SFIN> static cudaError_t launch_rows_t(const FastArgs<uint64_t>& s, cudaStream_t st)
+    {
+        using T = uint64_t;
+        if constexpr (D == 4) return launch_fast<Shape<T, false, 2, true, 4, 0, 12, 0>, false, false, void, SFIN>(s, st);
+        if constexpr (D == 5) return launch_fast<Shape<T, false, 2, true, 3, 2, 12, 0>, false, false, void, SFIN>(s, st);
+        if constexpr (D == 6) return launch_fast<Shape<T, false, 2, true, 3, 3, 12, 0>, false, false, void, SFIN>(s, st);
+        if constexpr (D == 7) return launch_fast<Shape<T, false, 2, true, 4, 3, 12, 0>, false, false, void, SFIN>(s, st);
+        return launch_fast<Shape<T, false, 2, true, 4, 4, 12, 0>, false, false, void, SFIN>(s, st);
+    }
+    cudaError_t fast_fourstep_rows_t(const uint64_t* buf, uint64_t* out, const uint64_t* n2_table, uint64_t p, int n_power, int lg1, int lg2,
+                                     int batch, int in_bound, cudaStream_t st, int* launched, void (*prof_begin)(int, cudaStream_t),
+                                     void (*prof_end)(cudaStream_t))
+    {
+        using T = uint64_t;
+        *launched = 0;
+        if (!fast_fourstep_rows_t_supported(lg1, lg2) || n_power != lg1 + lg2) return cudaSuccess;
+        if (!(p >= kF60ModulusMin && p < kF60ModulusLimit)) return cudaSuccess;
+        if (((long long) batch << lg2) >= (1LL << 31)) return cudaSuccess;
+        if ((reinterpret_cast<uintptr_t>(buf) | reinterpret_cast<uintptr_t>(out)) & 15) return cudaSuccess;
+        FastArgs<T> a{};
+        a.table = n2_table;
+        a.p = p;
+        a.pbits = 64 - __builtin_clzll((unsigned long long) p);
+        {
+            const unsigned __int128 m = (((unsigned __int128) 1) << (63 + a.pbits)) / (unsigned __int128) p;
+            a.mu = (m >> 64) ? ~0ull : (uint64_t) m;
+        }
+        a.n = n_power;
+        a.plus = 0;
+        a.batch = batch;
+        const int db = lg2 <= 8 ? lg2 : (lg2 - 8 >= 4 ? 8 : 7), da = lg2 - db;
+        cudaError_t e = cudaSuccess;
+        int kind = 2;
+        if (da > 0)
+        {
+            FastArgs<T> s = a;
+            s.in = buf;
+            s.out = out;
+            s.lo = lg1 + db;
+            s.first = 1; // opens the size-n2 transforms: twiddle-1 butterflies without a multiply
+            s.last = 0;
+            s.in_bound = in_bound;
+            s.work = (long long) batch << (s.lo - (12 - da));
+            s.rr = s.lo > 10 ? 1 : 0;
+            prof_begin(kind++, st);
+            switch (da)
+            {
+                case 4: e = launch_rows_t<4, false>(s, st); break;
+                case 5: e = launch_rows_t<5, false>(s, st); break;
+                case 6: e = launch_rows_t<6, false>(s, st); break;
+                case 7: e = launch_rows_t<7, false>(s, st); break;
+                default: e = launch_rows_t<8, false>(s, st); break;
+            }
+            prof_end(st);
+            if (e != cudaSuccess) return e;
+        }
+        {
+            FastArgs<T> s = a;
+            s.in = da > 0 ? out : buf;
+            s.out = out;
+            s.lo = lg1;
+            s.first = da > 0 ? 0 : 1;
+            s.last = 1;
+            s.in_bound = da > 0 ? 1 : in_bound;
+            s.work = ((long long) batch << (lg1 - (12 - db))) << da; // 2^da twiddle ranges
+            s.rr = 0;
+            prof_begin(kind++, st);
+            e = db == 7 ? launch_rows_t<7, true>(s, st) : launch_rows_t<8, true>(s, st);
+            prof_end(st);
+            if (e != cudaSuccess) return e;
+        }
+        *launched = kind - 2;
         return cudaSuccess;
     }
 

@@ -18,8 +18,9 @@
 // depends on tiles of strictly smaller time.  A tile that has been loaded is always computed, stored and signalled:
 // the producer thread polls "dependency satisfied?" and "consumers done?" in one loop and never spins on a dependency
 // while a finished tile waits for its store.  The grid never exceeds the number of co-resident CTAs.
-// The counters are self-cleaning (the last second-pass tile that observes a polynomial resets its word), so the
-// workspace is all-zero between calls and no memset is enqueued.
+// The counters clean up after themselves: every CTA takes a ticket when it is done and the last one zeroes the words
+// the call used, so the workspace is all-zero between calls, no memset is enqueued, and a captured graph can be
+// replayed any number of times.
 #include "fast_kernels.cuh"
 
 namespace gpuntt_b200
@@ -28,7 +29,7 @@ namespace gpuntt_b200
     template <typename T> struct FusedArgs
     {
         FastArgs<T> s, c;     // the strided pass / the contiguous pass (in, out, work, rr, cta_per_seg unused)
-        unsigned* counters;   // one word per polynomial: low 16 bits = first-pass tiles stored, high 16 = second-pass observers
+        unsigned* counters;   // one word per polynomial: first-pass tiles stored so far
         int fwd;              // 1: strided pass first (forward transform), 0: contiguous pass first (inverse)
         int lag;              // see above
         int g_str;            // CTAs [0, g_str) take the strided tiles, round robin
@@ -37,6 +38,7 @@ namespace gpuntt_b200
         int tpp_log;          // log2 strided tiles per polynomial
         int nranges;          // contiguous ranges per polynomial
         int ngroups;          // contiguous tile groups = ceil(batch / polynomials per tile)
+        long long ticket_off; // counters[ticket_off]: CTAs that have finished (the last one zeroes the counters)
     };
 
     __device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity)
@@ -105,21 +107,24 @@ namespace gpuntt_b200
     }
 
     // One CTA per SM: two consumer groups of 8 warps (each takes the next tile of the CTA's merged order as soon as it is
-    // free, so short strided tiles and long contiguous tiles balance out), one producer thread, kFusedBufs tile buffers --
-    // loads run up to kFusedBufs tiles ahead of the arithmetic, which is what hides the dependency checks, the HBM latency
-    // of the first-pass tiles and the store-completion waits of the signalling (with two CTAs x two buffers per SM the
-    // consumers spent a third of their time waiting for tiles: profiles/r2_fused_v1_ncu_summary.txt).
+    // free, so short strided tiles and long contiguous tiles balance out), a LOADER thread and a STORER thread in warps of
+    // their own, kFusedBufs tile buffers.  Loads run up to kFusedBufs tiles ahead of the arithmetic.  The loader blocks on
+    // dependencies, the storer on finished tiles and on the completion of first-pass stores (which it then signals) --
+    // neither ever waits for the other except through the free[] barriers of the buffers, so a finished tile is always
+    // stored and signalled.  (A single producer thread doing all of this serially was the bottleneck of the first two
+    // versions: the consumers spent 32 % / 55 % of their time waiting for tiles, profiles/r2_fused_v1_ncu_summary.txt.)
     constexpr int kFusedGroups = 2;
     constexpr int kFusedConsumers = kFusedGroups * kConsumers;
-    constexpr int kFusedThreads = kFusedConsumers + 32;
+    constexpr int kFusedThreads = kFusedConsumers + 64;
     constexpr int kFusedBufs = 5;
 
     struct FusedCtl
     {
-        uint64_t full[kFusedBufs], done[kFusedBufs];
-        int kind[kFusedBufs]; // what the producer loaded into each buffer
+        uint64_t full[kFusedBufs], done[kFusedBufs], free_[kFusedBufs];
+        int kind[kFusedBufs]; // what the loader put into each buffer
         int next_t;           // next tile index to be claimed by a consumer group
         int bcast[kFusedGroups][2];
+        int is_last;
     };
 
     template <typename SS, typename SC> struct FusedSmem
@@ -128,6 +133,13 @@ namespace gpuntt_b200
         static constexpr int TW = SS::TW_SMEM + SC::TW_SMEM;
         static constexpr int BYTES = kFusedBufs * TILE + TW + (int) sizeof(FusedCtl) + 1024; // + slack to align the tiles to 1 KiB
     };
+
+    __device__ __forceinline__ unsigned long long ld_acquire64(const unsigned* p)
+    {
+        unsigned long long v;
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        return v;
+    }
 
     template <typename SS, typename SC>
     __global__ void __launch_bounds__(kFusedThreads, 1)
@@ -189,6 +201,10 @@ namespace gpuntt_b200
         if (tid == kFusedConsumers)
         {
             tma_prefetch_desc(&mapA_in);
+            tma_prefetch_desc(&mapB);
+        }
+        if (tid == kFusedConsumers + 32)
+        {
             tma_prefetch_desc(&mapA_out);
             tma_prefetch_desc(&mapB);
         }
@@ -198,147 +214,106 @@ namespace gpuntt_b200
             {
                 mbar_init(smem_u32(&ctl->full[b]), 1);
                 mbar_init(smem_u32(&ctl->done[b]), kConsumers);
+                mbar_init(smem_u32(&ctl->free_[b]), 1);
             }
             ctl->next_t = 0;
+            ctl->is_last = 0;
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             fence_async();
         }
         __syncthreads();
 
-        if (tid >= kFusedConsumers)
+        if (tid == kFusedConsumers)
         {
-            // =================== producer: one thread runs the whole load / store / signal state machine ===================
-            if (tid == kFusedConsumers)
+            // =================== loader ===================
+            FusedCursor ldc = cur;
+            for (int t = 0; t < total; t++)
             {
-                FusedCursor ldc = cur;
-                FusedTile slot[NB];
-                FusedTile pq[4]; // first-pass tiles whose store has been issued but not yet signalled (FIFO)
-                unsigned pq_seq[4];
-                int pq_head = 0, pq_n = 0;
-                unsigned commits = 0; // bulk groups committed so far
-                int t_load = 0, t_store = 0;
-                while (t_store < total || pq_n > 0)
+                const FusedTile tl = fused_peek<SC::NPLOG>(ldc, fwd, lag, tpp_log, batch);
+                fused_advance(ldc, tl);
+                const bool second = fwd ? (tl.kind == 1) : (tl.kind == 0);
+                const int b = t % NB;
+                if (t >= NB) mbar_wait(smem_u32(&ctl->free_[b]), (unsigned) (t / NB - 1) & 1u); // the storer released this buffer
+                if (second)
                 {
-                    bool progressed = false;
-                    // ---- (1) store the next finished tile (in order)
-                    if (t_store < t_load)
+                    // every first-pass tile of the polynomials this tile touches has been stored
+                    if (tl.kind == 1)
                     {
-                        const int b = t_store % NB;
-                        if (mbar_test(smem_u32(&ctl->done[b]), (unsigned) (t_store / NB) & 1u))
+                        const long long p0 = tl.id << SC::NPLOG;
+                        long long p1 = p0 + (1 << SC::NPLOG);
+                        if (p1 > batch) p1 = batch;
+                        const unsigned need = 1u << tpp_log;
+                        if (SC::NPLOG == 1 && p1 - p0 == 2)
                         {
-                            const FusedTile t = slot[b];
-                            const bool second = fwd ? (t.kind == 1) : (t.kind == 0);
-                            const uint32_t src = smem_u32(bufs + b * TILE);
-                            const CUtensorMap* mp = second ? &mapB : &mapA_out;
-                            if (t.kind == 0)
-                            {
-                                const long long poly = t.id >> tpp_log, cc = t.id & ((1LL << tpp_log) - 1);
-                                tma_store_3d(mp, 0, (int) (cc << (SS::C - SS::CB)), (int) (poly << (n - f.s.lo)), src);
-                            }
-                            else
-                                tma_store_3d(mp, 0, range << (SC::KC - SC::CB), (int) (t.id << SC::NPLOG), src);
-                            bulk_commit();
-                            commits++;
-                            bulk_wait_read0(); // the buffer may be overwritten again
-                            if (!second)
-                            {
-                                const int e = (pq_head + pq_n) & 3;
-                                pq[e] = t;
-                                pq_seq[e] = commits;
-                                pq_n++;
-                            }
-                            t_store++;
-                            progressed = true;
+                            const unsigned long long want = ((unsigned long long) need << 32) | need;
+                            while (ld_acquire64(f.counters + p0) != want) __nanosleep(64);
                         }
-                    }
-                    // ---- (2) load the next tile of the merged order once a buffer is free and its dependencies are met
-                    if (t_load < total && t_load < t_store + NB)
-                    {
-                        const FusedTile t = fused_peek<SC::NPLOG>(ldc, fwd, lag, tpp_log, batch);
-                        const bool second = fwd ? (t.kind == 1) : (t.kind == 0);
-                        bool ok = true;
-                        long long p0 = 0, p1 = 0; // polynomials this tile depends on: [p0, p1)
-                        unsigned need = 0;
-                        if (second)
-                        {
-                            if (t.kind == 1)
-                            {
-                                p0 = t.id << SC::NPLOG;
-                                p1 = p0 + (1 << SC::NPLOG);
-                                if (p1 > batch) p1 = batch;
-                                need = 1u << tpp_log;
-                            }
-                            else
-                            {
-                                p0 = t.id >> tpp_log;
-                                p1 = p0 + 1;
-                                need = (unsigned) f.nranges;
-                            }
-                            for (long long p = p0; p < p1 && ok; p++) ok = (ld_acquire(f.counters + p) & 0xffffu) == need;
-                        }
-                        if (ok)
-                        {
-                            if (second) fence_proxy_async_all(); // the bulk read below is ordered after the acquire loads
-                            const int b = t_load % NB;
-                            const uint32_t bar = smem_u32(&ctl->full[b]);
-                            const uint32_t dst = smem_u32(bufs + b * TILE);
-                            ctl->kind[b] = t.kind; // (released by the arrive below, acquired by the consumers' wait)
-                            mbar_expect_tx(bar, TILE);
-                            const CUtensorMap* mp = second ? &mapB : &mapA_in;
-                            if (t.kind == 0)
-                            {
-                                const long long poly = t.id >> tpp_log, cc = t.id & ((1LL << tpp_log) - 1);
-                                tma_load_3d(dst, mp, 0, (int) (cc << (SS::C - SS::CB)), (int) (poly << (n - f.s.lo)), bar);
-                            }
-                            else
-                                tma_load_3d(dst, mp, 0, range << (SC::KC - SC::CB), (int) (t.id << SC::NPLOG), bar);
-                            if (second)
-                            {
-                                // self-cleaning counters: the last observer of a polynomial zeroes its word
-                                const unsigned observers = t.kind == 1 ? (unsigned) f.nranges : (1u << tpp_log);
-                                for (long long p = p0; p < p1; p++)
-                                {
-                                    const unsigned old = atomicAdd(f.counters + p, 0x10000u);
-                                    if ((old >> 16) == observers - 1) atomicExch(f.counters + p, 0u);
-                                }
-                            }
-                            slot[b] = t;
-                            fused_advance(ldc, t);
-                            t_load++;
-                            progressed = true;
-                        }
-                    }
-                    // ---- (3) signal first-pass tiles: their polynomials advance once the bulk store is COMPLETE (not merely
-                    //          read).  Only when there is nothing else to do, or the queue runs full -- the wait blocks.
-                    if (pq_n > 0 && (!progressed || pq_n >= 3))
-                    {
-                        const unsigned newer = commits - pq_seq[pq_head]; // groups committed after this tile's
-                        if (newer >= 2)
-                            asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
-                        else if (newer == 1)
-                            asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
                         else
-                            bulk_wait0();
-                        fence_proxy_async_all();
-                        const FusedTile t = pq[pq_head];
-                        if (t.kind == 0)
-                            red_release_add(f.counters + (t.id >> tpp_log), 1u);
-                        else
-                        {
-                            long long p0 = t.id << SC::NPLOG, p1 = p0 + (1 << SC::NPLOG);
-                            if (p1 > batch) p1 = batch;
-                            for (long long p = p0; p < p1; p++) red_release_add(f.counters + p, 1u);
-                        }
-                        pq_head = (pq_head + 1) & 3;
-                        pq_n--;
-                        progressed = true;
+                            for (long long p = p0; p < p1; p++)
+                                while (ld_acquire(f.counters + p) != need) __nanosleep(64);
                     }
-                    if (!progressed) __nanosleep(32);
+                    else
+                    {
+                        const unsigned* c = f.counters + (tl.id >> tpp_log);
+                        while (ld_acquire(c) != (unsigned) f.nranges) __nanosleep(64);
+                    }
+                    asm volatile("fence.proxy.async.global;" ::: "memory"); // the bulk read below is ordered after the acquire loads
                 }
-                bulk_wait0();
+                const uint32_t bar = smem_u32(&ctl->full[b]);
+                const uint32_t dst = smem_u32(bufs + b * TILE);
+                ctl->kind[b] = tl.kind; // (released by the arrive below, acquired by the consumers' wait)
+                mbar_expect_tx(bar, TILE);
+                const CUtensorMap* mp = second ? &mapB : &mapA_in;
+                if (tl.kind == 0)
+                {
+                    const long long poly = tl.id >> tpp_log, cc = tl.id & ((1LL << tpp_log) - 1);
+                    tma_load_3d(dst, mp, 0, (int) (cc << (SS::C - SS::CB)), (int) (poly << (n - f.s.lo)), bar);
+                }
+                else
+                    tma_load_3d(dst, mp, 0, range << (SC::KC - SC::CB), (int) (tl.id << SC::NPLOG), bar);
             }
         }
-        else
+        else if (tid == kFusedConsumers + 32)
+        {
+            // =================== storer ===================
+            FusedCursor stc = cur;
+            for (int t = 0; t < total; t++)
+            {
+                const FusedTile tl = fused_peek<SC::NPLOG>(stc, fwd, lag, tpp_log, batch);
+                fused_advance(stc, tl);
+                const bool second = fwd ? (tl.kind == 1) : (tl.kind == 0);
+                const int b = t % NB;
+                mbar_wait(smem_u32(&ctl->done[b]), (unsigned) (t / NB) & 1u); // a consumer group finished this tile
+                const uint32_t src = smem_u32(bufs + b * TILE);
+                const CUtensorMap* mp = second ? &mapB : &mapA_out;
+                if (tl.kind == 0)
+                {
+                    const long long poly = tl.id >> tpp_log, cc = tl.id & ((1LL << tpp_log) - 1);
+                    tma_store_3d(mp, 0, (int) (cc << (SS::C - SS::CB)), (int) (poly << (n - f.s.lo)), src);
+                }
+                else
+                    tma_store_3d(mp, 0, range << (SC::KC - SC::CB), (int) (tl.id << SC::NPLOG), src);
+                bulk_commit();
+                bulk_wait_read0();
+                mbar_arrive(smem_u32(&ctl->free_[b])); // the loader may refill the buffer
+                if (!second)
+                {
+                    // first-pass tile: its polynomials advance once the bulk store is COMPLETE (not merely read); wait_group
+                    // makes the writes visible to this thread, the release publishes them
+                    bulk_wait0();
+                    if (tl.kind == 0)
+                        red_release_add(f.counters + (tl.id >> tpp_log), 1u);
+                    else
+                    {
+                        long long p0 = tl.id << SC::NPLOG, p1 = p0 + (1 << SC::NPLOG);
+                        if (p1 > batch) p1 = batch;
+                        for (long long p = p0; p < p1; p++) red_release_add(f.counters + p, 1u);
+                    }
+                }
+            }
+            bulk_wait0();
+        }
+        else if (tid < kFusedConsumers)
         {
             // =================== consumer groups ===================
             const int g = tid / kConsumers, ctid = tid % kConsumers;
@@ -365,6 +340,20 @@ namespace gpuntt_b200
                 fence_async(); // make the generic-proxy writes visible to the bulk store
                 mbar_arrive(smem_u32(&ctl->done[b]));
             }
+        }
+        // ---- the counters go back to zero: the last CTA to finish (every other CTA has made all its observations) clears them
+        __syncthreads();
+        if (tid == 0)
+        {
+            __threadfence();
+            const unsigned old = atomicAdd(f.counters + f.ticket_off, 1u);
+            ctl->is_last = (old == gridDim.x - 1) ? 1 : 0;
+        }
+        __syncthreads();
+        if (ctl->is_last)
+        {
+            for (int i = tid; i < batch; i += kFusedThreads) f.counters[i] = 0u;
+            if (tid == 0) f.counters[f.ticket_off] = 0u;
         }
     }
 
@@ -423,6 +412,7 @@ namespace gpuntt_b200
         f.c.last = inverse ? 0 : 1;
         f.c.in_bound = 1;
         f.counters = counters;
+        f.ticket_off = batch; // (the workspace holds at least batch + 1 words)
         f.fwd = inverse ? 0 : 1;
         f.tpp_log = tpp_log;
         f.nranges = nranges;

@@ -622,7 +622,12 @@ namespace gpuntt_b200
                                       void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t));
     cudaError_t fast_fourstep_columns(const uint64_t* in, uint64_t* out, const uint64_t* n1_table, const uint64_t* w_table,
                                       void* w_pairs_ws, uint64_t p, int n_power, int lg1, int lg2, int batch, cudaStream_t st,
-                                      int* launched, void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t), int w_lazy);
+                                      int* launched, void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t), int w_lazy,
+                                      int transposed = 0);
+    bool fast_fourstep_rows_t_supported(int lg1, int lg2);
+    cudaError_t fast_fourstep_rows_t(const uint64_t* buf, uint64_t* out, const uint64_t* n2_table, uint64_t p, int n_power, int lg1, int lg2,
+                                     int batch, int in_bound, cudaStream_t st, int* launched, void (*prof_begin)(int, cudaStream_t),
+                                     void (*prof_end)(cudaStream_t));
     template <typename T>
     cudaError_t fast_merge(const T* in, T* out, const T* table, T p, T ninv, int n_power, int plus, bool inverse,
                            int batch, cudaStream_t st, int* launched, void (*prof_begin)(int, cudaStream_t),
@@ -681,12 +686,13 @@ namespace gpuntt_b200
     // (the kernels clean up after themselves), so they are zeroed once, when the buffer is allocated -- on the caller's
     // stream, i.e. before the first kernel that uses them.  nullptr: run the passes as separate launches.
     static std::atomic<int> g_fused_enabled{1};
+    static std::atomic<int> g_fourstep_transposed{1};
     static unsigned* fused_counters(void* stream, long long polys)
     {
         if (!g_fused_enabled.load() || polys <= 0) return nullptr;
         int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-        const size_t bytes = (size_t) polys * sizeof(unsigned);
+        const size_t bytes = ((size_t) polys + 1) * sizeof(unsigned); // + the ticket word
         std::lock_guard<std::mutex> lk(g_ws_mutex);
         Workspace& w = g_ws[std::make_tuple(dev, stream, 8)];
         if (w.bytes < bytes)
@@ -1211,6 +1217,7 @@ extern "C"
         {
             case GPUNTT_B200_TUNE_FUSED_PASSES: g_fused_enabled.store(value ? 1 : 0); break;
             case GPUNTT_B200_TUNE_FUSED_LAG: fused_set_lag_steps(value); break;
+            case GPUNTT_B200_TUNE_4STEP_TRANSPOSED: g_fourstep_transposed.store(value ? 1 : 0); break;
             default: break;
         }
     }

@@ -188,6 +188,10 @@ void gpuntt_b200_force_generic_path(int on);
  *   FUSED_LAG     how many tile times the second pass trails the first inside the fused kernel (default 2). */
 #define GPUNTT_B200_TUNE_FUSED_PASSES 1
 #define GPUNTT_B200_TUNE_FUSED_LAG 2
+/*   4STEP_TRANSPOSED  1 (default): the fused-contract forward 4-step writes its column phase as the n2 x n1 matrix
+ *                 (transposing TMA store) and runs the row transforms along that layout -- no transpose kernel;
+ *                 0: column pass, row Merge-NTT, transpose kernel. */
+#define GPUNTT_B200_TUNE_4STEP_TRANSPOSED 3
 void gpuntt_b200_tune(int knob, int value);
 
 /* Human-readable message for the last non-OK status returned on this thread. */

@@ -104,6 +104,8 @@ def ref():
         R.ref_4step_run.argtypes = [vp, C.c_int, C.c_int, _u64p, _u64p]
         R.ref_time_merge_ntt.restype = C.c_double
         R.ref_time_merge_ntt.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32]
+        R.ref_time_merge_ntt_io.restype = C.c_double
+        R.ref_time_merge_ntt_io.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u64p, _u64p]
         R.ref_hardware_threads.restype = C.c_int
         _ref = R
     return _ref

@@ -157,10 +157,43 @@ namespace
         auto t1 = std::chrono::steady_clock::now();
         return std::chrono::duration<double>(t1 - t0).count();
     }
+    // Same as time_merge on caller-provided polynomials, results kept: bench.py's cpu_baseline leg times this and then
+    // uses `out` to check the GPU's first step (the parity gate).
+    template <typename T>
+    static double time_merge_io(int logn, int poly, int count, int threads, const uint64_t* in, uint64_t* out)
+    {
+        NTTParameters<T> P(logn, rp<T>(poly));
+        size_t n = (size_t) 1 << logn;
+        std::vector<std::vector<T>> v(count, std::vector<T>(n));
+        for (int b = 0; b < count; b++)
+            for (size_t i = 0; i < n; i++) v[b][i] = (T) in[(size_t) b * n + i];
+        auto t0 = std::chrono::steady_clock::now();
+        std::vector<std::thread> th;
+        for (int t = 0; t < threads; t++)
+            th.emplace_back(
+                [&, t]()
+                {
+                    NTTCPU<T> cpu(P);
+                    for (int b = t; b < count; b += threads)
+                    {
+                        std::vector<T> r = cpu.ntt(v[b]);
+                        for (size_t i = 0; i < n; i++) out[(size_t) b * n + i] = r[i];
+                    }
+                });
+        for (auto& x : th) x.join();
+        auto t1 = std::chrono::steady_clock::now();
+        return std::chrono::duration<double>(t1 - t0).count();
+    }
 } // namespace
 
 extern "C"
 {
+    double ref_time_merge_ntt_io(int logn, int poly, int width, int count, int threads, const uint64_t* in, uint64_t* out)
+    {
+        if (width == 32) return time_merge_io<Data32>(logn, poly, count, threads, in, out);
+        return time_merge_io<Data64>(logn, poly, count, threads, in, out);
+    }
+
     // scal[10]; tables may be NULL. width = 32 or 64.
     void ref_merge_params(int logn, int poly, int width, uint64_t* scal, uint64_t* fwd,
                           uint64_t* inv, uint64_t* fwd_br, uint64_t* inv_br)

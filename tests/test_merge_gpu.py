@@ -310,7 +310,7 @@ def test_host_buffer_entry_point_chunked_pipeline():
                        x.ctypes.data, out.ctypes.data, None, P.modulus, 0, None, None, None)
     capi.check(capi.lib().gpuntt_b200_merge_ntt_host(C.byref(d), P.fwd_br.ctypes.data, P.fwd_br.size))
     assert (out == O.merge_ntt(x, P)).all()
-    assert capi.lib().gpuntt_b200_last_launch_count() == 6      # 3 chunks x 2 passes
+    assert capi.lib().gpuntt_b200_last_launch_count() in (3, 6)  # 3 chunks x (one fused launch | two passes)
 
 
 def test_streams_and_no_sync():
