@@ -11,8 +11,10 @@ call on the whole resident batch (512 MiB per GPU, > the 126 MB L2, so no L2 flu
 
 One JSON line on stdout (rank 0).  `value` = polynomials transformed per second with data resident
 in HBM (CUDA events, max over ranks); `e2e` = the same through gpuntt_b200_merge_ntt_host with
-pinned HOST buffers, H2D + D2H inside the timed region; `roofline` = algorithmic bytes per
-merge_pass_kernel launch / its live CUDA-event duration against the measured HBM copy peak;
+pinned HOST buffers, H2D + D2H inside the timed region; `roofline` = algorithmic bytes per launch of the
+dominant kernel (fused2_kernel / fast_pass_kernel) / its live CUDA-event duration against the measured HBM copy
+peak; `parity_gate` = the first step's output compared with the CPU reference before anything is timed (exit 3 on
+a mismatch);
 `cpu_baseline` = the reference's own NTTCPU<Data64>::ntt (oracle/_ref) on all host threads over a
 bounded sample of the same workload.
 """
@@ -189,6 +191,49 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- our arm
+def seed0_slice(capi, p, rank):
+    """Polynomials [BATCH * rank, BATCH * (rank + 1)) of the reference examples' seed-0 stream (SURVEY 8d:
+    std::mt19937 gen(0) + uniform_int_distribution<uint64_t>(0, p-1), polynomial-major), as a numpy [BATCH, N] array.
+    The distribution consumes a data-dependent number of draws, so rank r walks the stream from its start."""
+    import numpy as np
+    n = 1 << LOGN
+    out = np.empty((rank + 1) * BATCH * n, dtype=np.uint64)
+    capi.lib().gpuntt_b200_example_input(0, p, out.size, out.ctypes.data)
+    return out[rank * BATCH * n:].reshape(BATCH, n)
+
+
+def cpu_check_and_rate(x_host, y_gpu_host, count, threads=None):
+    """bench.py's cpu_baseline leg: the reference's NTTCPU<Data64>::ntt over the first `count` polynomials of THIS run's
+    input on all host threads -- timed (the baseline) and compared word for word with what the GPU produced for them in
+    its first step (the parity gate).  Returns (NTT/s, threads, kind, mismatching words)."""
+    import numpy as np
+    from oracle import oracle as O
+    R = O.ref()
+    xin = np.ascontiguousarray(x_host[:count])
+    want = np.empty_like(xin)
+    if R is not None:
+        threads = threads or R.ref_hardware_threads()
+        secs = R.ref_time_merge_ntt_io(LOGN, O.X_N_minus, BITS, count, threads, xin.reshape(-1), want.reshape(-1))
+        kind = "reference"
+    else:
+        import concurrent.futures as cf
+        threads = threads or os.cpu_count() or 1
+        P = O.merge_params(LOGN, O.X_N_minus, BITS)
+        L = O.lib()
+        want[:] = xin
+
+        def work(rows):
+            for r in rows:
+                L.ora_merge_ntt(want[r], LOGN, P.modulus, P.fwd, P.poly)
+        t0 = time.perf_counter()
+        with cf.ThreadPoolExecutor(threads) as ex:
+            list(ex.map(work, [list(range(i, count, threads)) for i in range(threads)]))
+        secs = time.perf_counter() - t0
+        kind = "port"
+    bad = int((want != y_gpu_host[:count]).sum())
+    return count / secs, threads, kind, bad
+
+
 def run_b200_arm(args):
     import numpy as np
     import torch
@@ -209,9 +254,13 @@ def run_b200_arm(args):
 
     P = NTTParameters(LOGN, X_N_minus, BITS)
     p = P.modulus
-    table = torch.from_numpy(P.gpu_root_of_unity_table_generator(P.forward_root_of_unity_table).view(np.int64)).cuda()
-    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
-    data = torch.randint(0, p, (BATCH, 1 << LOGN), dtype=torch.int64, device="cuda", generator=gen)
+    h_tab = P.gpu_root_of_unity_table_generator(P.forward_root_of_unity_table)
+    if args.corrupt_twiddle:                       # demonstration that the parity gate bites
+        h_tab = h_tab.copy()
+        h_tab[12345] ^= np.uint64(1)
+    table = torch.from_numpy(h_tab.view(np.int64)).cuda()
+    x_host = seed0_slice(capi, p, rank)            # SURVEY 8d input, this rank's batch slice
+    data = torch.from_numpy(x_host.view(np.int64)).cuda()
     stream = torch.cuda.current_stream()
 
     def step():
@@ -223,13 +272,41 @@ def run_b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- first step + parity gate (before anything is timed)
+    step()
+    torch.cuda.synchronize()
+    launches_per_step = lib.gpuntt_b200_last_launch_count()
+    y_host = data.cpu().numpy().view(np.uint64)
+    gate = {"checked_polynomials": 0, "mismatching_words": 0, "against": None}
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.quick:
+        rate, threads, kind, bad = cpu_check_and_rate(x_host, y_host, min(args.cpu_sample, BATCH))
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
+                        "sample": f"{min(args.cpu_sample, BATCH)} polynomials of this run's input (N=2^16, Data64, the examples' seed-0 "
+                                  f"mt19937 stream), NTTCPU::ntt sharded over {threads} host threads"}
+        gate = {"checked_polynomials": min(args.cpu_sample, BATCH), "mismatching_words": bad,
+                "against": "oracle/_ref NTTCPU<Data64>::ntt" if kind == "reference" else "oracle/ntt_oracle.c"}
+    else:
+        # no CPU leg in this mode (multi-GPU ranks, --quick): cross-check the tuned kernels against the generic pass kernel
+        # of the same library on the first 16 polynomials (two independent implementations; the CPU gate runs at N=1)
+        chk = torch.from_numpy(np.ascontiguousarray(x_host[:16]).view(np.int64)).cuda()
+        lib.gpuntt_b200_force_generic_path(1)
+        capi.ntt(chk, table, p, LOGN, X_N_minus, stream=stream)
+        lib.gpuntt_b200_force_generic_path(0)
+        torch.cuda.synchronize()
+        bad = int((chk.cpu().numpy().view(np.uint64) != y_host[:16]).sum())
+        gate = {"checked_polynomials": 16, "mismatching_words": bad, "against": "generic pass kernel of the same library"}
+    if gate["mismatching_words"]:
+        sys.stderr.write(f"bench.py: PARITY GATE FAILED on rank {rank}: {gate}\n")
+        sys.stderr.flush()
+        os._exit(3)
+
+    # ---- timed region: un-instrumented steps on the resident batch (values stay below p)
     warm = max(3, args.warmup)
     sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(warm):
         step()
     barrier()
-    lib.gpuntt_b200_set_profiling(1)
-    capi.profile_read()
     launches0 = lib.gpuntt_b200_total_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -239,6 +316,13 @@ def run_b200_arm(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = lib.gpuntt_b200_total_launch_count() - launches0
+    # ---- second, instrumented loop: per-launch durations for the roofline (CUDA events around every launch)
+    lib.gpuntt_b200_set_profiling(1)
+    capi.profile_read()
+    prof_steps = min(args.steps, 20)
+    for _ in range(prof_steps):
+        step()
+    torch.cuda.synchronize()
     recs = capi.profile_read()
     lib.gpuntt_b200_set_profiling(0)
     # keep the same load running ~1 s more (untimed) so the 100 ms clock sampler sees it
@@ -254,18 +338,24 @@ def run_b200_arm(args):
         ms = float(t.item())
     value = world * BATCH * args.steps / (ms * 1e-3)
 
-    # live roofline of the dominant kernel (merge_pass_kernel; npasses launches per step)
+    # live roofline of the dominant kernel
     pass_ms = [m for k, m in recs if k >= 1]
-    prep_ms = [m for k, m in recs if k == 0]
-    npasses = max(1, len(pass_ms) // max(1, args.steps))
+    npasses = max(1, len(pass_ms) // max(1, prof_steps))
     alg_bytes_per_launch = 2 * (1 << LOGN) * 8 * BATCH / npasses
     avg_pass_ms = sum(pass_ms) / max(1, len(pass_ms))
     peak, peak_src = measured_peak()
     achieved = alg_bytes_per_launch / (avg_pass_ms * 1e-3) / 1e9 if pass_ms else None
-    traffic = None
+    kernel = ("fused2_kernel (one launch per step: strided stages 0-7 and contiguous stages 8-15 chained through the L2)"
+              if npasses == 1 else
+              "fast_pass_kernel (%d launches per step: strided stages 0-7, contiguous stages 8-15)" % npasses)
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("fast_pass_kernel_dram_bytes_per_launch")   # from one ncu --set full capture
+            tj = json.load(f)
+        ent = tj.get("fused2_kernel" if npasses == 1 else "fast_pass_kernel")
+        if ent:
+            traffic = ent["dram_bytes_per_launch"]        # from one ncu --set full capture (not measured in this run)
+            traffic_src = {k: ent.get(k) for k in ("capture", "commit", "kernel")}
     except Exception:
         pass
     # informational second roof: the 32-bit integer multiplier pipe.  One 64-bit Shoup butterfly costs
@@ -281,14 +371,16 @@ def run_b200_arm(args):
     import ctypes as C
     h_in = torch.empty((BATCH, 1 << LOGN), dtype=torch.int64).pin_memory()
     h_out = torch.empty_like(h_in).pin_memory()
-    h_in.copy_(data.cpu())
-    h_tab = P.gpu_root_of_unity_table_generator(P.forward_root_of_unity_table)
+    h_in.copy_(torch.from_numpy(x_host.view(np.int64)))
     desc = capi.MergeDesc(BITS, 0, capi.FORWARD, LOGN, capi.PerPolynomial, X_N_minus, BATCH, 0,
                           h_in.data_ptr(), h_out.data_ptr(), None, p, 0, None, None, stream.cuda_stream)
 
     def e2e_step():
         capi.check(lib.gpuntt_b200_merge_ntt_host(C.byref(desc), h_tab.ctypes.data, h_tab.size))
     e2e_step()
+    if int((h_out.numpy().view(np.uint64) != y_host).sum()):
+        sys.stderr.write("bench.py: PARITY GATE FAILED: the host-buffer entry point disagrees with the device-resident call\n")
+        os._exit(3)
     e2e_steps = 1 if args.quick else max(1, min(args.steps, 10))
     barrier()
     t0 = time.perf_counter()
@@ -307,8 +399,11 @@ def run_b200_arm(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "l2": "inputs (512 MiB per GPU) larger than the 126 MB L2; no flush",
-                   "plan": capi.describe_plan(LOGN, BITS).strip(), "batch_per_gpu": BATCH,
+                   "plan": capi.describe_plan(LOGN, BITS).strip(), "batch_per_gpu": BATCH, "launches_per_step": launches_per_step,
+                   "input": "seed-0 std::mt19937 + uniform_int_distribution stream of the reference examples, polynomials "
+                            f"[{BATCH}*rank, {BATCH}*(rank+1)); timed steps re-run on the transformed data (values stay < p)",
                    "partition": f"batch slices, {world} x {BATCH} polynomials, no collective"},
+        "parity_gate": gate,
         "clocks": clocks,
         "e2e": {"value": world * BATCH * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": nbytes + h_tab.nbytes,
                 "d2h_bytes_per_step": nbytes, "steps": e2e_steps,
@@ -317,19 +412,15 @@ def run_b200_arm(args):
         "int_mul_roof": {"ntt_per_s_per_gpu": int_roof, "frac": (value / world) / int_roof,
                          "model": "28 multiplier-pipe issue cycles per warp-butterfly, %d multiplying butterflies per NTT, "
                                   "%d SMs x 4 sub-partitions at %.0f MHz" % (muls_per_ntt, sms, clk)},
-        "roofline": {"bound": "hbm", "kernel": "fast_pass_kernel (2 launches per step: strided stages 0-7, contiguous stages 8-15)",
-                     "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                     "peak_source": peak_src, "launches_per_step": npasses,
+                     "traffic_source": traffic_src, "peak_source": peak_src, "launches_per_step": npasses,
                      "algorithmic_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": avg_pass_ms,
-                     "prep_kernel_avg_ms": (sum(prep_ms) / len(prep_ms)) if prep_ms else None,
+                     "timing": "CUDA events around every launch in a second, instrumented loop (not the timed region)",
                      "frac_of_8TBps_nominal": (achieved / 8000.0) if achieved else None},
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.quick:
-        rate, threads, kind = cpu_reference_rate(args.cpu_sample)
-        out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
-                               "sample": f"{args.cpu_sample} polynomials of the same workload (N=2^16, Data64, seed 0), "
-                                         f"NTTCPU::ntt sharded over {threads} host threads"}
+    if cpu_baseline is not None:
+        out["cpu_baseline"] = cpu_baseline
         out["reference_gpu_same_box"] = reference_gpu_same_box()
     if rank == 0:
         emit_line(json.dumps(out))
@@ -340,12 +431,13 @@ def run_b200_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="kernel-timed region only (for runs under ncu)")
+    ap.add_argument("--corrupt-twiddle", action="store_true", help="flip one bit of the root table: the parity gate must exit non-zero")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":

@@ -99,6 +99,8 @@ def lib():
         L.gpuntt_b200_version.restype = i
         L.gpuntt_b200_force_generic_path.restype = None
         L.gpuntt_b200_force_generic_path.argtypes = [i]
+        L.gpuntt_b200_example_input.restype = None
+        L.gpuntt_b200_example_input.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]
         L.gpuntt_b200_tune.restype = None
         L.gpuntt_b200_tune.argtypes = [i, i]
         L.gpuntt_b200_set_profiling.restype = None
@@ -115,6 +117,15 @@ TUNE_FUSED_PASSES, TUNE_FUSED_LAG = 1, 2
 def tune(knob: int, value: int) -> None:
     """gpuntt_b200_tune: A/B knobs (results never depend on them)."""
     lib().gpuntt_b200_tune(knob, value)
+
+
+def example_input(modulus: int, count: int, seed: int = 0):
+    """The reference example drivers' input stream (std::mt19937(seed) + uniform_int_distribution<uint64_t>(0, p-1))
+    as a numpy uint64 array."""
+    import numpy as np
+    out = np.empty(count, dtype=np.uint64)
+    lib().gpuntt_b200_example_input(seed, modulus, count, out.ctypes.data)
+    return out
 
 
 def check(status: int) -> None:

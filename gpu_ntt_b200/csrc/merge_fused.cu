@@ -324,12 +324,14 @@ namespace gpuntt_b200
             if (doS) build_twiddles<SS>(twS, f.s.table, 0, n, f.s.n_tw, f.s.lo, f.s.plus, f.s.p, f.s.mu, f.s.pbits, tid, kFusedConsumers);
             if (doC) build_twiddles<SC>(twC, f.c.table, range, n, f.c.n_tw, 0, f.c.plus, f.c.p, f.c.mu, f.c.pbits, tid, kFusedConsumers);
             asm volatile("bar.sync 3, %0;" ::"n"(kFusedConsumers) : "memory");
-            for (int it = 0;; it++)
+            // tile claims run one ahead: the leader takes the NEXT index before the group starts on the current tile, so the
+            // shared-memory atomic and its broadcast are off the critical path
+            if (ctid == 0) ctl->bcast[g][0] = atomicAdd(&ctl->next_t, 1);
+            consumer_sync(1 + g);
+            int t = ctl->bcast[g][0];
+            for (int it = 0; t < total; it++)
             {
-                if (ctid == 0) ctl->bcast[g][it & 1] = atomicAdd(&ctl->next_t, 1);
-                consumer_sync(1 + g);
-                const int t = ctl->bcast[g][it & 1];
-                if (t >= total) break;
+                if (ctid == 0) ctl->bcast[g][(it + 1) & 1] = atomicAdd(&ctl->next_t, 1);
                 const int b = t % NB;
                 unsigned char* buf = bufs + b * TILE;
                 mbar_wait(smem_u32(&ctl->full[b]), (unsigned) (t / NB) & 1u); // tile landed
@@ -339,6 +341,8 @@ namespace gpuntt_b200
                     tile_rounds<SC, false>(buf, twC, twC + SC::TW1, twC + SC::TW1 + SC::TW2, MC, ctid, ninv, nullptr, f.c, false, 1 + g);
                 fence_async(); // make the generic-proxy writes visible to the bulk store
                 mbar_arrive(smem_u32(&ctl->done[b]));
+                consumer_sync(1 + g);
+                t = ctl->bcast[g][(it + 1) & 1];
             }
         }
         // ---- the counters go back to zero: the last CTA to finish (every other CTA has made all its observations) clears them
@@ -357,12 +361,15 @@ namespace gpuntt_b200
         }
     }
 
-    static std::atomic<int> g_fused_lag_steps{6};
+    static std::atomic<int> g_fused_lag_steps{4};
     void fused_set_lag_steps(int v) { g_fused_lag_steps.store(v < 0 ? 0 : v); }
 
     // in / out / table / p / ninv / mu / pbits / n / plus / batch / in_bound of `a` are filled in; lo_s = row stride (log2) of the
     // strided pass.  Returns cudaErrorNotSupported when this call cannot take the fused kernel (the caller launches the
     // two passes separately).
+    static std::atomic<int> g_fused_policy{1};
+    void fused_set_policy(int v) { g_fused_policy.store(v); }
+
     template <typename SS, typename SC>
     static cudaError_t launch_fused(const FastArgs<typename SS::T>& a, int lo_s, bool inverse, unsigned* counters, cudaStream_t st,
                                     void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t))
@@ -418,6 +425,10 @@ namespace gpuntt_b200
         f.nranges = nranges;
         f.ngroups = (batch + (1 << SC::NPLOG) - 1) >> SC::NPLOG;
         const long long n_str = (long long) batch << tpp_log;
+        // Measured (profiles/r2_fused_ab.jsonl): 32-bit transforms gain at every batch size (the data crosses HBM once and
+        // the strided pass is bandwidth-bound on its own); 64-bit transforms are bound by the integer multiplier, so the
+        // fused kernel only wins while the call is launch-bound -- at most one strided tile per CTA.
+        if (g_fused_policy.load() == 1 && sizeof(T) == 8 && n_str > slots) return cudaErrorNotSupported;
         long long grid;
         const long long con_each = (slots - n_str) / nranges; // CTAs per range left over when every strided tile has its own CTA
         if (n_str <= slots / 2 && con_each >= 1)

@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <random>
 #include <map>
 #include <string>
 #include <tuple>
@@ -633,6 +634,7 @@ namespace gpuntt_b200
                            int batch, cudaStream_t st, int* launched, void (*prof_begin)(int, cudaStream_t),
                            void (*prof_end)(cudaStream_t), int in_bound = 1, unsigned* counters = nullptr);
     void fused_set_lag_steps(int v); // merge_fused.cu
+    void fused_set_policy(int v);
     bool fast_supported(int n_power, int element_bits);
 
     static int fail(int code, const std::string& msg)
@@ -1215,7 +1217,10 @@ extern "C"
     {
         switch (knob)
         {
-            case GPUNTT_B200_TUNE_FUSED_PASSES: g_fused_enabled.store(value ? 1 : 0); break;
+            case GPUNTT_B200_TUNE_FUSED_PASSES:
+                g_fused_enabled.store(value ? 1 : 0);
+                fused_set_policy(value);
+                break;
             case GPUNTT_B200_TUNE_FUSED_LAG: fused_set_lag_steps(value); break;
             case GPUNTT_B200_TUNE_4STEP_TRANSPOSED: g_fourstep_transposed.store(value ? 1 : 0); break;
             default: break;
@@ -1246,6 +1251,14 @@ extern "C"
             g_prof_pool[r.dev].push_back(r.e1);
         }
         return n;
+    }
+
+    void gpuntt_b200_example_input(uint32_t seed, uint64_t modulus, uint64_t count, uint64_t* host_out)
+    {
+        if (!host_out || modulus == 0) return;
+        std::mt19937 gen(seed);
+        std::uniform_int_distribution<std::uint64_t> dis(0, modulus - 1);
+        for (uint64_t i = 0; i < count; i++) host_out[i] = dis(gen);
     }
 
     int gpuntt_b200_version(void) { return GPUNTT_B200_VERSION; }

@@ -184,8 +184,9 @@ void gpuntt_b200_force_generic_path(int on);
 
 /* Tuning / A-B testing knobs (process-wide; results never depend on them):
  *   FUSED_PASSES  1 (default): two-pass plans run as ONE launch with the passes chained through the L2
- *                 (merge_fused.cu); 0: one launch per pass.
- *   FUSED_LAG     how many tile times the second pass trails the first inside the fused kernel (default 2). */
+ *                 (merge_fused.cu) wherever that measured faster (32-bit data; launch-bound 64-bit calls);
+ *                 2: wherever the shapes allow; 0: one launch per pass.
+ *   FUSED_LAG     how many tile times the second pass trails the first inside the fused kernel (default 4). */
 #define GPUNTT_B200_TUNE_FUSED_PASSES 1
 #define GPUNTT_B200_TUNE_FUSED_LAG 2
 /*   4STEP_TRANSPOSED  1 (default): the fused-contract forward 4-step writes its column phase as the n2 x n1 matrix
@@ -193,6 +194,12 @@ void gpuntt_b200_force_generic_path(int on);
  *                 0: column pass, row Merge-NTT, transpose kernel. */
 #define GPUNTT_B200_TUNE_4STEP_TRANSPOSED 3
 void gpuntt_b200_tune(int knob, int value);
+
+/* The input recipe of the reference's example drivers (example/ntt_merge/test_merge_ntt.cu:70-85,
+ * test_4step_ntt.cu:48-57): std::mt19937 gen(seed); std::uniform_int_distribution<uint64_t> dis(0, modulus - 1);
+ * count values, in order, into the HOST array out (uint64_t; callers narrow for 32-bit data).  Used by examples/,
+ * bench.py and anything else that wants the reference's seed-0 stream without linking the reference. */
+void gpuntt_b200_example_input(uint32_t seed, uint64_t modulus, uint64_t count, uint64_t* host_out);
 
 /* Human-readable message for the last non-OK status returned on this thread. */
 const char* gpuntt_b200_last_error(void);

@@ -20,7 +20,7 @@ from gpu_ntt_b200.params import NTTParameters, X_N_minus  # noqa: E402
 from perf_configs import dev, peak, time_ms  # noqa: E402
 
 
-def case(logn, batch, bits, iters, inverse=False, fused=1, lag=6):
+def case(logn, batch, bits, iters, inverse=False, fused=2, lag=4):
     P = NTTParameters(logn, X_N_minus, bits)
     p = P.modulus
     tab = dev(P.gpu_root_of_unity_table_generator(P.inverse_root_of_unity_table if inverse else P.forward_root_of_unity_table), bits)
@@ -37,7 +37,7 @@ def case(logn, batch, bits, iters, inverse=False, fused=1, lag=6):
     ms = time_ms(fn, iters)
     launches = capi.lib().gpuntt_b200_last_launch_count()
     capi.tune(capi.TUNE_FUSED_PASSES, 1)
-    capi.tune(capi.TUNE_FUSED_LAG, 6)
+    capi.tune(capi.TUNE_FUSED_LAG, 4)
     gbs = 2 * (1 << logn) * (bits // 8) * batch / (ms * 1e-3) / 1e9
     print(json.dumps({"logn": logn, "batch": batch, "bits": bits, "op": "inv" if inverse else "fwd", "fused": fused, "lag": lag,
                       "launches": launches, "ms": round(ms, 4), "us": round(ms * 1e3, 2), "ntt_per_s": round(batch / (ms * 1e-3), 1),
@@ -52,17 +52,17 @@ def main():
     args = ap.parse_args()
     it = 5 if args.quick else 20
     capi.lib()
-    for fused in (1, 0):
+    for fused in (2, 0):
         case(16, 1024, 64, it, fused=fused)
         case(16, 1024, 64, it, inverse=True, fused=fused)
         case(14, 4096, 32, it, fused=fused)
         case(14, 4096, 32, it, inverse=True, fused=fused)
-    for lag in (1, 2, 3, 4, 8, 12):
+    for lag in (2, 3, 5, 6):
         case(16, 1024, 64, it, lag=lag)
         case(14, 4096, 32, it, lag=lag)
     if args.quick:
         return
-    for fused in (1, 0):
+    for fused in (2, 0):
         for logn in (12, 13, 14, 15):
             case(logn, (1 << 26) >> logn, 64, it, fused=fused)
         for logn in (13, 15, 16, 17, 18):
