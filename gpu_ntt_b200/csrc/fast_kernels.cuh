@@ -916,19 +916,17 @@ namespace gpuntt_b200
     }
 
     // ------------------------------------------------------------------ host side
+    // (function-local static with an initialiser: thread-safe by the language rules)
     static PFN_cuTensorMapEncodeTiled get_encode()
     {
-        static PFN_cuTensorMapEncodeTiled fn = nullptr;
-        static bool tried = false;
-        if (!tried)
+        static const PFN_cuTensorMapEncodeTiled fn = []() -> PFN_cuTensorMapEncodeTiled
         {
-            tried = true;
             void* p = nullptr;
             cudaDriverEntryPointQueryResult q;
-            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-                q == cudaDriverEntryPointSuccess)
-                fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
-        }
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+                return reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+            return nullptr;
+        }();
         return fn;
     }
 

@@ -360,28 +360,60 @@ static int fourstep_execute(const gpuntt_b200_4step_desc* d)
     if (d->mod_count == 0 && d->modulus_value < 5) return fail(GPUNTT_B200_ERR_ARGUMENT, "modulus_value too small");
     // The reference's own 4-step examples call the RNS overload with ONE modulus held on the device
     // (test_4step_ntt.cu:126-154).  The tuned kernels take the modulus as a launch argument and pick their arithmetic
-    // policy from it on the host, so that one Modulus (and n^-1) is read back here -- 24 + 8 bytes, after the work
-    // already enqueued on the stream -- and the call continues as the single-modulus form.  Under stream capture no
-    // read-back is possible and the device-modulus kernels run instead.
+    // policy from it on the host, so that one Modulus (and n^-1) is read back ONCE per (device, modulus pointer, n^-1
+    // pointer) -- 24 + 8 bytes and one stream synchronisation on the first call -- and remembered; later calls with the
+    // same pointers enqueue and return like every other entry point.  The cached value is dropped by
+    // gpuntt_b200_release_workspaces(); GPUNTT_B200_TUNE_4STEP_MODULUS_CACHE 0 disables the read-back altogether (the
+    // device-modulus kernels run), 2 re-reads on every call.  Under stream capture nothing is read back.
     gpuntt_b200_4step_desc single;
-    if (d->mod_count == 1 && d->element_bits == 64 && !g_force_generic.load())
+    const int cache_mode = g_fourstep_modcache.load();
+    if (d->mod_count == 1 && d->element_bits == 64 && !g_force_generic.load() && cache_mode != 0)
     {
-        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-        cudaStreamIsCapturing((cudaStream_t) d->stream, &cap);
-        if (cap == cudaStreamCaptureStatusNone)
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const auto key = std::make_tuple(dev, (const void*) d->modulus_dev, (const void*) (d->direction == GPUNTT_B200_INVERSE ? d->mod_inverse_dev : nullptr));
+        uint64_t host_mod = 0, host_ninv = 0;
+        bool have = false;
+        if (cache_mode == 1)
         {
-            uint64_t host_mod[3] = {0, 0, 0}, host_ninv = 0;
-            cudaError_t e = cudaMemcpyAsync(host_mod, d->modulus_dev, sizeof(host_mod), cudaMemcpyDeviceToHost, (cudaStream_t) d->stream);
-            if (e == cudaSuccess && d->direction == GPUNTT_B200_INVERSE)
-                e = cudaMemcpyAsync(&host_ninv, d->mod_inverse_dev, sizeof(host_ninv), cudaMemcpyDeviceToHost, (cudaStream_t) d->stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t) d->stream);
-            if (e != cudaSuccess) return cuda_fail(e, "4-step modulus read-back");
-            if (host_mod[0] < 5) return fail(GPUNTT_B200_ERR_ARGUMENT, "modulus_value too small");
+            std::lock_guard<std::mutex> lk(g_ws_mutex);
+            auto it = g_modcache.find(key);
+            if (it != g_modcache.end())
+            {
+                host_mod = it->second.first;
+                host_ninv = it->second.second;
+                have = true;
+            }
+        }
+        if (!have)
+        {
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            cudaStreamIsCapturing((cudaStream_t) d->stream, &cap);
+            if (cap == cudaStreamCaptureStatusNone)
+            {
+                uint64_t m3[3] = {0, 0, 0};
+                cudaError_t e = cudaMemcpyAsync(m3, d->modulus_dev, sizeof(m3), cudaMemcpyDeviceToHost, (cudaStream_t) d->stream);
+                if (e == cudaSuccess && d->direction == GPUNTT_B200_INVERSE)
+                    e = cudaMemcpyAsync(&host_ninv, d->mod_inverse_dev, sizeof(host_ninv), cudaMemcpyDeviceToHost, (cudaStream_t) d->stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t) d->stream);
+                if (e != cudaSuccess) return cuda_fail(e, "4-step modulus read-back");
+                host_mod = m3[0];
+                have = true;
+                if (cache_mode == 1)
+                {
+                    std::lock_guard<std::mutex> lk(g_ws_mutex);
+                    g_modcache[key] = std::make_pair(host_mod, host_ninv);
+                }
+            }
+        }
+        if (have)
+        {
+            if (host_mod < 5) return fail(GPUNTT_B200_ERR_ARGUMENT, "modulus_value too small");
             single = *d;
             single.mod_count = 0;
             single.modulus_dev = nullptr;
             single.mod_inverse_dev = nullptr;
-            single.modulus_value = host_mod[0];
+            single.modulus_value = host_mod;
             single.mod_inverse_value = host_ninv;
             d = &single;
         }

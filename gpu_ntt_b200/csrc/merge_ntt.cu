@@ -20,6 +20,7 @@
 #include <random>
 #include <map>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <type_traits>
 #include <vector>
@@ -654,7 +655,16 @@ namespace gpuntt_b200
         size_t bytes = 0;
     };
     static std::mutex g_ws_mutex;
-    static std::map<std::tuple<int, void*, int>, Workspace> g_ws; // (device, stream, slot)
+    // (device, stream, slot).  Scratch is reused by the calls of one stream, which the stream itself orders.  The handle
+    // cudaStreamPerThread names a DIFFERENT stream in every host thread, so for it the key carries the calling thread.
+    using WsKey = std::tuple<int, void*, int, size_t>;
+    static std::map<WsKey, Workspace> g_ws;
+    static WsKey ws_key(int dev, void* stream, int slot)
+    {
+        size_t th = 0;
+        if ((cudaStream_t) stream == cudaStreamPerThread) th = std::hash<std::thread::id>()(std::this_thread::get_id()) | 1;
+        return WsKey(dev, stream, slot, th);
+    }
 
     // slot 0: twiddle companions; slots 1,2: host-convenience staging buffers
     static cudaError_t get_workspace(void* stream, int slot, size_t bytes, void** out)
@@ -663,7 +673,7 @@ namespace gpuntt_b200
         cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
         std::lock_guard<std::mutex> lk(g_ws_mutex);
-        Workspace& w = g_ws[std::make_tuple(dev, stream, slot)];
+        Workspace& w = g_ws[ws_key(dev, stream, slot)];
         if (w.bytes < bytes)
         {
             if (w.ptr)
@@ -689,6 +699,8 @@ namespace gpuntt_b200
     // stream, i.e. before the first kernel that uses them.  nullptr: run the passes as separate launches.
     static std::atomic<int> g_fused_enabled{1};
     static std::atomic<int> g_fourstep_transposed{1};
+    static std::atomic<int> g_fourstep_modcache{1};
+    static std::map<std::tuple<int, const void*, const void*>, std::pair<uint64_t, uint64_t>> g_modcache; // under g_ws_mutex
     static unsigned* fused_counters(void* stream, long long polys)
     {
         if (!g_fused_enabled.load() || polys <= 0) return nullptr;
@@ -696,7 +708,7 @@ namespace gpuntt_b200
         if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
         const size_t bytes = ((size_t) polys + 1) * sizeof(unsigned); // + the ticket word
         std::lock_guard<std::mutex> lk(g_ws_mutex);
-        Workspace& w = g_ws[std::make_tuple(dev, stream, 8)];
+        Workspace& w = g_ws[ws_key(dev, stream, 8)];
         if (w.bytes < bytes)
         {
             cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -893,11 +905,9 @@ namespace gpuntt_b200
         }
         if (rns && !d->is_signed && !g_force_generic.load() && d->ntt_layout == GPUNTT_B200_PER_POLYNOMIAL)
         {
-            void* flag = nullptr;
-            cudaError_t fe = get_workspace(d->stream, 7, sizeof(int), &flag);
-            if (fe != cudaSuccess) return cuda_fail(fe, "RNS policy flag allocation");
+            void* flag = nullptr; // (the dual-policy kernels read the moduli themselves: no flag buffer any more)
             int launched = 0;
-            fe = fast_merge_rns<T>(reinterpret_cast<const T*>(d->in), reinterpret_cast<T*>(d->out),
+            cudaError_t fe = fast_merge_rns<T>(reinterpret_cast<const T*>(d->in), reinterpret_cast<T*>(d->out),
                                    reinterpret_cast<const T*>(d->root_of_unity_table), reinterpret_cast<const T*>(d->modulus_dev),
                                    reinterpret_cast<const T*>(d->mod_inverse_dev), d->modulus_order_dev, d->poly_order_dev, d->mod_count, n,
                                    plus ? 1 : 0, inv, d->batch_size,
@@ -1172,6 +1182,7 @@ extern "C"
                 cudaFree(kv.second.ptr);
             }
         g_ws.clear();
+        g_modcache.clear();
     }
 
     int gpuntt_b200_describe_plan(int n_power, int element_bits, char* buf, size_t buf_len)
@@ -1223,6 +1234,7 @@ extern "C"
                 break;
             case GPUNTT_B200_TUNE_FUSED_LAG: fused_set_lag_steps(value); break;
             case GPUNTT_B200_TUNE_4STEP_TRANSPOSED: g_fourstep_transposed.store(value ? 1 : 0); break;
+            case GPUNTT_B200_TUNE_4STEP_MODULUS_CACHE: g_fourstep_modcache.store(value); break;
             default: break;
         }
     }

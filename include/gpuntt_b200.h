@@ -18,7 +18,10 @@
  *    N/2 powers of omega for X^N-1, N powers of psi for X^N+1;
  *  - RNS form: polynomial b uses modulus[b % mod_count], table slice starting at element
  *    (b % mod_count) << n_power, mod_inverse[b % mod_count] (ntt.cu:613-619,672-673);
- *  - calls only enqueue work on `stream` and return; they never synchronise;
+ *  - calls only enqueue work on `stream` and return; they never synchronise -- with two documented exceptions:
+ *    a cached scratch buffer that has to GROW is re-allocated after a stream synchronisation, and the first
+ *    gpuntt_b200_4step_ntt call per (device, modulus pointer) in the one-device-modulus RNS form reads that modulus
+ *    back (see GPUNTT_B200_TUNE_4STEP_MODULUS_CACHE);
  *  - in == out is allowed (that is all the reference's *_Inplace entry points do).
  *
  * Unlike the reference the engine keeps one small device scratch buffer per (device, stream)
@@ -193,6 +196,12 @@ void gpuntt_b200_force_generic_path(int on);
  *                 (transposing TMA store) and runs the row transforms along that layout -- no transpose kernel;
  *                 0: column pass, row Merge-NTT, transpose kernel. */
 #define GPUNTT_B200_TUNE_4STEP_TRANSPOSED 3
+/*   4STEP_MODULUS_CACHE  how gpuntt_b200_4step_ntt treats the RNS form with ONE device modulus (what the reference's
+ *                 examples pass): 1 (default) read the Modulus / n^-1 back once per (device, pointers) -- the first such
+ *                 call synchronises the stream, later ones do not -- and run the single-modulus tuned kernels (the value
+ *                 behind a cached pointer must not change; gpuntt_b200_release_workspaces() forgets it); 0 never read
+ *                 back (device-modulus kernels); 2 read back on every call. */
+#define GPUNTT_B200_TUNE_4STEP_MODULUS_CACHE 4
 void gpuntt_b200_tune(int knob, int value);
 
 /* The input recipe of the reference's example drivers (example/ntt_merge/test_merge_ntt.cu:70-85,
