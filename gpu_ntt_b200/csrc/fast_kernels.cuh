@@ -193,6 +193,8 @@ namespace gpuntt_b200
         int n, lo, plus, first, last, batch, rr;
         int in_bound; // forward first pass of a cyclic transform: inputs are below in_bound * p (0/1: canonical)
         int w_lazy;   // WMUL forward kernels: leave the products below 2p (one correction) instead of canonical
+        int signed_io; // Data32s / Data64s: forward = signed input (x < 0 -> x + p as the first pass loads, modular_arith.cuh:372-385 of
+                       // the reference), inverse = centred signed output (r > p/2 -> r - p after n^-1, modular_arith.cuh:389-405)
         int n_tw; // transform size (log2) for twiddle indexing when it differs from the layout size n (0: n)
         int cta_per_seg, seg_extra; // cta_per_seg > 0: every CTA works inside ONE twiddle segment; the first seg_extra segments get
                                     // cta_per_seg + 1 CTAs, the others cta_per_seg (set by launch_fast)
@@ -235,7 +237,7 @@ namespace gpuntt_b200
                                                const typename ModOf<S>::type& M, int ctid,
                                                const Twiddle<typename S::T>& ninv,
                                                const Twiddle<typename S::T>* __restrict__ wtile = nullptr, int lo = 0, int in_bound = 1,
-                                               bool w_lazy = false, int bar = 1)
+                                               bool w_lazy = false, int bar = 1, int sflags = 0)
     {
         using T = typename S::T;
         constexpr int E = 1 << R;
@@ -295,6 +297,13 @@ namespace gpuntt_b200
                 for (int a = 0; a < E; a++) e[a] = *reinterpret_cast<const T*>(addr(a));
             }
 
+            if (sflags & 1) // signed input: -|x| -> p - |x|
+            {
+                using ST = typename std::make_signed<T>::type;
+#pragma unroll
+                for (int a = 0; a < E; a++)
+                    if ((ST) e[a] < 0) e[a] += M.p;
+            }
             // 4-step twiddle-matrix product on the item's elements (forward: epilogue, canonical results; inverse:
             // prologue, lazy results in [0,3p)).  Loads in batches of 8 (32 registers): ptxas otherwise serialises
             // load -> multiply -> load and exposes one global-memory latency per element.
@@ -414,6 +423,12 @@ namespace gpuntt_b200
                 {
 #pragma unroll
                     for (int a = 0; a < E; a++) e[a] = M.canon_inv(e[a], ninv);
+                    if (sflags & 2) // centred signed output
+                    {
+#pragma unroll
+                        for (int a = 0; a < E; a++)
+                            if (e[a] > (M.p >> 1)) e[a] -= M.p;
+                    }
                 }
             }
 
@@ -509,6 +524,7 @@ namespace gpuntt_b200
                                                 const FastArgs<typename S::T>& a, bool triv, int bar = 1)
     {
         constexpr bool W1 = WMUL && S::R2 == 0, W2 = WMUL && S::R2 > 0;
+        const int sin = (a.signed_io && a.first) ? 1 : 0, sout = a.signed_io ? 2 : 0;
         if constexpr (!S::INV)
         {
 #ifdef GPUNTT_EXPERIMENT_NOCANON // timing experiment only (lazy outputs): what the final canonicalisation costs
@@ -521,12 +537,12 @@ namespace gpuntt_b200
             {
                 if (triv)
                     fast_round<S, S::R1, S::LB1, S::G1, FIN1, true, W1, TS1>(buf, tw1, M, tid, ninv, wtile, a.lo,
-                                                                              a.in_bound > 1 ? a.in_bound : 1, a.w_lazy != 0, bar);
+                                                                              a.in_bound > 1 ? a.in_bound : 1, a.w_lazy != 0, bar, sin);
                 else
-                    fast_round<S, S::R1, S::LB1, S::G1, FIN1, false, W1, TS1>(buf, tw1, M, tid, ninv, wtile, a.lo, 1, a.w_lazy != 0, bar);
+                    fast_round<S, S::R1, S::LB1, S::G1, FIN1, false, W1, TS1>(buf, tw1, M, tid, ninv, wtile, a.lo, 1, a.w_lazy != 0, bar, sin);
             }
             else
-                fast_round<S, S::R1, S::LB1, S::G1, FIN1>(buf, tw1, M, tid, ninv);
+                fast_round<S, S::R1, S::LB1, S::G1, FIN1>(buf, tw1, M, tid, ninv, nullptr, 0, 1, false, bar, sin);
             if constexpr (S::R2 > 0)
             {
                 consumer_sync(bar);
@@ -553,7 +569,7 @@ namespace gpuntt_b200
             if constexpr (S::STRIDED)
             {
                 if (a.last)
-                    fast_round<S, S::R1, S::LB1, S::G1, true, false, W1>(buf, tw1, M, tid, ninv, wtile, a.lo);
+                    fast_round<S, S::R1, S::LB1, S::G1, true, false, W1>(buf, tw1, M, tid, ninv, wtile, a.lo, 1, false, bar, sout);
                 else
                     fast_round<S, S::R1, S::LB1, S::G1, false, false, W1>(buf, tw1, M, tid, ninv, wtile, a.lo);
             }
@@ -561,7 +577,7 @@ namespace gpuntt_b200
             {
                 // whole transforms in the tile: the top round is the last one of a single-pass inverse (n^-1 there)
                 if (a.last)
-                    fast_round<S, S::R1, S::LB1, S::G1, true>(buf, tw1, M, tid, ninv);
+                    fast_round<S, S::R1, S::LB1, S::G1, true>(buf, tw1, M, tid, ninv, nullptr, 0, 1, false, bar, sout);
                 else
                     fast_round<S, S::R1, S::LB1, S::G1, false>(buf, tw1, M, tid, ninv);
             }

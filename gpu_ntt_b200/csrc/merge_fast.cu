@@ -98,10 +98,11 @@ namespace gpuntt_b200
             covered = inverse ? ((uint64_t) a.p < kFastModulusLimit) : ((uint64_t) a.p >= kF60ModulusMin && (uint64_t) a.p < kF60ModulusLimit);
         else
             covered = inverse || (uint32_t) a.p < kL32ModulusLimit;
-        if (!covered) return cudaSuccess;
         cudaError_t e;
         prof_begin(1, st);
-        if constexpr (sizeof(T) == 8)
+        if (!covered) // exact policy: any modulus the reference accepts
+            e = inverse ? launch_small<T, true, 0>(n_power, s, st) : launch_small<T, false, 0>(n_power, s, st);
+        else if constexpr (sizeof(T) == 8)
             e = inverse ? launch_small<T, true, 1>(n_power, s, st) : launch_small<T, false, 2>(n_power, s, st);
         else
             e = inverse ? launch_small<T, true, 0>(n_power, s, st) : launch_small<T, false, 2>(n_power, s, st);
@@ -117,13 +118,14 @@ namespace gpuntt_b200
     template <typename T>
     cudaError_t fast_merge(const T* in, T* out, const T* table, T p, T ninv, int n_power, int plus, bool inverse,
                            int batch, cudaStream_t st, int* launched, void (*prof_begin)(int, cudaStream_t),
-                           void (*prof_end)(cudaStream_t), int in_bound, unsigned* counters)
+                           void (*prof_end)(cudaStream_t), int in_bound, unsigned* counters, int signed_io)
     {
         *launched = 0;
         if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return cudaSuccess;
         if (fast_small_supported(n_power, (int) sizeof(T) * 8))
         {
             if (sizeof(T) == 4 && ((uint32_t) p >= (1u << 30) || (uint32_t) p < 3)) return cudaSuccess;
+            if (sizeof(T) == 8 && ((uint64_t) p >= (1ull << 62) || (uint64_t) p < 3)) return cudaSuccess;
             FastArgs<T> a{};
             a.table = table;
             a.p = p;
@@ -142,6 +144,7 @@ namespace gpuntt_b200
             }
             a.plus = plus;
             a.in_bound = 1;
+            a.signed_io = signed_io;
             return fast_small<T>(a, in, out, n_power, inverse, batch, st, launched, prof_begin, prof_end);
         }
         if (!fast_supported(n_power, (int) sizeof(T) * 8)) return cudaSuccess;
@@ -156,7 +159,7 @@ namespace gpuntt_b200
             const bool lazy_fwd = !f60 && (uint64_t) p >= kFastModulusMin && (uint64_t) p < kFastModulusLimit;
             const bool fast_inv = (uint64_t) p < kFastModulusLimit;
             const bool fast_arith = inverse ? fast_inv : (f60 || lazy_fwd);
-            if (!fast_arith && n_power != 16) return cudaSuccess;
+            if (!fast_arith && (uint64_t) p >= (1ull << 62)) return cudaSuccess; // (the exact policy needs 4p < 2^64, like the reference)
             FastArgs<T> a{};
             a.table = table;
             a.p = p;
@@ -171,6 +174,7 @@ namespace gpuntt_b200
             a.plus = plus;
             a.batch = batch;
             a.in_bound = in_bound;
+            a.signed_io = signed_io;
             using Cf = Shape<T, false, 2, false, 4, 4, 12, GPUNTT_FAST_P1_NPLOG>;
             using Ci = Shape<T, true, 1, false, 4, 4, 12, 1>;
             using Cfx = Shape<T, false, 0, false, 4, 4, 12, 1>;
@@ -210,7 +214,7 @@ namespace gpuntt_b200
                         e = inverse ? launch_strided<T, true, 1>(pl.d[i], s, st)
                                     : (f60 ? launch_strided<T, false, 2>(pl.d[i], s, st) : launch_strided<T, false, 1>(pl.d[i], s, st));
                     else
-                        e = inverse ? launch_strided<T, true, 0>(8, s, st) : launch_strided<T, false, 0>(8, s, st);
+                        e = inverse ? launch_strided<T, true, 0>(pl.d[i], s, st) : launch_strided<T, false, 0>(pl.d[i], s, st);
                 }
                 else
                 {
@@ -242,6 +246,7 @@ namespace gpuntt_b200
             a.n = n_power;
             a.plus = plus;
             a.batch = batch;
+            a.signed_io = signed_io;
             using Cf = Shape<T, false, 0, false, 5, 5, 13, 1>;
             using Cl = Shape<T, false, 2, false, 5, 5, 13, 1>; // lazy forward policy (p <= 2^29)
             using Ci = Shape<T, true, 0, false, 5, 5, 13, 1>;
@@ -295,8 +300,8 @@ namespace gpuntt_b200
     }
 
     template cudaError_t fast_merge<uint64_t>(const uint64_t*, uint64_t*, const uint64_t*, uint64_t, uint64_t, int, int, bool,
-                                              int, cudaStream_t, int*, void (*)(int, cudaStream_t), void (*)(cudaStream_t), int, unsigned*);
+                                              int, cudaStream_t, int*, void (*)(int, cudaStream_t), void (*)(cudaStream_t), int, unsigned*, int);
     template cudaError_t fast_merge<uint32_t>(const uint32_t*, uint32_t*, const uint32_t*, uint32_t, uint32_t, int, int, bool,
-                                              int, cudaStream_t, int*, void (*)(int, cudaStream_t), void (*)(cudaStream_t), int, unsigned*);
+                                              int, cudaStream_t, int*, void (*)(int, cudaStream_t), void (*)(cudaStream_t), int, unsigned*, int);
 
 } // namespace gpuntt_b200

@@ -425,10 +425,16 @@ namespace gpuntt_b200
         f.nranges = nranges;
         f.ngroups = (batch + (1 << SC::NPLOG) - 1) >> SC::NPLOG;
         const long long n_str = (long long) batch << tpp_log;
-        // Measured (profiles/r2_fused_ab.jsonl): 32-bit transforms gain at every batch size (the data crosses HBM once and
-        // the strided pass is bandwidth-bound on its own); 64-bit transforms are bound by the integer multiplier, so the
-        // fused kernel only wins while the call is launch-bound -- at most one strided tile per CTA.
-        if (g_fused_policy.load() == 1 && sizeof(T) == 8 && n_str > slots) return cudaErrorNotSupported;
+        // Measured (profiles/r2_fused_ab.jsonl): the small 32-bit rings gain at every batch size (the data crosses HBM once
+        // and their strided pass is bandwidth-bound on its own); the 64-bit transforms are bound by the integer multiplier,
+        // so beyond 2^13 the fused kernel only wins while the call is launch-bound (a few tiles per CTA).
+        // Round-2 numbers at saturating batch (unfused / fused time): 32-bit 2^13 1.31, 2^14 1.26, 2^15 1.17, 2^16 1.10,
+        // 2^17 0.98, 2^18 0.98; 64-bit 2^12 1.09, 2^13 1.01, 2^14 0.98, 2^15 0.98, 2^16 0.90; small batches 1.1-1.5 everywhere.
+        if (g_fused_policy.load() == 1)
+        {
+            const bool always = sizeof(T) == 8 ? n <= 13 : n <= 16;
+            if (!always && n_str > 8 * slots) return cudaErrorNotSupported;
+        }
         long long grid;
         const long long con_each = (slots - n_str) / nranges; // CTAs per range left over when every strided tile has its own CTA
         if (n_str <= slots / 2 && con_each >= 1)

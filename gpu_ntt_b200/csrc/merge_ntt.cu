@@ -633,7 +633,7 @@ namespace gpuntt_b200
     template <typename T>
     cudaError_t fast_merge(const T* in, T* out, const T* table, T p, T ninv, int n_power, int plus, bool inverse,
                            int batch, cudaStream_t st, int* launched, void (*prof_begin)(int, cudaStream_t),
-                           void (*prof_end)(cudaStream_t), int in_bound = 1, unsigned* counters = nullptr);
+                           void (*prof_end)(cudaStream_t), int in_bound = 1, unsigned* counters = nullptr, int signed_io = 0);
     void fused_set_lag_steps(int v); // merge_fused.cu
     void fused_set_policy(int v);
     bool fast_supported(int n_power, int element_bits);
@@ -893,13 +893,15 @@ namespace gpuntt_b200
         const bool rns = d->mod_count > 0;
         const bool plus = d->reduction_poly == GPUNTT_B200_X_N_PLUS;
         cudaStream_t st = (cudaStream_t) d->stream;
-        if (!rns && !d->is_signed && !g_force_generic.load() && d->ntt_layout == GPUNTT_B200_PER_POLYNOMIAL)
+        if (!rns && !g_force_generic.load() && d->ntt_layout == GPUNTT_B200_PER_POLYNOMIAL)
         {
+            // (signed data: same kernels -- the first forward round fixes negative inputs up as it loads, the last inverse
+            // round centres its outputs, ntt.cu:481-489, 1178-1186 of the reference)
             int launched = 0;
             cudaError_t fe = fast_merge<T>(reinterpret_cast<const T*>(d->in), reinterpret_cast<T*>(d->out),
                                            reinterpret_cast<const T*>(d->root_of_unity_table), (T) d->modulus_value,
                                            (T) d->mod_inverse_value, n, plus ? 1 : 0, inv, d->batch_size, st, &launched,
-                                           prof_begin, prof_end, 1, fused_counters(d->stream, d->batch_size));
+                                           prof_begin, prof_end, 1, fused_counters(d->stream, d->batch_size), d->is_signed ? 1 : 0);
             if (fe != cudaSuccess) return cuda_fail(fe, "fast_pass_kernel launch");
             if (launched > 0) return GPUNTT_B200_OK;
         }

@@ -126,7 +126,7 @@ def test_default_policy_launch_counts():
     """Default policy: 32-bit two-pass transforms are one launch at every batch size, 64-bit ones while the call is
     launch-bound (at most one strided tile per SM); results identical either way."""
     capi.tune(capi.TUNE_FUSED_PASSES, 1)
-    for bits, logn, batch, expect in ((32, 14, 600, 1), (64, 16, 2, 1), (64, 16, 300, 2), (64, 13, 8, 1)):
+    for bits, logn, batch, expect in ((32, 14, 600, 1), (64, 16, 2, 1), (64, 16, 300, 2), (64, 13, 8, 1), (64, 12, 2000, 1), (32, 17, 4, 1)):
         P = O.merge_params(logn, O.X_N_minus, bits)
         x = O.example_input(P.modulus, batch << logn, seed=batch)
         d = to_dev(x, bits)

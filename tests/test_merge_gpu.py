@@ -115,6 +115,41 @@ def test_golden_vectors_through_c_abi(golden):
 
 
 @pytest.mark.parametrize("bits", [64, 32])
+@pytest.mark.parametrize("logn,batch", [(10, 8), (13, 5), (14, 64), (16, 3), (17, 2)])
+def test_signed_variants_take_the_tuned_kernels(bits, logn, batch):
+    """Data32s/Data64s on the tuned kernels: the first forward round fixes negative inputs up as it loads, the last
+    inverse round centres its outputs (ntt.cu:481-489, 1178-1186 of the reference) -- no generic-kernel launches
+    (those would be a twiddle-prep kernel plus the passes)."""
+    P = O.merge_params(logn, O.X_N_plus, bits)
+    p = P.modulus
+    rng = np.random.default_rng(logn * 7 + bits)
+    mag = rng.integers(0, p // 2, size=batch << logn, dtype=np.int64)
+    sx = np.where(rng.integers(0, 2, size=mag.size) == 1, -mag, mag).astype(np.int64)
+    sx[:3] = (-(p // 2) + 1, -1, p // 2 - 1)
+    want = O.merge_ntt(O.reduce_signed(sx, p), P)
+    d = torch.from_numpy(sx if bits == 64 else sx.astype(np.int32)).cuda()
+    out = torch.zeros_like(d)
+    tab, itab = to_dev(P.fwd_br, bits), to_dev(P.inv_br, bits)
+    st = torch.cuda.current_stream().cuda_stream
+    capi.lib().gpuntt_b200_set_profiling(1)      # launch kinds: 0 = the generic path's twiddle-prep kernel
+    capi.profile_read()
+    capi.merge_ntt(in_ptr=d.data_ptr(), out_ptr=out.data_ptr(), table_ptr=tab.data_ptr(), n_power=logn, batch=batch,
+                   element_bits=bits, direction=capi.FORWARD, reduction_poly=O.X_N_plus, modulus=p, is_signed=True, stream=st)
+    torch.cuda.synchronize()
+    assert 0 not in [k for k, _ in capi.profile_read()], "signed forward fell back to the generic kernel"
+    assert (to_host(out, bits) == want).all()
+    back = torch.zeros_like(d)
+    capi.merge_ntt(in_ptr=out.data_ptr(), out_ptr=back.data_ptr(), table_ptr=itab.data_ptr(), n_power=logn, batch=batch,
+                   element_bits=bits, direction=capi.INVERSE, reduction_poly=O.X_N_plus, modulus=p, mod_inverse=P.n_inv,
+                   is_signed=True, stream=st)
+    torch.cuda.synchronize()
+    kinds = [k for k, _ in capi.profile_read()]
+    capi.lib().gpuntt_b200_set_profiling(0)
+    assert 0 not in kinds, "signed inverse fell back to the generic kernel"
+    assert (to_host_signed(back) == sx).all()
+
+
+@pytest.mark.parametrize("bits", [64, 32])
 @pytest.mark.parametrize("logn", [4, 12, 16])
 def test_signed_variants(bits, logn):
     """Data32s/Data64s: signed input on forward (test_merge_ntt.cu:184-341), centred output on inverse."""

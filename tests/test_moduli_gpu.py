@@ -77,7 +77,7 @@ LIMITS = [1 << 29, 1 << 33, (1 << 36) - 1, (1 << 36) + (1 << 30), (1 << 40) - 1,
 
 
 @pytest.mark.parametrize("limit", LIMITS)
-@pytest.mark.parametrize("logn,poly", [(16, O.X_N_minus), (16, O.X_N_plus), (13, O.X_N_minus)])
+@pytest.mark.parametrize("logn,poly", [(16, O.X_N_minus), (16, O.X_N_plus), (13, O.X_N_minus), (10, O.X_N_plus), (18, O.X_N_minus)])
 def test_modulus_ranges(limit, logn, poly):
     p = ntt_prime_below(limit, 2 << logn)
     P = custom_params(logn, poly, p)
@@ -89,11 +89,18 @@ def test_modulus_ranges(limit, logn, poly):
     want = O.merge_ntt(x, P)
     d = to_dev(x, 64)
     tab, itab = to_dev(P.fwd_br, 64), to_dev(P.inv_br, 64)
+    capi.lib().gpuntt_b200_set_profiling(1)      # launch kinds: 0 = the generic path's twiddle-prep kernel
+    capi.profile_read()
     capi.ntt(d, tab, p, logn, poly)
     torch.cuda.synchronize()
+    # every modulus the reference accepts (p < 2^62) stays on the tuned kernels: exact policy where the lazy ones do not apply
+    assert 0 not in [k for k, _ in capi.profile_read()], f"p={p} fell back to the generic kernel"
     assert (to_host(d, 64).reshape(batch, -1) == want).all(), f"forward mismatch p={p}"
     capi.intt(d, itab, p, P.n_inv, logn, poly)
     torch.cuda.synchronize()
+    kinds = [k for k, _ in capi.profile_read()]
+    capi.lib().gpuntt_b200_set_profiling(0)
+    assert 0 not in kinds, f"p={p} fell back to the generic kernel (inverse)"
     assert (to_host(d, 64).reshape(batch, -1) == x).all(), f"inverse mismatch p={p}"
     # the generic pass kernel with the same modulus
     capi.lib().gpuntt_b200_force_generic_path(1)
