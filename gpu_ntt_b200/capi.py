@@ -101,6 +101,9 @@ def lib():
         L.gpuntt_b200_force_generic_path.argtypes = [i]
         L.gpuntt_b200_example_input.restype = None
         L.gpuntt_b200_example_input.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]
+        for f in (L.gpuntt_b200_scatter_batch, L.gpuntt_b200_gather_batch):
+            f.restype = i
+            f.argtypes = [C.c_void_p, i, C.POINTER(C.c_void_p), C.POINTER(i), i, C.c_size_t, C.c_longlong, i, C.POINTER(C.c_void_p)]
         L.gpuntt_b200_tune.restype = None
         L.gpuntt_b200_tune.argtypes = [i, i]
         L.gpuntt_b200_set_profiling.restype = None

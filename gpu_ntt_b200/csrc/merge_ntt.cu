@@ -1267,6 +1267,58 @@ extern "C"
         return n;
     }
 
+    static int batch_copy(bool scatter, const void* one, int one_dev, void* const* many, const int* devices, int ndev, size_t poly_bytes,
+                          long long batch, int mod_count, void* const* streams)
+    {
+        if (!one || !many || !devices || ndev < 1 || batch < 0 || mod_count < 0) return fail(GPUNTT_B200_ERR_ARGUMENT, "bad scatter / gather arguments");
+        const long long unit = mod_count > 0 ? mod_count : 1;
+        if (batch % unit) return fail(GPUNTT_B200_ERR_ARGUMENT, "batch_size must be a multiple of mod_count");
+        const long long groups = batch / unit;
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (int g = 0; g < ndev; g++)
+        {
+            const long long lo = groups * g / ndev * unit, hi = groups * (g + 1) / ndev * unit;
+            if (hi == lo) continue;
+            if (!many[g]) return fail(GPUNTT_B200_ERR_ARGUMENT, "null slice pointer");
+            if (devices[g] != one_dev)
+            {
+                // peer access in both directions (an error here only means the copy is staged through the host)
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, devices[g], one_dev) == cudaSuccess && can)
+                {
+                    cudaSetDevice(devices[g]);
+                    if (cudaDeviceEnablePeerAccess(one_dev, 0) != cudaSuccess) cudaGetLastError();
+                    cudaSetDevice(one_dev);
+                    if (cudaDeviceEnablePeerAccess(devices[g], 0) != cudaSuccess) cudaGetLastError();
+                }
+            }
+            cudaSetDevice(devices[g]);
+            cudaStream_t st = streams ? (cudaStream_t) streams[g] : nullptr;
+            const unsigned char* whole = static_cast<const unsigned char*>(one) + (size_t) lo * poly_bytes;
+            cudaError_t e = scatter ? cudaMemcpyPeerAsync(many[g], devices[g], whole, one_dev, (size_t) (hi - lo) * poly_bytes, st)
+                                    : cudaMemcpyPeerAsync(const_cast<unsigned char*>(whole), one_dev, many[g], devices[g],
+                                                          (size_t) (hi - lo) * poly_bytes, st);
+            if (e != cudaSuccess)
+            {
+                cudaSetDevice(cur);
+                return cuda_fail(e, scatter ? "scatter_batch copy" : "gather_batch copy");
+            }
+        }
+        cudaSetDevice(cur);
+        return GPUNTT_B200_OK;
+    }
+    int gpuntt_b200_scatter_batch(const void* src, int src_device, void* const* dst, const int* devices, int ndev, size_t poly_bytes,
+                                  long long batch_size, int mod_count, void* const* streams)
+    {
+        return batch_copy(true, src, src_device, dst, devices, ndev, poly_bytes, batch_size, mod_count, streams);
+    }
+    int gpuntt_b200_gather_batch(void* dst, int dst_device, const void* const* src, const int* devices, int ndev, size_t poly_bytes,
+                                 long long batch_size, int mod_count, void* const* streams)
+    {
+        return batch_copy(false, dst, dst_device, const_cast<void* const*>(src), devices, ndev, poly_bytes, batch_size, mod_count, streams);
+    }
+
     void gpuntt_b200_example_input(uint32_t seed, uint64_t modulus, uint64_t count, uint64_t* host_out)
     {
         if (!host_out || modulus == 0) return;

@@ -31,3 +31,27 @@ def aggregate_rate(units_local: int, ms_local: float, dist=None, device=None) ->
     dist.all_reduce(u, op=dist.ReduceOp.SUM)
     ms, units = float(t.item()), int(u.item())
     return units / (ms * 1e-3), ms, units
+
+
+def _slices_call(fn, whole, whole_device, parts, devices, batch, mod_count, streams):
+    import ctypes as C
+    from . import capi
+    n = len(parts)
+    ptrs = (C.c_void_p * n)(*[p.data_ptr() for p in parts])
+    devs = (C.c_int * n)(*devices)
+    sts = None if streams is None else (C.c_void_p * n)(*[getattr(s, "cuda_stream", s) for s in streams])
+    poly_bytes = whole.numel() * whole.element_size() // batch
+    capi.check(fn(whole.data_ptr(), whole_device, ptrs, devs, n, poly_bytes, batch, mod_count, sts))
+
+
+def scatter_batch(src, parts, devices, mod_count: int = 0, streams=None) -> None:
+    """gpuntt_b200_scatter_batch on torch tensors: slice g of src ([batch, N] on one GPU) -> parts[g] on devices[g]
+    (batch_slice(g, len(parts), batch, mod_count) rows), peer copies over NVLink where available."""
+    from . import capi
+    _slices_call(capi.lib().gpuntt_b200_scatter_batch, src, src.device.index, parts, devices, src.shape[0], mod_count, streams)
+
+
+def gather_batch(dst, parts, devices, mod_count: int = 0, streams=None) -> None:
+    """gpuntt_b200_gather_batch: the reverse of scatter_batch."""
+    from . import capi
+    _slices_call(capi.lib().gpuntt_b200_gather_batch, dst, dst.device.index, parts, devices, dst.shape[0], mod_count, streams)

@@ -204,6 +204,18 @@ void gpuntt_b200_force_generic_path(int on);
 #define GPUNTT_B200_TUNE_4STEP_MODULUS_CACHE 4
 void gpuntt_b200_tune(int knob, int value);
 
+/* Batch-slice helpers for callers whose whole batch lives on ONE GPU: device g of ndev owns the
+ * contiguous polynomials [groups * g / ndev, groups * (g + 1) / ndev) * unit with unit = max(mod_count, 1) and
+ * groups = batch_size / unit (slice boundaries fall on multiples of mod_count, so every device can use the same modulus
+ * array -- polynomial b uses modulus b % mod_count, ntt.cu:613 of the reference).  scatter copies slice g of the
+ * [batch_size][poly_bytes] array `src` (on src_device) to dst[g] (on devices[g]); gather is the reverse.  The copies are
+ * cudaMemcpyPeerAsync on streams[g] (a stream of devices[g]; NULL array = default streams): NVLink / NVSwitch when peer
+ * access is available (it is enabled on first use), staged through the host otherwise.  Nothing synchronises. */
+int gpuntt_b200_scatter_batch(const void* src, int src_device, void* const* dst, const int* devices, int ndev,
+                              size_t poly_bytes, long long batch_size, int mod_count, void* const* streams);
+int gpuntt_b200_gather_batch(void* dst, int dst_device, const void* const* src, const int* devices, int ndev,
+                             size_t poly_bytes, long long batch_size, int mod_count, void* const* streams);
+
 /* The input recipe of the reference's example drivers (example/ntt_merge/test_merge_ntt.cu:70-85,
  * test_4step_ntt.cu:48-57): std::mt19937 gen(seed); std::uniform_int_distribution<uint64_t> dis(0, modulus - 1);
  * count values, in order, into the HOST array out (uint64_t; callers narrow for 32-bit data).  Used by examples/,
