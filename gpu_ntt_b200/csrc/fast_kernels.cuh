@@ -251,8 +251,8 @@ namespace gpuntt_b200
         // LB == 0: the item is one or more whole 128-byte rows; chunks are 16-byte vectors.
         static_assert(LB == 0 || LB >= S::CB, "round must start at bit 0 or on a row boundary");
         constexpr int NI = TS ? (ITEMS / kConsumers) : 1;
-        static_assert(!TS || (S::STRIDED && !S::INV && LB == S::C && R >= 1 && S::D >= 5 && sizeof(T) == 8 && ITEMS % kConsumers == 0),
-                      "transposed store: lowest round of a forward strided 64-bit pass");
+        static_assert(!TS || (S::STRIDED && LB >= S::C && R >= 1 && S::D >= 5 && sizeof(T) == 8 && ITEMS % kConsumers == 0),
+                      "transposed store: last executed round of a strided 64-bit pass");
         T keep[NI][TS ? E : 1];
 #pragma unroll(TS ? NI : 1)
         for (int item = ctid, ii = 0; item < ITEMS; item += kConsumers, ii++)
@@ -462,14 +462,31 @@ namespace gpuntt_b200
             {
                 const int item = ctid + ii * kConsumers;
                 const int l_base = ((item >> LB) << (LB + R)) | (item & ((1 << LB) - 1));
-                const int col = l_base & ((1 << S::C) - 1), row0 = l_base >> S::C; // row0 has zeros in its low R bits
-#pragma unroll
-                for (int a = 0; a < E; a += 2)
+                const int col = l_base & ((1 << S::C) - 1), row0 = l_base >> S::C; // row0 has zeros in the R bits of this round
+                if constexpr (LB == S::C)
                 {
-                    const int row = row0 | a;
-                    const int line = ((row >> 4) << S::C) + col;
-                    const int off = (line << 7) + (((((row & 15) >> 1) ^ (col & 7))) << 4);
-                    *reinterpret_cast<ulonglong2*>(buf + off) = make_ulonglong2(keep[ii][a], keep[ii][a + 1]);
+                    // the round on the lowest row bits (forward passes): consecutive rows, one vector store per pair
+#pragma unroll
+                    for (int a = 0; a < E; a += 2)
+                    {
+                        const int row = row0 | a;
+                        const int line = ((row >> 4) << S::C) + col;
+                        const int off = (line << 7) + (((((row & 15) >> 1) ^ (col & 7))) << 4);
+                        *reinterpret_cast<ulonglong2*>(buf + off) = make_ulonglong2(keep[ii][a], keep[ii][a + 1]);
+                    }
+                }
+                else
+                {
+                    // a round on higher row bits (the last round of an INVERSE pass): rows 2^(LB - C) apart, one 8-byte store
+                    // each (two-way bank conflicts between columns j and j + 8; 16 stores per thread and tile)
+#pragma unroll
+                    for (int a = 0; a < E; a++)
+                    {
+                        const int row = row0 | (a << (LB - S::C));
+                        const int line = ((row >> 4) << S::C) + col;
+                        const int off = (line << 7) + (((((row & 15) >> 1) ^ (col & 7))) << 4) + ((row & 1) << 3);
+                        *reinterpret_cast<T*>(buf + off) = keep[ii][a];
+                    }
                 }
             }
         }
@@ -569,9 +586,9 @@ namespace gpuntt_b200
             if constexpr (S::STRIDED)
             {
                 if (a.last)
-                    fast_round<S, S::R1, S::LB1, S::G1, true, false, W1>(buf, tw1, M, tid, ninv, wtile, a.lo, 1, false, bar, sout);
+                    fast_round<S, S::R1, S::LB1, S::G1, true, false, W1, TS>(buf, tw1, M, tid, ninv, wtile, a.lo, 1, false, bar, sout);
                 else
-                    fast_round<S, S::R1, S::LB1, S::G1, false, false, W1>(buf, tw1, M, tid, ninv, wtile, a.lo);
+                    fast_round<S, S::R1, S::LB1, S::G1, false, false, W1, TS>(buf, tw1, M, tid, ninv, wtile, a.lo, 1, false, bar);
             }
             else if constexpr (S::NT > 0)
             {

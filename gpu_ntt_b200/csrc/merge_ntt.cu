@@ -621,7 +621,7 @@ namespace gpuntt_b200
     cudaError_t fast_fourstep_inverse(const uint64_t* rows_in, uint64_t* work, uint64_t* dst, const uint64_t* n1_table,
                                       const uint64_t* n2_table, const uint64_t* w_table, void* w_pairs_ws, uint64_t p, uint64_t ninv,
                                       int n_power, int lg1, int lg2, int batch, cudaStream_t st, int* launched,
-                                      void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t));
+                                      void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t), int transposed_src = 0);
     cudaError_t fast_fourstep_columns(const uint64_t* in, uint64_t* out, const uint64_t* n1_table, const uint64_t* w_table,
                                       void* w_pairs_ws, uint64_t p, int n_power, int lg1, int lg2, int batch, cudaStream_t st,
                                       int* launched, void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t), int w_lazy,

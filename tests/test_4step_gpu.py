@@ -202,13 +202,48 @@ def test_4step_transposed_and_transpose_kernel_paths_agree():
         for mode in (1, 0):
             capi.tune(3, mode)
             d = to_dev(x, bits)
+            capi.lib().gpuntt_b200_set_profiling(1)       # launch kinds: 9 = transpose_kernel
+            capi.profile_read()
             capi.fourstep_ntt(d.view(batch, P.n), t1, t2, W, P.modulus, logn)
             torch.cuda.synchronize()
-            outs.append((to_host(d, bits), capi.lib().gpuntt_b200_last_launch_count()))
+            outs.append((to_host(d, bits), [k for k, _ in capi.profile_read()]))
     finally:
         capi.tune(3, 1)
+        capi.lib().gpuntt_b200_set_profiling(0)
     assert (outs[0][0] == want).all() and (outs[1][0] == want).all()
-    assert outs[0][1] == 4 and outs[1][1] > 4
+    assert 9 not in outs[0][1] and 9 in outs[1][1]
+
+
+def test_4step_inverse_fused_contract_runs_without_a_transpose_kernel():
+    """Fused-contract inverse: the size-n1 transforms are a strided pass over the caller's array whose transposing store
+    writes the n2 x n1 matrix the remaining passes expect (no launch of kind 9); with the knob off the transpose kernel
+    runs first.  Both equal the oracle, in place and out of place."""
+    bits, batch = 64, 2
+    for logn in (17, 20, 22, 23):
+        P = O.fourstep_params(logn, O.X_N_minus, bits)
+        z = O.example_input(P.modulus, batch * P.n, seed=logn).reshape(batch, P.n)
+        want = _threaded(O.fourstep_intt, z, P)
+        it1, it2, iW = tables(P, bits, True)
+        try:
+            for mode in (1, 0):
+                capi.tune(3, mode)
+                capi.lib().gpuntt_b200_set_profiling(1)
+                capi.profile_read()
+                d = to_dev(z, bits)
+                out = torch.zeros_like(d)
+                capi.fourstep_ntt(d.view(batch, P.n), it1, it2, iW, P.modulus, logn, direction=capi.INVERSE, mod_inverse=P.n_inv,
+                                  out=out.view(batch, P.n))
+                torch.cuda.synchronize()
+                kinds = [k for k, _ in capi.profile_read()]
+                assert (to_host(out, bits) == want).all(), (logn, mode)
+                assert (to_host(d, bits) == z).all(), "out-of-place call modified its input"
+                assert (9 in kinds) == (mode == 0), (logn, mode, kinds)
+                capi.fourstep_ntt(d.view(batch, P.n), it1, it2, iW, P.modulus, logn, direction=capi.INVERSE, mod_inverse=P.n_inv)
+                torch.cuda.synchronize()
+                assert (to_host(d, bits) == want).all(), (logn, mode, "in place")
+        finally:
+            capi.tune(3, 1)
+            capi.lib().gpuntt_b200_set_profiling(0)
 
 
 def test_4step_errors():
