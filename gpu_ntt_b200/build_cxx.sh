@@ -9,7 +9,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -I$ROOT/include -I$HERE/csrc"
 OBJ="$HERE/lib/obj"
 mkdir -p "$OBJ"
-for f in csrc/merge_ntt csrc/merge_fast csrc/merge_fast_rns csrc/merge_fast_4step csrc/merge_fused cxx/common cxx/nttparameters cxx/ntt_cpu cxx/ntt_api cxx/ntt_4step_api; do
+for f in csrc/merge_ntt csrc/merge_fast csrc/merge_fast_rns csrc/merge_fast_4step csrc/merge_fused csrc/merge_wcol cxx/common cxx/nttparameters cxx/ntt_cpu cxx/ntt_api cxx/ntt_4step_api; do
     o="$OBJ/$(basename $f).o"
     if [ ! -f "$o" ] || [ "$HERE/$f.cu" -nt "$o" ] || [ -n "$(find "$HERE/csrc" "$ROOT/include" -newer "$o" -name '*.*h' -o -newer "$o" -name '*.inl' | head -1)" ]; then
         $NVCC $FLAGS -c -o "$o" "$HERE/$f.cu" &

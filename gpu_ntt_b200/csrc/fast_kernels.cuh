@@ -232,7 +232,9 @@ namespace gpuntt_b200
     // SWIZZLE_128B tile -- so a thread's consecutive rows are one vector store per pair and the eight lanes of a quarter
     // warp (eight columns) hit eight different bank groups.  This is how the 4-step column phase writes its output as the
     // n2 x n1 matrix without a transpose kernel.
-    template <typename S, int R, int LB, int G, bool FINAL, bool TRIV = false, bool WMUL = false, bool TS = false>
+    // WL: the (w, w') pairs of the twiddle-matrix product sit in SHARED memory in tile order (merge_wcol.cu passes lo = C so that
+    // the pair of local element l is entry l): plain loads instead of __ldg.
+    template <typename S, int R, int LB, int G, bool FINAL, bool TRIV = false, bool WMUL = false, bool TS = false, bool WL = false>
     __device__ __forceinline__ void fast_round(unsigned char* buf, const Twiddle<typename S::T>* __restrict__ tws,
                                                const typename ModOf<S>::type& M, int ctid,
                                                const Twiddle<typename S::T>& ninv,
@@ -314,14 +316,20 @@ namespace gpuntt_b200
                     static_assert(!WMUL || (S::STRIDED && LB >= S::C), "the twiddle-matrix product belongs to strided passes");
                     // offset of element a: row (l >> C) * 2^lo + column (l & (2^C - 1)); a only moves the row
                     const Twiddle<T>* wp = wtile + (((long long) (l_base >> S::C)) << lo) + (l_base & ((1 << S::C) - 1));
-                    constexpr int WB = E < 8 ? E : 8;
+                    constexpr int WB = WL ? (E < 4 ? E : 4) : (E < 8 ? E : 8); // (shared-memory pairs: short latency, fewer registers)
 #pragma unroll
                     for (int h = 0; h < E; h += WB)
                     {
                         ulonglong2 v[WB];
 #pragma unroll
                         for (int j = 0; j < WB; j++)
-                            v[j] = __ldg(reinterpret_cast<const ulonglong2*>(wp + (((long long) (h + j) << (LB - S::C)) << lo)));
+                        {
+                            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(wp + (((long long) (h + j) << (LB - S::C)) << lo));
+                            if constexpr (WL)
+                                v[j] = *src;
+                            else
+                                v[j] = __ldg(src);
+                        }
 #pragma unroll
                         for (int j = 0; j < WB; j++)
                         {
@@ -534,7 +542,7 @@ namespace gpuntt_b200
     // the transform (4-step row phase on the transposed layout) canonicalises as well.
     // 4-step twiddle-matrix product: forward = epilogue of the last round, inverse = prologue of the first executed
     // round; either way that is the low round when there are two.
-    template <typename S, bool WMUL, bool SFIN = false, bool TS = false>
+    template <typename S, bool WMUL, bool SFIN = false, bool TS = false, bool WL = false>
     __device__ __forceinline__ void tile_rounds(unsigned char* buf, const Twiddle<typename S::T>* tw1, const Twiddle<typename S::T>* tw2,
                                                 const Twiddle<typename S::T>* tw3, const typename ModOf<S>::type& M, int tid,
                                                 const Twiddle<typename S::T>& ninv, const Twiddle<typename S::T>* wtile,
@@ -553,17 +561,17 @@ namespace gpuntt_b200
             if constexpr (S::STRIDED && S::POL == 2 && S::G1 == 1)
             {
                 if (triv)
-                    fast_round<S, S::R1, S::LB1, S::G1, FIN1, true, W1, TS1>(buf, tw1, M, tid, ninv, wtile, a.lo,
+                    fast_round<S, S::R1, S::LB1, S::G1, FIN1, true, W1, TS1, WL>(buf, tw1, M, tid, ninv, wtile, a.lo,
                                                                               a.in_bound > 1 ? a.in_bound : 1, a.w_lazy != 0, bar, sin);
                 else
-                    fast_round<S, S::R1, S::LB1, S::G1, FIN1, false, W1, TS1>(buf, tw1, M, tid, ninv, wtile, a.lo, 1, a.w_lazy != 0, bar, sin);
+                    fast_round<S, S::R1, S::LB1, S::G1, FIN1, false, W1, TS1, WL>(buf, tw1, M, tid, ninv, wtile, a.lo, 1, a.w_lazy != 0, bar, sin);
             }
             else
                 fast_round<S, S::R1, S::LB1, S::G1, FIN1>(buf, tw1, M, tid, ninv, nullptr, 0, 1, false, bar, sin);
             if constexpr (S::R2 > 0)
             {
                 consumer_sync(bar);
-                fast_round<S, S::R2, S::LB2, S::G2, FIN2, false, W2, TS2>(buf, tw2, M, tid, ninv, wtile, a.lo, 1, a.w_lazy != 0, bar);
+                fast_round<S, S::R2, S::LB2, S::G2, FIN2, false, W2, TS2, WL>(buf, tw2, M, tid, ninv, wtile, a.lo, 1, a.w_lazy != 0, bar);
             }
             if constexpr (S::R3 > 0)
             {

@@ -273,24 +273,6 @@ template <typename T> static int fourstep_execute_t(const gpuntt_b200_4step_desc
         // T = n2 rows of n1 (the reference contract passes it; the fused contract passes its transpose)
         const T* src = in;
         bool inverse_done = false;
-        if constexpr (sizeof(T) == 8)
-        {
-            // fused contract on the tuned kernels without a transpose kernel: the size-n1 transforms run as a strided pass
-            // over the caller's array and its transposing store produces the n2 x n1 matrix in the scratch buffer
-            if (fused && !rns && !g_force_generic.load() && g_fourstep_transposed.load() && in != reinterpret_cast<const T*>(ws))
-            {
-                void* pairs = nullptr;
-                cudaError_t we = get_workspace(d->stream, 6, (size_t) N * sizeof(Twiddle<T>), &pairs);
-                if (we != cudaSuccess) return cuda_fail(we, "4-step twiddle-pair workspace allocation");
-                int launched = 0;
-                we = fast_fourstep_inverse(reinterpret_cast<const uint64_t*>(in), reinterpret_cast<uint64_t*>(ws), reinterpret_cast<uint64_t*>(out),
-                                           reinterpret_cast<const uint64_t*>(d->n1_table), reinterpret_cast<const uint64_t*>(d->n2_table),
-                                           reinterpret_cast<const uint64_t*>(d->w_table), pairs, (uint64_t) d->modulus_value,
-                                           (uint64_t) d->mod_inverse_value, n, lg1, lg2, batch, st, &launched, prof_begin, prof_end, 1);
-                if (we != cudaSuccess) return cuda_fail(we, "fast 4-step inverse launch");
-                if (launched > 0) return GPUNTT_B200_OK;
-            }
-        }
         if (fused)
         {
             e = launch_transpose<T>(in, ws, n2, n1, N, batch, st, 9);

@@ -20,6 +20,10 @@ namespace gpuntt_b200
         out[i] = Twiddle<uint64_t>{v, shoup_companion_mu(v, p, mu, pbits)};
     }
 
+    cudaError_t fourstep_columns_resident_pairs(const FastArgs<uint64_t>& a, int lg1, cudaStream_t st); // merge_wcol.cu
+    static std::atomic<int> g_resident_pairs{1};
+    void fourstep_set_resident_pairs(int on) { g_resident_pairs.store(on ? 1 : 0); }
+
     // Forward 4-step column phase on the tuned strided kernel: the first lg1 stages of a size-2^n transform with the
     // n1 table (rows 2^lg2 elements apart), then every element times W[offset] (pairs built into w_pairs_ws, N
     // entries), canonical outputs.  Single modulus, 64-bit, F60 moduli; *launched = 0 when not covered.
@@ -62,7 +66,16 @@ namespace gpuntt_b200
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         prof_begin(1, st);
-        if (transposed) // the pass writes the n2 x n1 matrix (every column transform becomes a contiguous row)
+        bool resident = false;
+        if (transposed && g_resident_pairs.load())
+        {
+            // position-major kernel with the pairs of a tile position resident in shared memory (merge_wcol.cu)
+            e = fourstep_columns_resident_pairs(a, lg1, st);
+            resident = e != cudaErrorNotSupported; // (not supported: the per-tile kernel below)
+        }
+        if (resident)
+            ;
+        else if (transposed) // the pass writes the n2 x n1 matrix (every column transform becomes a contiguous row)
             switch (lg1)
             {
                 case 5: e = launch_fast<Shape<T, false, 2, true, 3, 2, 12, 0>, true, false, void, false, true>(a, st); break;
@@ -182,12 +195,11 @@ namespace gpuntt_b200
     cudaError_t fast_fourstep_inverse(const uint64_t* rows_in, uint64_t* work, uint64_t* dst, const uint64_t* n1_table,
                                       const uint64_t* n2_table, const uint64_t* w_table, void* w_pairs_ws, uint64_t p, uint64_t ninv,
                                       int n_power, int lg1, int lg2, int batch, cudaStream_t st, int* launched,
-                                      void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t), int transposed_src)
+                                      void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t))
     {
         using T = uint64_t;
         *launched = 0;
         if (lg1 < 5 || lg1 > 8 || n_power != lg1 + lg2 || n_power < 12) return cudaSuccess;
-        if (transposed_src && (rows_in == work || lg2 < 12 - lg1)) return cudaSuccess;
         if (((long long) batch << lg2) >= (1LL << 31)) return cudaSuccess;
         if (!(p < kFastModulusLimit) || p < 5) return cudaSuccess;
         if ((reinterpret_cast<uintptr_t>(rows_in) | reinterpret_cast<uintptr_t>(work) | reinterpret_cast<uintptr_t>(dst)) & 15) return cudaSuccess;
@@ -224,36 +236,6 @@ namespace gpuntt_b200
         prof_end(st);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         int kind = 1;
-        if (transposed_src)
-        {
-            // `rows_in` is the TRANSPOSE of the n2 x n1 matrix (n1 rows of n2: what the fused contract hands over).  The
-            // size-n1 transforms then run along its rows' index -- a strided pass over the top lg1 index bits -- and the
-            // transposing store writes the n2 x n1 matrix the remaining passes expect: no transpose kernel.
-            FastArgs<T> s = a;
-            s.in = rows_in;
-            s.out = work;
-            s.table = n1_table;
-            s.n = n_power;
-            s.lo = lg2;
-            s.first = 1;
-            s.last = 0;
-            s.batch = batch;
-            s.work = (long long) batch << (lg2 - (12 - lg1));
-            s.rr = lg2 > 10 ? 1 : 0;
-            if (((long long) batch << lg1) >= (1LL << 31)) return cudaSuccess;
-            prof_begin(kind++, st);
-            switch (lg1)
-            {
-                case 5: e = launch_fast<Shape<T, true, 1, true, 3, 2, 12, 0>, false, false, void, false, true>(s, st); break;
-                case 6: e = launch_fast<Shape<T, true, 1, true, 3, 3, 12, 0>, false, false, void, false, true>(s, st); break;
-                case 7: e = launch_fast<Shape<T, true, 1, true, 4, 3, 12, 0>, false, false, void, false, true>(s, st); break;
-                default: e = launch_fast<Shape<T, true, 1, true, 4, 4, 12, 0>, false, false, void, false, true>(s, st); break;
-            }
-            prof_end(st);
-            if (e == cudaErrorNotSupported) return cudaSuccess;
-            if (e != cudaSuccess) return e;
-        }
-        else
         {
             // row phase: the array as (batch * N / 2048) chunks of 2048 elements, transforms of 2^lg1 inside
             FastArgs<T> s = a;

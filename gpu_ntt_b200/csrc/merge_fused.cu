@@ -39,6 +39,7 @@ namespace gpuntt_b200
         int nranges;          // contiguous ranges per polynomial
         int ngroups;          // contiguous tile groups = ceil(batch / polynomials per tile)
         long long ticket_off; // counters[ticket_off]: CTAs that have finished (the last one zeroes the counters)
+        int g_slot;           // RNS: CTAs per modulus slot (grid = mod_count * g_slot)
     };
 
     __device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity)
@@ -125,6 +126,9 @@ namespace gpuntt_b200
         int next_t;           // next tile index to be claimed by a consumer group
         int bcast[kFusedGroups][2];
         int is_last;
+        // RNS: this CTA's modulus slot
+        unsigned long long seg_p, seg_mu, seg_ninv_w, seg_ninv_wq;
+        int seg_pbits, seg_mi;
     };
 
     template <typename SS, typename SC> struct FusedSmem
@@ -141,10 +145,13 @@ namespace gpuntt_b200
         return v;
     }
 
-    template <typename SS, typename SC>
-    __global__ void __launch_bounds__(kFusedThreads, 1)
-        fused2_kernel(const FusedArgs<typename SS::T> f, const __grid_constant__ CUtensorMap mapA_in, const __grid_constant__ CUtensorMap mapA_out,
-                      const __grid_constant__ CUtensorMap mapB)
+    // RNS (polynomial b uses modulus slot b % mod_count, ntt.cu:613-619 of the reference): the CTAs are partitioned among the
+    // modulus slots (f.g_slot CTAs each), so a CTA has ONE modulus, one strided twiddle set and one contiguous twiddle set
+    // like in the single-modulus form; f.s.batch is then the number of polynomials PER SLOT, counters are indexed by the
+    // polynomial's position in the caller's array, contiguous tiles come from the 4-D map {row, rows, slot, polynomial}.
+    template <typename SS, typename SC, bool RNS>
+    __device__ __forceinline__ void fused2_body(const FusedArgs<typename SS::T>& f, const CUtensorMap& mapA_in, const CUtensorMap& mapA_out,
+                                                const CUtensorMap& mapB)
     {
         using T = typename SS::T;
         static_assert(SS::STRIDED && !SC::STRIDED && SS::TILE_SMEM == SC::TILE_SMEM && SS::INV == SC::INV, "one strided and one contiguous pass");
@@ -161,19 +168,22 @@ namespace gpuntt_b200
         const int tid = threadIdx.x;
         const int batch = f.s.batch, n = f.s.n;
         const int fwd = f.fwd, lag = f.lag, tpp_log = f.tpp_log;
+        const int mslot = RNS ? (int) blockIdx.x / f.g_slot : 0;          // modulus slot of this CTA
+        const int cta = RNS ? (int) blockIdx.x % f.g_slot : (int) blockIdx.x; // index among the CTAs of the slot
+        const int mc = RNS ? f.s.mod_count : 1;
 
         // ---- this CTA's shares
         FusedCursor cur;
         cur.s_step = f.g_str;
-        cur.s_next = (int) blockIdx.x < f.g_str ? (long long) blockIdx.x : 0;
-        cur.s_end = (int) blockIdx.x < f.g_str ? ((long long) batch << tpp_log) : 0;
+        cur.s_next = cta < f.g_str ? (long long) cta : 0;
+        cur.s_end = cta < f.g_str ? ((long long) batch << tpp_log) : 0;
         int range = 0;
         cur.q_next = 0;
         cur.q_end = 0;
         cur.q_step = 1;
-        if ((int) blockIdx.x >= f.c_off)
+        if (cta >= f.c_off)
         {
-            const int cb = (int) blockIdx.x - f.c_off;
+            const int cb = cta - f.c_off;
             const int big = f.con_extra * (f.con_k + 1);
             int kk, j;
             if (cb < big)
@@ -218,10 +228,38 @@ namespace gpuntt_b200
             }
             ctl->next_t = 0;
             ctl->is_last = 0;
+            if constexpr (RNS)
+            {
+                const int mi = f.s.mod_order ? f.s.mod_order[mslot] : mslot;
+                const T p = f.s.mod_dev[3 * mi];
+                ctl->seg_mi = mi;
+                ctl->seg_p = (unsigned long long) p;
+                if constexpr (sizeof(T) == 8)
+                {
+                    ctl->seg_pbits = 64 - __clzll((long long) p);
+                    ctl->seg_mu = (p & (p - 1)) ? recip_mu64(p, ctl->seg_pbits) : ~0ull;
+                }
+                else
+                {
+                    ctl->seg_pbits = 32 - __clz((int) p);
+                    ctl->seg_mu = ~0ull / (unsigned long long) p;
+                }
+                const T nv = SS::INV ? f.s.ninv_dev[mi] : T(0);
+                ctl->seg_ninv_w = (unsigned long long) nv;
+                if constexpr (sizeof(T) == 8)
+                    ctl->seg_ninv_wq = SS::INV ? shoup_companion_mu(nv, p, ctl->seg_mu, ctl->seg_pbits) : 0ull;
+                else
+                    ctl->seg_ninv_wq = SS::INV ? (unsigned long long) shoup_companion(nv, p) : 0ull;
+            }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             fence_async();
         }
         __syncthreads();
+        const T seg_p = RNS ? (T) ctl->seg_p : f.s.p;
+        const uint64_t seg_mu = RNS ? ctl->seg_mu : f.s.mu;
+        const int seg_pbits = RNS ? ctl->seg_pbits : f.s.pbits;
+        const T* tabS = RNS ? f.s.table + ((size_t) ctl->seg_mi << n) : f.s.table;
+        const T* tabC = RNS ? f.c.table + ((size_t) ctl->seg_mi << n) : f.c.table;
 
         if (tid == kFusedConsumers)
         {
@@ -243,18 +281,18 @@ namespace gpuntt_b200
                         long long p1 = p0 + (1 << SC::NPLOG);
                         if (p1 > batch) p1 = batch;
                         const unsigned need = 1u << tpp_log;
-                        if (SC::NPLOG == 1 && p1 - p0 == 2)
+                        if (!RNS && SC::NPLOG == 1 && p1 - p0 == 2)
                         {
                             const unsigned long long want = ((unsigned long long) need << 32) | need;
                             while (ld_acquire64(f.counters + p0) != want) __nanosleep(64);
                         }
                         else
                             for (long long p = p0; p < p1; p++)
-                                while (ld_acquire(f.counters + p) != need) __nanosleep(64);
+                                while (ld_acquire(f.counters + p * mc + mslot) != need) __nanosleep(64);
                     }
                     else
                     {
-                        const unsigned* c = f.counters + (tl.id >> tpp_log);
+                        const unsigned* c = f.counters + (tl.id >> tpp_log) * mc + mslot;
                         while (ld_acquire(c) != (unsigned) f.nranges) __nanosleep(64);
                     }
                     asm volatile("fence.proxy.async.global;" ::: "memory"); // the bulk read below is ordered after the acquire loads
@@ -266,9 +304,11 @@ namespace gpuntt_b200
                 const CUtensorMap* mp = second ? &mapB : &mapA_in;
                 if (tl.kind == 0)
                 {
-                    const long long poly = tl.id >> tpp_log, cc = tl.id & ((1LL << tpp_log) - 1);
+                    const long long poly = (tl.id >> tpp_log) * mc + mslot, cc = tl.id & ((1LL << tpp_log) - 1);
                     tma_load_3d(dst, mp, 0, (int) (cc << (SS::C - SS::CB)), (int) (poly << (n - f.s.lo)), bar);
                 }
+                else if constexpr (RNS)
+                    tma_load_4d(dst, mp, 0, range << (SC::KC - SC::CB), mslot, (int) (tl.id << SC::NPLOG), bar);
                 else
                     tma_load_3d(dst, mp, 0, range << (SC::KC - SC::CB), (int) (tl.id << SC::NPLOG), bar);
             }
@@ -288,9 +328,11 @@ namespace gpuntt_b200
                 const CUtensorMap* mp = second ? &mapB : &mapA_out;
                 if (tl.kind == 0)
                 {
-                    const long long poly = tl.id >> tpp_log, cc = tl.id & ((1LL << tpp_log) - 1);
+                    const long long poly = (tl.id >> tpp_log) * mc + mslot, cc = tl.id & ((1LL << tpp_log) - 1);
                     tma_store_3d(mp, 0, (int) (cc << (SS::C - SS::CB)), (int) (poly << (n - f.s.lo)), src);
                 }
+                else if constexpr (RNS)
+                    tma_store_4d(mp, 0, range << (SC::KC - SC::CB), mslot, (int) (tl.id << SC::NPLOG), src);
                 else
                     tma_store_3d(mp, 0, range << (SC::KC - SC::CB), (int) (tl.id << SC::NPLOG), src);
                 bulk_commit();
@@ -302,12 +344,12 @@ namespace gpuntt_b200
                     // makes the writes visible to this thread, the release publishes them
                     bulk_wait0();
                     if (tl.kind == 0)
-                        red_release_add(f.counters + (tl.id >> tpp_log), 1u);
+                        red_release_add(f.counters + (tl.id >> tpp_log) * mc + mslot, 1u);
                     else
                     {
                         long long p0 = tl.id << SC::NPLOG, p1 = p0 + (1 << SC::NPLOG);
                         if (p1 > batch) p1 = batch;
-                        for (long long p = p0; p < p1; p++) red_release_add(f.counters + p, 1u);
+                        for (long long p = p0; p < p1; p++) red_release_add(f.counters + p * mc + mslot, 1u);
                     }
                 }
             }
@@ -317,12 +359,12 @@ namespace gpuntt_b200
         {
             // =================== consumer groups ===================
             const int g = tid / kConsumers, ctid = tid % kConsumers;
-            typename ModOf<SS>::type MS(f.s.p);
-            typename ModOf<SC>::type MC(f.c.p);
-            const Twiddle<T> ninv{f.s.ninv_w, f.s.ninv_wq};
-            const bool triv = !SS::INV && !f.s.plus && f.s.first && (f.s.lo + SS::D == n) && f.s.table[0] == T(1);
-            if (doS) build_twiddles<SS>(twS, f.s.table, 0, n, f.s.n_tw, f.s.lo, f.s.plus, f.s.p, f.s.mu, f.s.pbits, tid, kFusedConsumers);
-            if (doC) build_twiddles<SC>(twC, f.c.table, range, n, f.c.n_tw, 0, f.c.plus, f.c.p, f.c.mu, f.c.pbits, tid, kFusedConsumers);
+            typename ModOf<SS>::type MS(seg_p);
+            typename ModOf<SC>::type MC(seg_p);
+            const Twiddle<T> ninv = RNS ? Twiddle<T>{(T) ctl->seg_ninv_w, (T) ctl->seg_ninv_wq} : Twiddle<T>{f.s.ninv_w, f.s.ninv_wq};
+            const bool triv = !SS::INV && !f.s.plus && f.s.first && (f.s.lo + SS::D == n) && tabS[0] == T(1);
+            if (doS) build_twiddles<SS>(twS, tabS, 0, n, f.s.n_tw, f.s.lo, f.s.plus, seg_p, seg_mu, seg_pbits, tid, kFusedConsumers);
+            if (doC) build_twiddles<SC>(twC, tabC, range, n, f.c.n_tw, 0, f.c.plus, seg_p, seg_mu, seg_pbits, tid, kFusedConsumers);
             asm volatile("bar.sync 3, %0;" ::"n"(kFusedConsumers) : "memory");
             // tile claims run one ahead: the leader takes the NEXT index before the group starts on the current tile, so the
             // shared-memory atomic and its broadcast are off the critical path
@@ -356,8 +398,39 @@ namespace gpuntt_b200
         __syncthreads();
         if (ctl->is_last)
         {
-            for (int i = tid; i < batch; i += kFusedThreads) f.counters[i] = 0u;
+            for (long long i = tid; i < (long long) batch * mc; i += kFusedThreads) f.counters[i] = 0u;
             if (tid == 0) f.counters[f.ticket_off] = 0u;
+        }
+    }
+
+    template <typename SS, typename SC>
+    __global__ void __launch_bounds__(kFusedThreads, 1)
+        fused2_kernel(const FusedArgs<typename SS::T> f, const __grid_constant__ CUtensorMap mapA_in, const __grid_constant__ CUtensorMap mapA_out,
+                      const __grid_constant__ CUtensorMap mapB)
+    {
+        fused2_body<SS, SC, false>(f, mapA_in, mapA_out, mapB);
+    }
+
+    // RNS calls: the moduli live on the device, so the arithmetic policy is chosen HERE, per CTA, from the CTA's own modulus
+    // (SSL / SCL: the lazy-policy pair of passes, SSX / SCX: the exact pair; both bodies are in the kernel).
+    template <typename SSL, typename SCL, typename SSX, typename SCX>
+    __global__ void __launch_bounds__(kFusedThreads, 1)
+        fused2_rns_kernel(const FusedArgs<typename SSL::T> f, const __grid_constant__ CUtensorMap mapA_in,
+                          const __grid_constant__ CUtensorMap mapA_out, const __grid_constant__ CUtensorMap mapB)
+    {
+        using T = typename SSL::T;
+        static_assert(FusedSmem<SSL, SCL>::BYTES == FusedSmem<SSX, SCX>::BYTES, "same pass shapes, two policies");
+        if constexpr (std::is_same<SSL, SSX>::value)
+            fused2_body<SSL, SCL, true>(f, mapA_in, mapA_out, mapB);
+        else
+        {
+            const int mslot = (int) blockIdx.x / f.g_slot;
+            const T p = f.s.mod_dev[3 * (f.s.mod_order ? f.s.mod_order[mslot] : mslot)];
+            const bool lazy_ok = SSL::INV ? ((uint64_t) p < kFastModulusLimit) : ((uint64_t) p >= kF60ModulusMin && (uint64_t) p < kF60ModulusLimit);
+            if (lazy_ok)
+                fused2_body<SSL, SCL, true>(f, mapA_in, mapA_out, mapB);
+            else
+                fused2_body<SSX, SCX, true>(f, mapA_in, mapA_out, mapB);
         }
     }
 

@@ -621,7 +621,7 @@ namespace gpuntt_b200
     cudaError_t fast_fourstep_inverse(const uint64_t* rows_in, uint64_t* work, uint64_t* dst, const uint64_t* n1_table,
                                       const uint64_t* n2_table, const uint64_t* w_table, void* w_pairs_ws, uint64_t p, uint64_t ninv,
                                       int n_power, int lg1, int lg2, int batch, cudaStream_t st, int* launched,
-                                      void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t), int transposed_src = 0);
+                                      void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t));
     cudaError_t fast_fourstep_columns(const uint64_t* in, uint64_t* out, const uint64_t* n1_table, const uint64_t* w_table,
                                       void* w_pairs_ws, uint64_t p, int n_power, int lg1, int lg2, int batch, cudaStream_t st,
                                       int* launched, void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t), int w_lazy,
@@ -636,6 +636,7 @@ namespace gpuntt_b200
                            void (*prof_end)(cudaStream_t), int in_bound = 1, unsigned* counters = nullptr, int signed_io = 0);
     void fused_set_lag_steps(int v); // merge_fused.cu
     void fused_set_policy(int v);
+    void fourstep_set_resident_pairs(int on); // merge_fast_4step.cu
     bool fast_supported(int n_power, int element_bits);
 
     static int fail(int code, const std::string& msg)
@@ -1237,6 +1238,7 @@ extern "C"
             case GPUNTT_B200_TUNE_FUSED_LAG: fused_set_lag_steps(value); break;
             case GPUNTT_B200_TUNE_4STEP_TRANSPOSED: g_fourstep_transposed.store(value ? 1 : 0); break;
             case GPUNTT_B200_TUNE_4STEP_MODULUS_CACHE: g_fourstep_modcache.store(value); break;
+            case GPUNTT_B200_TUNE_4STEP_RESIDENT_PAIRS: fourstep_set_resident_pairs(value); break;
             default: break;
         }
     }

@@ -202,6 +202,9 @@ void gpuntt_b200_force_generic_path(int on);
  *                 behind a cached pointer must not change; gpuntt_b200_release_workspaces() forgets it); 0 never read
  *                 back (device-modulus kernels); 2 read back on every call. */
 #define GPUNTT_B200_TUNE_4STEP_MODULUS_CACHE 4
+/*   4STEP_RESIDENT_PAIRS  1 (default): the transposing column pass walks the batch through one tile position at a time with
+ *                 that position's (W, W') pairs resident in shared memory (merge_wcol.cu); 0: pairs fetched per tile. */
+#define GPUNTT_B200_TUNE_4STEP_RESIDENT_PAIRS 5
 void gpuntt_b200_tune(int knob, int value);
 
 /* Batch-slice helpers for callers whose whole batch lives on ONE GPU: device g of ndev owns the
