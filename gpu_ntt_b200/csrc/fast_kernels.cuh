@@ -1147,6 +1147,9 @@ namespace gpuntt_b200
     template <typename T>
     cudaError_t fused_merge(const FastArgs<T>& a, const FastPlan& pl, bool inverse, bool f60_or_l32, bool lazy_inv, unsigned* counters,
                             cudaStream_t st, void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t));
+    template <typename T>
+    cudaError_t fused_merge_rns(const FastArgs<T>& a, const FastPlan& pl, bool inverse, unsigned* counters, cudaStream_t st,
+                                void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t));
     void fused_set_lag_steps(int v);
     void fused_set_policy(int v); // 1: where measured faster, 2: wherever the shapes allow
 

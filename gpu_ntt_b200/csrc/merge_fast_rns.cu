@@ -67,7 +67,20 @@ namespace gpuntt_b200
         a.poly_order = poly_order;
         a.policy_flag = nullptr;
         int kind = 1;
-        (void) flag_ws; // (the policy flag of the two-launch scheme; the dual kernels read the moduli themselves)
+        if (flag_ws != nullptr && pl.npass == 2)
+        {
+            // one launch, the two passes chained through the L2 (merge_fused.cu); flag_ws = the per-polynomial counters
+            FastArgs<T> s = a;
+            s.in = in;
+            s.out = out;
+            const cudaError_t fe = fused_merge_rns<T>(s, pl, inverse, reinterpret_cast<unsigned*>(flag_ws), st, prof_begin, prof_end);
+            if (fe == cudaSuccess)
+            {
+                *launched = 1;
+                return cudaSuccess;
+            }
+            if (fe != cudaErrorNotSupported) return fe;
+        }
         for (int k = 0; k < pl.npass; k++)
         {
             const int i = inverse ? pl.npass - 1 - k : k;

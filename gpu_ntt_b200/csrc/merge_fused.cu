@@ -443,16 +443,26 @@ namespace gpuntt_b200
     static std::atomic<int> g_fused_policy{1};
     void fused_set_policy(int v) { g_fused_policy.store(v); }
 
-    template <typename SS, typename SC>
+    // SSX / SCX = void: single modulus.  Otherwise the RNS form (a.mod_count slots, a.batch polynomials PER SLOT, moduli on the
+    // device): SSX / SCX are the exact-policy twins of SS / SC (the same types when there is only one policy).
+    template <typename SS, typename SC, typename SSX = void, typename SCX = void>
     static cudaError_t launch_fused(const FastArgs<typename SS::T>& a, int lo_s, bool inverse, unsigned* counters, cudaStream_t st,
                                     void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t))
     {
         using T = typename SS::T;
+        constexpr bool RNS = !std::is_void<SSX>::value;
         constexpr int kMaxDev = 64;
         static std::atomic<int> cached_bps[kMaxDev];
         static std::atomic<int> cached_sms[kMaxDev];
         constexpr int SMEM = FusedSmem<SS, SC>::BYTES;
-        auto kern = fused2_kernel<SS, SC>;
+        using KernT = void (*)(const FusedArgs<T>, const CUtensorMap, const CUtensorMap, const CUtensorMap);
+        KernT kern;
+        if constexpr (RNS)
+            kern = fused2_rns_kernel<SS, SC, SSX, SCX>;
+        else
+            kern = fused2_kernel<SS, SC>;
+        const int mc = RNS ? a.mod_count : 1;
+        if (RNS && (mc < 1 || a.poly_order != nullptr)) return cudaErrorNotSupported;
         int dev = 0;
         cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
@@ -476,9 +486,9 @@ namespace gpuntt_b200
         const int tpp_log = lo_s - SS::C;
         const int nranges = 1 << (n - SC::KC);
         if (n < SC::KC || tpp_log > 14 || nranges > 16384) return cudaErrorNotSupported;
-        const long long slots = (long long) sms * bps;
+        const long long slots = ((long long) sms * bps) / mc; // CTAs per modulus slot
         if (nranges > slots) return cudaErrorNotSupported;
-        const long long rows = (long long) batch << (n - lo_s);
+        const long long rows = ((long long) batch * mc) << (n - lo_s);
         if (rows >= (1LL << 31)) return cudaErrorNotSupported;
 
         FusedArgs<T> f{};
@@ -492,7 +502,7 @@ namespace gpuntt_b200
         f.c.last = inverse ? 0 : 1;
         f.c.in_bound = 1;
         f.counters = counters;
-        f.ticket_off = batch; // (the workspace holds at least batch + 1 words)
+        f.ticket_off = (long long) batch * mc; // (the workspace holds at least that many words + 1)
         f.fwd = inverse ? 0 : 1;
         f.tpp_log = tpp_log;
         f.nranges = nranges;
@@ -505,7 +515,7 @@ namespace gpuntt_b200
         // 2^17 0.98, 2^18 0.98; 64-bit 2^12 1.09, 2^13 1.01, 2^14 0.98, 2^15 0.98, 2^16 0.90; small batches 1.1-1.5 everywhere.
         if (g_fused_policy.load() == 1)
         {
-            const bool always = sizeof(T) == 8 ? n <= 13 : n <= 16;
+            const bool always = !RNS && (sizeof(T) == 8 ? n <= 13 : n <= 16);
             if (!always && n_str > 8 * slots) return cudaErrorNotSupported;
         }
         long long grid;
@@ -535,24 +545,27 @@ namespace gpuntt_b200
             if (lag > 0x3fffffff) lag = 0x3fffffff;
             f.lag = (int) lag;
         }
+        f.g_slot = (int) grid;
+        grid *= mc;
+        const int mm = RNS ? mc : 0; // (make_map: 0 = single-modulus views)
         alignas(64) CUtensorMap mA_in, mA_out, mB;
         if (!inverse)
         {
-            if (!make_map<SS>(&mA_in, a.in, n, lo_s, batch)) return cudaErrorNotSupported;
+            if (!make_map<SS>(&mA_in, a.in, n, lo_s, batch, mm)) return cudaErrorNotSupported;
             if (a.in == a.out)
                 mA_out = mA_in;
-            else if (!make_map<SS>(&mA_out, a.out, n, lo_s, batch))
+            else if (!make_map<SS>(&mA_out, a.out, n, lo_s, batch, mm))
                 return cudaErrorNotSupported;
-            if (!make_map<SC>(&mB, a.out, n, 0, batch)) return cudaErrorNotSupported;
+            if (!make_map<SC>(&mB, a.out, n, 0, batch, mm)) return cudaErrorNotSupported;
         }
         else
         {
-            if (!make_map<SC>(&mA_in, a.in, n, 0, batch)) return cudaErrorNotSupported;
+            if (!make_map<SC>(&mA_in, a.in, n, 0, batch, mm)) return cudaErrorNotSupported;
             if (a.in == a.out)
                 mA_out = mA_in;
-            else if (!make_map<SC>(&mA_out, a.out, n, 0, batch))
+            else if (!make_map<SC>(&mA_out, a.out, n, 0, batch, mm))
                 return cudaErrorNotSupported;
-            if (!make_map<SS>(&mB, a.out, n, lo_s, batch)) return cudaErrorNotSupported;
+            if (!make_map<SS>(&mB, a.out, n, lo_s, batch, mm)) return cudaErrorNotSupported;
         }
         prof_begin(1, st);
         kern<<<(unsigned) grid, kFusedThreads, SMEM, st>>>(f, mA_in, mA_out, mB);
@@ -638,6 +651,63 @@ namespace gpuntt_b200
             }
         }
     }
+    // RNS form (GPU_NTT / GPU_INTT with Modulus*, GPU_NTT_Modulus_Ordered): a.batch = polynomials per slot, a.mod_count,
+    // a.mod_dev, a.ninv_dev, a.mod_order set; the moduli are device data, so 64-bit kernels carry the lazy and the exact pair
+    // of passes and every CTA picks from its own modulus.
+    template <typename T>
+    cudaError_t fused_merge_rns(const FastArgs<T>& a, const FastPlan& pl, bool inverse, unsigned* counters, cudaStream_t st,
+                                void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t))
+    {
+        if (pl.npass != 2 || !pl.strided[0] || pl.strided[1]) return cudaErrorNotSupported;
+        const int d = pl.d[0], lo = pl.lo[0];
+        if constexpr (sizeof(T) == 8)
+        {
+            using Cf = Shape<T, false, 2, false, 4, 4, 12, 1>;
+            using Cfx = Shape<T, false, 0, false, 4, 4, 12, 1>;
+            using Ci = Shape<T, true, 1, false, 4, 4, 12, 1>;
+            using Cix = Shape<T, true, 0, false, 4, 4, 12, 1>;
+#define GPUNTT_FUSED_RNS64(R1, R2)                                                                                                               \
+    (inverse ? launch_fused<Shape<T, true, 1, true, R1, R2, 12, 0>, Ci, Shape<T, true, 0, true, R1, R2, 12, 0>, Cix>(a, lo, true, counters, st,      \
+                                                                                                                    prof_begin, prof_end)         \
+             : launch_fused<Shape<T, false, 2, true, R1, R2, 12, 0>, Cf, Shape<T, false, 0, true, R1, R2, 12, 0>, Cfx>(a, lo, false, counters, st,   \
+                                                                                                                      prof_begin, prof_end))
+            switch (d)
+            {
+                case 4: return GPUNTT_FUSED_RNS64(4, 0);
+                case 5: return GPUNTT_FUSED_RNS64(3, 2);
+                case 6: return GPUNTT_FUSED_RNS64(3, 3);
+                case 7: return GPUNTT_FUSED_RNS64(4, 3);
+                case 8: return GPUNTT_FUSED_RNS64(4, 4);
+                default: return cudaErrorNotSupported;
+            }
+#undef GPUNTT_FUSED_RNS64
+        }
+        else
+        {
+            using Cf = Shape<T, false, 0, false, 5, 5, 13, 1>;
+            using Ci = Shape<T, true, 0, false, 5, 5, 13, 1>;
+#define GPUNTT_FUSED_RNS32(R1, R2)                                                                                                               \
+    (inverse ? launch_fused<Shape<T, true, 0, true, R1, R2, 13, 0>, Ci, Shape<T, true, 0, true, R1, R2, 13, 0>, Ci>(a, lo, true, counters, st,       \
+                                                                                                                   prof_begin, prof_end)          \
+             : launch_fused<Shape<T, false, 0, true, R1, R2, 13, 0>, Cf, Shape<T, false, 0, true, R1, R2, 13, 0>, Cf>(a, lo, false, counters, st,    \
+                                                                                                                     prof_begin, prof_end))
+            switch (d)
+            {
+                case 4: return GPUNTT_FUSED_RNS32(4, 0);
+                case 5: return GPUNTT_FUSED_RNS32(5, 0);
+                case 6: return GPUNTT_FUSED_RNS32(3, 3);
+                case 7: return GPUNTT_FUSED_RNS32(4, 3);
+                case 8: return GPUNTT_FUSED_RNS32(4, 4);
+                default: return cudaErrorNotSupported;
+            }
+#undef GPUNTT_FUSED_RNS32
+        }
+    }
+    template cudaError_t fused_merge_rns<uint64_t>(const FastArgs<uint64_t>&, const FastPlan&, bool, unsigned*, cudaStream_t,
+                                                   void (*)(int, cudaStream_t), void (*)(cudaStream_t));
+    template cudaError_t fused_merge_rns<uint32_t>(const FastArgs<uint32_t>&, const FastPlan&, bool, unsigned*, cudaStream_t,
+                                                   void (*)(int, cudaStream_t), void (*)(cudaStream_t));
+
     template cudaError_t fused_merge<uint64_t>(const FastArgs<uint64_t>&, const FastPlan&, bool, bool, bool, unsigned*, cudaStream_t,
                                                void (*)(int, cudaStream_t), void (*)(cudaStream_t));
     template cudaError_t fused_merge<uint32_t>(const FastArgs<uint32_t>&, const FastPlan&, bool, bool, bool, unsigned*, cudaStream_t,

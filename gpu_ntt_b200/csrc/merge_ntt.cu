@@ -908,7 +908,7 @@ namespace gpuntt_b200
         }
         if (rns && !d->is_signed && !g_force_generic.load() && d->ntt_layout == GPUNTT_B200_PER_POLYNOMIAL)
         {
-            void* flag = nullptr; // (the dual-policy kernels read the moduli themselves: no flag buffer any more)
+            void* flag = fused_counters(d->stream, d->batch_size); // progress counters of the single-launch kernels (may be null)
             int launched = 0;
             cudaError_t fe = fast_merge_rns<T>(reinterpret_cast<const T*>(d->in), reinterpret_cast<T*>(d->out),
                                    reinterpret_cast<const T*>(d->root_of_unity_table), reinterpret_cast<const T*>(d->modulus_dev),

@@ -239,16 +239,22 @@ def test_rns_form(bits, logn, batch, mod_count):
     (64, 18, 3, 3, (59, 61, 50)),
     (32, 19, 4, 2, (29, 28)),
 ])
-def test_rns_form_tuned_kernels(bits, logn, batch, mod_count, tops):
+@pytest.mark.parametrize("fused", [2, 0])
+def test_rns_form_tuned_kernels(bits, logn, batch, mod_count, tops, fused):
     """RNS overloads on the tuned kernels (two-pass ring sizes, batch a multiple of mod_count): per-slot modulus,
-    table slice and N^-1 are read per segment on the device, and for 64-bit data every pass kernel holds the lazy and
-    the exact arithmetic body and picks one from the moduli it finds."""
+    table slice and N^-1 are read per segment on the device, and for 64-bit data every kernel holds the lazy and
+    the exact arithmetic body and picks one from the moduli it finds.  fused = 2: the single-launch kernel (the CTAs
+    are partitioned among the modulus slots, each picks its policy from its own modulus); 0: one launch per pass."""
     primes = [rns_primes(bits, logn, 1 + i, t)[i] for i, t in enumerate(tops)]
     assert len({p for p, _ in primes}) == mod_count
-    _rns_roundtrip(bits, logn, batch, mod_count, primes)
+    try:
+        capi.tune(capi.TUNE_FUSED_PASSES, fused)
+        _rns_roundtrip(bits, logn, batch, mod_count, primes)
+    finally:
+        capi.tune(capi.TUNE_FUSED_PASSES, 1)
     # the inverse call was the last one: one launch per pass (64-bit: the dual kernel picks the lazy or the exact body
     # from the modulus array on the device)
-    assert capi.lib().gpuntt_b200_last_launch_count() == (2 if logn <= (16 if bits == 64 else 18) else 3)
+    assert capi.lib().gpuntt_b200_last_launch_count() == ((1 if fused else 2) if logn <= (16 if bits == 64 else 18) else 3)
 
 
 def _rns_roundtrip(bits, logn, batch, mod_count, primes):
