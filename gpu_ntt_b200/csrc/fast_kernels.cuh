@@ -239,7 +239,7 @@ namespace gpuntt_b200
                                                const typename ModOf<S>::type& M, int ctid,
                                                const Twiddle<typename S::T>& ninv,
                                                const Twiddle<typename S::T>* __restrict__ wtile = nullptr, int lo = 0, int in_bound = 1,
-                                               bool w_lazy = false, int bar = 1, int sflags = 0)
+                                               bool w_lazy = false, int bar = 1)
     {
         using T = typename S::T;
         constexpr int E = 1 << R;
@@ -299,13 +299,6 @@ namespace gpuntt_b200
                 for (int a = 0; a < E; a++) e[a] = *reinterpret_cast<const T*>(addr(a));
             }
 
-            if (sflags & 1) // signed input: -|x| -> p - |x|
-            {
-                using ST = typename std::make_signed<T>::type;
-#pragma unroll
-                for (int a = 0; a < E; a++)
-                    if ((ST) e[a] < 0) e[a] += M.p;
-            }
             // 4-step twiddle-matrix product on the item's elements (forward: epilogue, canonical results; inverse:
             // prologue, lazy results in [0,3p)).  Loads in batches of 8 (32 registers): ptxas otherwise serialises
             // load -> multiply -> load and exposes one global-memory latency per element.
@@ -431,12 +424,6 @@ namespace gpuntt_b200
                 {
 #pragma unroll
                     for (int a = 0; a < E; a++) e[a] = M.canon_inv(e[a], ninv);
-                    if (sflags & 2) // centred signed output
-                    {
-#pragma unroll
-                        for (int a = 0; a < E; a++)
-                            if (e[a] > (M.p >> 1)) e[a] -= M.p;
-                    }
                 }
             }
 
@@ -536,6 +523,31 @@ namespace gpuntt_b200
         }
     }
 
+    // Elementwise sweep over a whole tile buffer (any layout: every byte of the buffer is data).  CENTRE = false: signed input,
+    // x < 0 -> x + p (modular_arith.cuh:372-385 of the reference); true: centred output, r > p/2 -> r - p (:389-405).
+    template <typename S, bool CENTRE> __device__ __forceinline__ void signed_tile_fixup(unsigned char* buf, typename S::T p, int ctid)
+    {
+        using T = typename S::T;
+        using ST = typename std::make_signed<T>::type;
+        constexpr int VN = 16 / (int) sizeof(T);
+        const T half = p >> 1;
+#pragma unroll 2
+        for (int off = ctid * 16; off < S::TILE_SMEM; off += kConsumers * 16)
+        {
+            T v[VN];
+            *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(buf + off);
+#pragma unroll
+            for (int k = 0; k < VN; k++)
+            {
+                if constexpr (CENTRE)
+                    v[k] = v[k] > half ? v[k] - p : v[k];
+                else
+                    v[k] = (ST) v[k] < 0 ? v[k] + p : v[k];
+            }
+            *reinterpret_cast<uint4*>(buf + off) = *reinterpret_cast<const uint4*>(v);
+        }
+    }
+
     // ------------------------------------------------------------------ the register rounds of one tile
     // In the merge plans the contiguous pass is always the LAST forward / FIRST inverse pass, so only it canonicalises
     // forward and only a strided pass (the top one) applies n^-1 on the inverse.  SFIN: a forward STRIDED pass that ends
@@ -549,9 +561,15 @@ namespace gpuntt_b200
                                                 const FastArgs<typename S::T>& a, bool triv, int bar = 1)
     {
         constexpr bool W1 = WMUL && S::R2 == 0, W2 = WMUL && S::R2 > 0;
-        const int sin = (a.signed_io && a.first) ? 1 : 0, sout = a.signed_io ? 2 : 0;
         if constexpr (!S::INV)
         {
+            // Data32s / Data64s: negative inputs become p - |x| before the first round of the first pass -- a separate sweep
+            // over the tile, so that the unsigned path carries no extra instructions
+            if (a.signed_io && a.first)
+            {
+                signed_tile_fixup<S, false>(buf, M.p, tid);
+                consumer_sync(bar);
+            }
 #ifdef GPUNTT_EXPERIMENT_NOCANON // timing experiment only (lazy outputs): what the final canonicalisation costs
             constexpr bool FIN1 = false, FIN2 = false;
 #else
@@ -562,12 +580,12 @@ namespace gpuntt_b200
             {
                 if (triv)
                     fast_round<S, S::R1, S::LB1, S::G1, FIN1, true, W1, TS1, WL>(buf, tw1, M, tid, ninv, wtile, a.lo,
-                                                                              a.in_bound > 1 ? a.in_bound : 1, a.w_lazy != 0, bar, sin);
+                                                                              a.in_bound > 1 ? a.in_bound : 1, a.w_lazy != 0, bar);
                 else
-                    fast_round<S, S::R1, S::LB1, S::G1, FIN1, false, W1, TS1, WL>(buf, tw1, M, tid, ninv, wtile, a.lo, 1, a.w_lazy != 0, bar, sin);
+                    fast_round<S, S::R1, S::LB1, S::G1, FIN1, false, W1, TS1, WL>(buf, tw1, M, tid, ninv, wtile, a.lo, 1, a.w_lazy != 0, bar);
             }
             else
-                fast_round<S, S::R1, S::LB1, S::G1, FIN1>(buf, tw1, M, tid, ninv, nullptr, 0, 1, false, bar, sin);
+                fast_round<S, S::R1, S::LB1, S::G1, FIN1>(buf, tw1, M, tid, ninv, nullptr, 0, 1, false, bar);
             if constexpr (S::R2 > 0)
             {
                 consumer_sync(bar);
@@ -594,7 +612,7 @@ namespace gpuntt_b200
             if constexpr (S::STRIDED)
             {
                 if (a.last)
-                    fast_round<S, S::R1, S::LB1, S::G1, true, false, W1, TS>(buf, tw1, M, tid, ninv, wtile, a.lo, 1, false, bar, sout);
+                    fast_round<S, S::R1, S::LB1, S::G1, true, false, W1, TS>(buf, tw1, M, tid, ninv, wtile, a.lo, 1, false, bar);
                 else
                     fast_round<S, S::R1, S::LB1, S::G1, false, false, W1, TS>(buf, tw1, M, tid, ninv, wtile, a.lo, 1, false, bar);
             }
@@ -602,12 +620,18 @@ namespace gpuntt_b200
             {
                 // whole transforms in the tile: the top round is the last one of a single-pass inverse (n^-1 there)
                 if (a.last)
-                    fast_round<S, S::R1, S::LB1, S::G1, true>(buf, tw1, M, tid, ninv, nullptr, 0, 1, false, bar, sout);
+                    fast_round<S, S::R1, S::LB1, S::G1, true>(buf, tw1, M, tid, ninv, nullptr, 0, 1, false, bar);
                 else
                     fast_round<S, S::R1, S::LB1, S::G1, false>(buf, tw1, M, tid, ninv);
             }
             else
                 fast_round<S, S::R1, S::LB1, S::G1, false>(buf, tw1, M, tid, ninv);
+            // centred signed output after n^-1 (last pass of the inverse): again a separate sweep
+            if (a.signed_io && a.last)
+            {
+                consumer_sync(bar);
+                signed_tile_fixup<S, true>(buf, M.p, tid);
+            }
         }
     }
 
