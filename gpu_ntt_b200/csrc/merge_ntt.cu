@@ -15,6 +15,7 @@
 //     2 passes up to 2^22/2^23, 3 passes above; several small polynomials share one tile.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <random>
@@ -1116,7 +1117,12 @@ extern "C"
         int chunk_polys = hd->batch_size;
         if (hd->ntt_layout == GPUNTT_B200_PER_POLYNOMIAL && hd->batch_size > 1)
         {
-            const size_t target = (size_t) 32 << 20;
+            size_t target = (size_t) 32 << 20;
+            if (const char* ev = getenv("GPUNTT_B200_HOST_CHUNK_MB")) // (measurement knob: tools/e2e_chunk_sweep.py)
+            {
+                const long mb = atol(ev);
+                if (mb > 0) target = (size_t) mb << 20;
+            }
             size_t cp = poly_bytes >= target ? 1 : target / poly_bytes;
             if (cp < (size_t) hd->batch_size) chunk_polys = (int) cp;
         }

@@ -41,8 +41,10 @@ namespace gpuntt_b200
     __device__ __forceinline__ uint64_t mulhi(uint64_t a, uint64_t b) { return __umul64hi(a, b); }
     __device__ __forceinline__ uint32_t mulhi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
 
-    // x in [0, 2m) -> [0, m)
+    // x in [0, 2m) -> [0, m).  32-bit: min(x, x - m) -- the difference wraps above x exactly when x < m -- is one subtraction and one
+    // VIMNMX instead of a compare and a select (the 32-bit kernels are bound by instruction issue, not by the multiplier).
     template <typename T> __device__ __forceinline__ T csub(T x, T m) { return (x >= m) ? x - m : x; }
+    template <> __device__ __forceinline__ uint32_t csub<uint32_t>(uint32_t x, uint32_t m) { return min(x, x - m); }
 
     // companion w' = floor(w * 2^BITS / p), w < p
     __host__ __device__ __forceinline__ uint64_t shoup_companion(uint64_t w, uint64_t p)
@@ -71,19 +73,33 @@ namespace gpuntt_b200
         __device__ __forceinline__ void ct(T& X, T& Y, const Twiddle<T>& tw) const
         {
             const T t = mul(Y, tw);
-            const bool P = X >= two_p;
-            const T g = P ? T(0) - two_p : T(0), k = P ? T(0) : two_p;
-            const T Xn = X + g + t;
-            Y = X + k - t;
-            X = Xn;
+            if constexpr (sizeof(T) == 4)
+            {
+                const T x = csub(X, two_p); // [0,4p) -> [0,2p)
+                Y = x + two_p - t;
+                X = x + t;
+            }
+            else
+            {
+                const bool P = X >= two_p;
+                const T g = P ? T(0) - two_p : T(0), k = P ? T(0) : two_p;
+                const T Xn = X + g + t;
+                Y = X + k - t;
+                X = Xn;
+            }
         }
         // Gentleman-Sande butterfly (replaces GentlemanSandeUnit, ntt.cuh:80-92). In/out: [0,2p).
         __device__ __forceinline__ void gs(T& X, T& Y, const Twiddle<T>& tw) const
         {
             const T d = X + two_p - Y;
             const T s = X + Y;
-            const T g = (s >= two_p) ? T(0) - two_p : T(0);
-            X = X + Y + g;
+            if constexpr (sizeof(T) == 4)
+                X = csub(s, two_p);
+            else
+            {
+                const T g = (s >= two_p) ? T(0) - two_p : T(0);
+                X = X + Y + g;
+            }
             Y = mul(d, tw);
         }
         // forward lazy value -> canonical
@@ -296,11 +312,9 @@ namespace gpuntt_b200
         __device__ __forceinline__ void ctB(T& X, T& Y, const Twiddle<T>& tw) const // in: X < 8p; out < 6p
         {
             const T t = mul(Y, tw);
-            const bool P = X >= four_p;
-            const T g = P ? T(0) - four_p : T(0), k = P ? T(0) - two_p : two_p;
-            const T Xn = X + g + t;
-            Y = X + k - t;
-            X = Xn;
+            const T x = csub(X, four_p); // [0,8p) -> [0,4p)
+            Y = x + two_p - t;
+            X = x + t;
         }
         __device__ __forceinline__ void add_sub(T& X, T& Y, T K) const
         {
