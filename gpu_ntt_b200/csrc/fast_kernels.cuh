@@ -196,6 +196,10 @@ namespace gpuntt_b200
         int signed_io; // Data32s / Data64s: forward = signed input (x < 0 -> x + p as the first pass loads, modular_arith.cuh:372-385 of
                        // the reference), inverse = centred signed output (r > p/2 -> r - p after n^-1, modular_arith.cuh:389-405)
         int n_tw; // transform size (log2) for twiddle indexing when it differs from the layout size n (0: n)
+        int tw_fixed; // strided passes whose transforms are SHORTER than the row count (size 2^D transforms on every block of 2^D
+                      // matrix rows: the 4-step inverse row phase read from the n2 x n1 matrix): one twiddle set for every range
+        int cc_major; // strided passes: inside a range the tiles are ordered column-chunk-major, polynomial-minor (default:
+                      // polynomial-major), so the tiles that share the twiddle-matrix pairs of a position follow each other
         int cta_per_seg, seg_extra; // cta_per_seg > 0: every CTA works inside ONE twiddle segment; the first seg_extra segments get
                                     // cta_per_seg + 1 CTAs, the others cta_per_seg (set by launch_fast)
         long long work; // total tiles of this pass
@@ -306,7 +310,8 @@ namespace gpuntt_b200
             {
                 if constexpr (WMUL)
                 {
-                    static_assert(!WMUL || (S::STRIDED && LB >= S::C), "the twiddle-matrix product belongs to strided passes");
+                    static_assert(!WMUL || (S::STRIDED && LB >= S::C) || (WL && !S::STRIDED && LB == 0),
+                                  "the twiddle-matrix product belongs to strided passes (contiguous passes: resident pairs, lowest round)");
                     // offset of element a: row (l >> C) * 2^lo + column (l & (2^C - 1)); a only moves the row
                     const Twiddle<T>* wp = wtile + (((long long) (l_base >> S::C)) << lo) + (l_base & ((1 << S::C) - 1));
                     constexpr int WB = WL ? (E < 4 ? E : 4) : (E < 8 ? E : 8); // (shared-memory pairs: short latency, fewer registers)
@@ -318,6 +323,9 @@ namespace gpuntt_b200
                         for (int j = 0; j < WB; j++)
                         {
                             const ulonglong2* src = reinterpret_cast<const ulonglong2*>(wp + (((long long) (h + j) << (LB - S::C)) << lo));
+                            // contiguous tiles: the pair table is built element-major inside a tile position (entry a * ITEMS + item is
+                            // the pair of local element item * E + a, merge_wcol.cu), so a warp's loads are 32 consecutive pairs
+                            if constexpr (WL && !S::STRIDED) src = reinterpret_cast<const ulonglong2*>(wtile + (h + j) * ITEMS + item);
                             if constexpr (WL)
                                 v[j] = *src;
                             else
@@ -606,15 +614,15 @@ namespace gpuntt_b200
             }
             if constexpr (S::R2 > 0)
             {
-                fast_round<S, S::R2, S::LB2, S::G2, false, false, W2>(buf, tw2, M, tid, ninv, wtile, a.lo);
+                fast_round<S, S::R2, S::LB2, S::G2, false, false, W2, false, WL>(buf, tw2, M, tid, ninv, wtile, a.lo, 1, false, bar);
                 consumer_sync(bar);
             }
             if constexpr (S::STRIDED)
             {
                 if (a.last)
-                    fast_round<S, S::R1, S::LB1, S::G1, true, false, W1, TS>(buf, tw1, M, tid, ninv, wtile, a.lo, 1, false, bar);
+                    fast_round<S, S::R1, S::LB1, S::G1, true, false, W1, TS, WL>(buf, tw1, M, tid, ninv, wtile, a.lo, 1, false, bar);
                 else
-                    fast_round<S, S::R1, S::LB1, S::G1, false, false, W1, TS>(buf, tw1, M, tid, ninv, wtile, a.lo, 1, false, bar);
+                    fast_round<S, S::R1, S::LB1, S::G1, false, false, W1, TS, WL>(buf, tw1, M, tid, ninv, wtile, a.lo, 1, false, bar);
             }
             else if constexpr (S::NT > 0)
             {
@@ -679,6 +687,7 @@ namespace gpuntt_b200
         // a.cta_per_seg: when there are fewer segments than CTA slots, cta_per_seg CTAs split each segment, so nobody
         // builds two twiddle sets for a handful of tiles
         const long long step = a.rr ? (long long) gridDim.x : 1LL;
+        const bool pmajor = !a.rr && !a.cc_major; // tile order inside a range: polynomial-major or column-chunk-major
         long long w_begin, w_end;
         if (a.rr)
         {
@@ -769,8 +778,8 @@ namespace gpuntt_b200
                     {
                         const int ccb = a.lo - S::C;
                         const long long within = ww % tiles_per_range;
-                        const long long poly = a.rr ? within % a.batch : within >> ccb;
-                        const long long cc = a.rr ? within / a.batch : (within & ((1LL << ccb) - 1));
+                        const long long poly = pmajor ? within >> ccb : within % a.batch;
+                        const long long cc = pmajor ? (within & ((1LL << ccb) - 1)) : within / a.batch;
                         long long gp = RNS ? poly * a.mod_count + mslot : poly; // polynomial in the caller's array
                         if constexpr (RNS)
                             if (a.poly_order) gp = a.poly_order[gp];
@@ -839,7 +848,7 @@ namespace gpuntt_b200
                 M = typename ModOf<S>::type(seg_p);
                 triv = S::STRIDED && !S::INV && !a.plus && a.first && (a.lo + S::D == a.n) && seg_table[0] == T(1);
             }
-            build_twiddles<S>(tw1, seg_table, range, n, a.n_tw, a.lo, a.plus, seg_p, seg_mu, seg_pbits, tid, kFastThreads);
+            build_twiddles<S>(tw1, seg_table, a.tw_fixed ? 0 : range, n, a.n_tw, a.lo, a.plus, seg_p, seg_mu, seg_pbits, tid, kFastThreads);
             __syncthreads();
 
             if (tid >= kConsumers)
@@ -860,13 +869,13 @@ namespace gpuntt_b200
                         {
                             const int ccb = a.lo - S::C;
                             const long long within = ww % tiles_per_range;
-                            const long long poly = a.rr ? within % a.batch : within >> ccb;
-                            const long long cc = a.rr ? within / a.batch : (within & ((1LL << ccb) - 1));
+                            const long long poly = pmajor ? within >> ccb : within % a.batch;
+                            const long long cc = pmajor ? (within & ((1LL << ccb) - 1)) : within / a.batch;
                             long long gp = RNS ? poly * a.mod_count + mslot : poly;
                             if constexpr (RNS)
                                 if (a.poly_order) gp = a.poly_order[gp];
-                            if constexpr (TS) // transposing box {16 rows, 2^C columns, 2^(D-4) row blocks} of the n2 x n1 output matrix
-                                tma_store_3d(&map_out, 0, (int) ((gp << a.lo) + (cc << S::C)), 0, src);
+                            if constexpr (TS) // transposing box {16 rows, 2^C columns, 2^(D-4) row blocks} of the transposed output matrix
+                                tma_store_3d(&map_out, 0, (int) ((gp << a.lo) + (cc << S::C)), range << (S::D - 4), src);
                             else
                                 tma_store_3d(&map_out, 0, (int) (cc << (S::C - S::CB)),
                                              (int) ((gp << (a.n - a.lo)) + ((long long) range << S::D)), src);
@@ -921,7 +930,7 @@ namespace gpuntt_b200
                     {
                         // pair of the tile's first element: row block `range`, column chunk cc (same for every polynomial)
                         const long long within = (w + i * step) % tiles_per_range;
-                        const long long cc = a.rr ? within / a.batch : (within & ((1LL << (a.lo - S::C)) - 1));
+                        const long long cc = pmajor ? (within & ((1LL << (a.lo - S::C)) - 1)) : within / a.batch;
                         wtile = reinterpret_cast<const Twiddle<T>*>(a.w_pairs) + ((((long long) range << S::D)) << a.lo) + (cc << S::C);
                         // pull this thread's pairs towards the SM now
                         constexpr int RW = S::R2 > 0 ? S::R2 : S::R1, LBW = S::R2 > 0 ? S::LB2 : S::LB1;
@@ -1063,14 +1072,16 @@ namespace gpuntt_b200
     // polynomial (one range: lo + D == n) and writes its transpose, 2^lo rows of 2^D contiguous elements.  View
     // {16 elements of a transposed row, every transposed row of every polynomial, 2^(D-4) blocks of 16 elements along
     // that row}; box {16, 2^C, 2^(D-4)}.
-    template <typename S> static bool make_map_tstore(CUtensorMap* map, const void* base, int lo, int batch)
+    // n > lo + D (several twiddle ranges: the pass works on 2^D of the 2^(n - lo) matrix rows at a time): the transposed rows are
+    // 2^(n - lo) elements long and range r fills elements [r * 2^D, (r + 1) * 2^D) of each -- third coordinate r * 2^(D - 4).
+    template <typename S> static bool make_map_tstore(CUtensorMap* map, const void* base, int lo, int batch, int n)
     {
         using T = typename S::T;
         static_assert(sizeof(T) == 8 && S::STRIDED && S::D >= 5, "transposing store: 64-bit strided passes of 5..8 stages");
         PFN_cuTensorMapEncodeTiled enc = get_encode();
         if (!enc) return false;
-        cuuint64_t gdim[3] = {16, (cuuint64_t) batch << lo, 1ull << (S::D - 4)};
-        cuuint64_t gstride[2] = {(cuuint64_t) sizeof(T) << S::D, 128};
+        cuuint64_t gdim[3] = {16, (cuuint64_t) batch << lo, 1ull << (n - lo - 4)};
+        cuuint64_t gstride[2] = {(cuuint64_t) sizeof(T) << (n - lo), 128};
         cuuint32_t box[3] = {16, 1u << S::C, 1u << (S::D - 4)}, estr[3] = {1, 1, 1};
         CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1124,8 +1135,8 @@ namespace gpuntt_b200
         if (!make_map<S>(&map_in, args.in, args.n, args.lo, args.batch, mc, opb)) return cudaErrorNotSupported;
         if constexpr (TS)
         {
-            if (args.in == args.out || args.lo + S::D != args.n) return cudaErrorNotSupported;
-            if (!make_map_tstore<S>(&map_out, args.out, args.lo, args.batch)) return cudaErrorNotSupported;
+            if (args.in == args.out || args.lo + S::D > args.n) return cudaErrorNotSupported;
+            if (!make_map_tstore<S>(&map_out, args.out, args.lo, args.batch, args.n)) return cudaErrorNotSupported;
         }
         else if (args.in == args.out)
             map_out = map_in;

@@ -104,7 +104,10 @@ template <typename T> static int fourstep_execute_t(const gpuntt_b200_4step_desc
 
     // scratch for the contracts that cannot run in `out` alone
     T* ws = nullptr;
-    if (fused || inv)
+    const bool fwd_ref_transposeless = !inv && !fused && sizeof(T) == 8 && !rns && !g_force_generic.load() && g_fourstep_transposed.load() &&
+                                       batch >= 4 && fast_fourstep_rows_t_supported(lg1, lg2) &&
+                                       (uint64_t) d->modulus_value >= kF60ModulusMin && (uint64_t) d->modulus_value < kF60ModulusLimit;
+    if (fused || inv || fwd_ref_transposeless)
     {
         void* w = nullptr;
         cudaError_t e = get_workspace(d->stream, 5, (size_t) batch * (size_t) N * sizeof(T), &w);
@@ -182,13 +185,28 @@ template <typename T> static int fourstep_execute_t(const gpuntt_b200_4step_desc
             if (launched > 0)
             {
                 int rl = 0;
-                we = fast_fourstep_rows_t(reinterpret_cast<const uint64_t*>(ws), reinterpret_cast<uint64_t*>(out),
-                                          reinterpret_cast<const uint64_t*>(d->n2_table), (uint64_t) d->modulus_value, n, lg1, lg2, batch, 2, st,
-                                          &rl, prof_begin, prof_end);
+                we = fast_fourstep_rows_t(reinterpret_cast<const uint64_t*>(ws), reinterpret_cast<uint64_t*>(out), reinterpret_cast<uint64_t*>(out),
+                                          reinterpret_cast<const uint64_t*>(d->n2_table), (uint64_t) d->modulus_value, n, lg1, lg2, batch, 2, false,
+                                          2, st, &rl, prof_begin, prof_end);
                 if (we != cudaSuccess) return cuda_fail(we, "fast 4-step row passes launch");
                 if (rl == 0) return fail(GPUNTT_B200_ERR_CUDA, "4-step row phase: tuned kernels declined after a transposing column phase");
                 return GPUNTT_B200_OK;
             }
+        }
+        // Reference contract, forward, without a transpose kernel either: the column transforms are contiguous runs of the
+        // n2 x n1 matrix the caller's GPU_Transpose made; the last row pass stores the n1 x n2 matrix the contract asks for.
+        if (fwd_ref_transposeless)
+        {
+            void* pairs = nullptr;
+            cudaError_t we = get_workspace(d->stream, 6, (size_t) N * sizeof(Twiddle<T>), &pairs);
+            if (we != cudaSuccess) return cuda_fail(we, "4-step twiddle-pair workspace allocation");
+            int launched = 0;
+            we = fast_fourstep_forward_transposed_in(reinterpret_cast<const uint64_t*>(in), reinterpret_cast<uint64_t*>(ws),
+                                                     reinterpret_cast<uint64_t*>(out), reinterpret_cast<const uint64_t*>(d->n1_table),
+                                                     reinterpret_cast<const uint64_t*>(d->n2_table), reinterpret_cast<const uint64_t*>(d->w_table),
+                                                     pairs, (uint64_t) d->modulus_value, n, lg1, lg2, batch, st, &launched, prof_begin, prof_end);
+            if (we != cudaSuccess) return cuda_fail(we, "fast 4-step forward (transposed input) launch");
+            if (launched > 0) return GPUNTT_B200_OK;
         }
     }
     if (!inv)
@@ -273,6 +291,29 @@ template <typename T> static int fourstep_execute_t(const gpuntt_b200_4step_desc
         // T = n2 rows of n1 (the reference contract passes it; the fused contract passes its transpose)
         const T* src = in;
         bool inverse_done = false;
+        void* pairs = nullptr;
+        const bool tuned = sizeof(T) == 8 && !rns && !g_force_generic.load();
+        if (tuned)
+        {
+            cudaError_t we = get_workspace(d->stream, 6, (size_t) N * sizeof(Twiddle<T>), &pairs);
+            if (we != cudaSuccess) return cuda_fail(we, "4-step twiddle-pair workspace allocation");
+        }
+        if constexpr (sizeof(T) == 8)
+        {
+            // tuned kernels without a transpose kernel: the fused contract's first pass reads y with a transposing store, the
+            // reference contract's product pass stores the n1 x n2 matrix
+            if (tuned && g_fourstep_transposed.load())
+            {
+                int launched = 0;
+                cudaError_t we = fast_fourstep_inverse(reinterpret_cast<const uint64_t*>(in), reinterpret_cast<uint64_t*>(ws),
+                                                       reinterpret_cast<uint64_t*>(out), reinterpret_cast<const uint64_t*>(d->n1_table),
+                                                       reinterpret_cast<const uint64_t*>(d->n2_table), reinterpret_cast<const uint64_t*>(d->w_table),
+                                                       pairs, (uint64_t) d->modulus_value, (uint64_t) d->mod_inverse_value, n, lg1, lg2, batch,
+                                                       fused, !fused, st, &launched, prof_begin, prof_end);
+                if (we != cudaSuccess) return cuda_fail(we, "fast 4-step inverse launch");
+                if (launched > 0) return GPUNTT_B200_OK;
+            }
+        }
         if (fused)
         {
             e = launch_transpose<T>(in, ws, n2, n1, N, batch, st, 9);
@@ -282,17 +323,14 @@ template <typename T> static int fourstep_execute_t(const gpuntt_b200_4step_desc
         if constexpr (sizeof(T) == 8)
         {
             // tuned kernels: row phase + strided Gentleman-Sande passes with the W^-1 product as the first one loads
-            if (!rns && !g_force_generic.load())
+            if (tuned)
             {
-                void* pairs = nullptr;
-                cudaError_t we = get_workspace(d->stream, 6, (size_t) N * sizeof(Twiddle<T>), &pairs);
-                if (we != cudaSuccess) return cuda_fail(we, "4-step twiddle-pair workspace allocation");
                 int launched = 0;
-                we = fast_fourstep_inverse(reinterpret_cast<const uint64_t*>(src), reinterpret_cast<uint64_t*>(ws),
-                                           reinterpret_cast<uint64_t*>(fused ? out : ws), reinterpret_cast<const uint64_t*>(d->n1_table),
-                                           reinterpret_cast<const uint64_t*>(d->n2_table), reinterpret_cast<const uint64_t*>(d->w_table), pairs,
-                                           (uint64_t) d->modulus_value, (uint64_t) d->mod_inverse_value, n, lg1, lg2, batch, st, &launched,
-                                           prof_begin, prof_end);
+                cudaError_t we = fast_fourstep_inverse(reinterpret_cast<const uint64_t*>(src), reinterpret_cast<uint64_t*>(ws),
+                                                       reinterpret_cast<uint64_t*>(fused ? out : ws), reinterpret_cast<const uint64_t*>(d->n1_table),
+                                                       reinterpret_cast<const uint64_t*>(d->n2_table), reinterpret_cast<const uint64_t*>(d->w_table),
+                                                       pairs, (uint64_t) d->modulus_value, (uint64_t) d->mod_inverse_value, n, lg1, lg2, batch,
+                                                       false, false, st, &launched, prof_begin, prof_end);
                 if (we != cudaSuccess) return cuda_fail(we, "fast 4-step inverse launch");
                 inverse_done = launched > 0;
             }

@@ -619,18 +619,22 @@ namespace gpuntt_b200
                                const int* poly_order, int mod_count, int n_power, int plus, bool inverse, int batch, int* flag_ws,
                                cudaStream_t st, int* launched,
                                void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t));
-    cudaError_t fast_fourstep_inverse(const uint64_t* rows_in, uint64_t* work, uint64_t* dst, const uint64_t* n1_table,
+    cudaError_t fast_fourstep_inverse(const uint64_t* src, uint64_t* work, uint64_t* dst, const uint64_t* n1_table,
                                       const uint64_t* n2_table, const uint64_t* w_table, void* w_pairs_ws, uint64_t p, uint64_t ninv,
-                                      int n_power, int lg1, int lg2, int batch, cudaStream_t st, int* launched,
-                                      void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t));
+                                      int n_power, int lg1, int lg2, int batch, bool src_is_y, bool transposed_out, cudaStream_t st,
+                                      int* launched, void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t));
+    cudaError_t fast_fourstep_forward_transposed_in(const uint64_t* in_t, uint64_t* work, uint64_t* out, const uint64_t* n1_table,
+                                                    const uint64_t* n2_table, const uint64_t* w_table, void* w_pairs_ws, uint64_t p, int n_power,
+                                                    int lg1, int lg2, int batch, cudaStream_t st, int* launched,
+                                                    void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t));
     cudaError_t fast_fourstep_columns(const uint64_t* in, uint64_t* out, const uint64_t* n1_table, const uint64_t* w_table,
                                       void* w_pairs_ws, uint64_t p, int n_power, int lg1, int lg2, int batch, cudaStream_t st,
                                       int* launched, void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t), int w_lazy,
                                       int transposed = 0);
     bool fast_fourstep_rows_t_supported(int lg1, int lg2);
-    cudaError_t fast_fourstep_rows_t(const uint64_t* buf, uint64_t* out, const uint64_t* n2_table, uint64_t p, int n_power, int lg1, int lg2,
-                                     int batch, int in_bound, cudaStream_t st, int* launched, void (*prof_begin)(int, cudaStream_t),
-                                     void (*prof_end)(cudaStream_t));
+    cudaError_t fast_fourstep_rows_t(const uint64_t* buf, uint64_t* mid, uint64_t* out, const uint64_t* n2_table, uint64_t p, int n_power,
+                                     int lg1, int lg2, int batch, int in_bound, bool transposed_out, int first_kind, cudaStream_t st,
+                                     int* launched, void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t));
     template <typename T>
     cudaError_t fast_merge(const T* in, T* out, const T* table, T p, T ninv, int n_power, int plus, bool inverse,
                            int batch, cudaStream_t st, int* launched, void (*prof_begin)(int, cudaStream_t),

@@ -238,3 +238,85 @@ def test_4step_column_kernel_with_resident_pairs(logn, batch):
             assert (to_host(d, bits) == want).all(), f"knob={knob} in place"
     finally:
         capi.tune(5, 1)
+
+
+def _kinds_of(call):
+    """launch kinds of one call (9 = transpose_kernel)"""
+    capi.lib().gpuntt_b200_set_profiling(1)
+    try:
+        capi.profile_read()
+        call()
+        torch.cuda.synchronize()
+        return [k for k, _ in capi.profile_read()]
+    finally:
+        capi.lib().gpuntt_b200_set_profiling(0)
+
+
+@pytest.mark.parametrize("logn,batch", [(12, 4), (13, 5), (16, 4), (17, 6), (18, 4), (20, 4), (21, 4), (22, 5), (23, 4)])
+def test_4step_reference_contract_forward_without_transpose_kernel(logn, batch):
+    """Reference contract (GPU_Transpose'd input in, n1 x n2 matrix out), batch >= 4: contiguous column pass on the transposed
+    input with the pairs resident in shared memory, row passes along that layout, transposing store in the last one -- no
+    transpose_kernel inside the call; knob 3 = 0 gives the same words through the transposing path."""
+    bits = 64
+    P = O.fourstep_params(logn, O.X_N_minus, bits, inverse_tables=False)
+    n = P.n
+    x = O.example_input(P.modulus, batch * n, seed=7 * logn + batch).reshape(batch, n)
+    want = _threaded(O.fourstep_ntt, x, P)
+    t1, t2, W = tables(P, bits, False)
+    xt = to_dev(transposed(x, P.n1, P.n2), bits)       # what GPU_Transpose(x, row = n1, col = n2) leaves
+    try:
+        for knob in (1, 0):
+            capi.tune(3, knob)
+            r = torch.zeros_like(xt)
+            kinds = _kinds_of(lambda: capi.fourstep_ntt(xt.view(batch, n), t1, t2, W, P.modulus, logn, io_contract=capi.FOURSTEP_REFERENCE,
+                                                        out=r.view(batch, n)))
+            got = transposed(to_host(r, bits), P.n1, P.n2)  # the caller's closing GPU_Transpose
+            assert (got == want).all(), f"knob={knob}: {int((got != want).sum())} words differ"
+            assert (to_host(xt, bits) == transposed(x, P.n1, P.n2)).all(), "the call modified its input"
+            lg2 = P.n2.bit_length() - 1
+            covered = lg2 in (7, 8) or 4 <= lg2 - (8 if lg2 - 8 >= 4 else 7) <= 8    # fast_fourstep_rows_t_supported
+            assert (9 in kinds) == (knob == 0 or not covered), kinds
+    finally:
+        capi.tune(3, 1)
+
+
+@pytest.mark.parametrize("logn,batch", [(12, 4), (13, 2), (16, 5), (17, 4), (18, 3), (19, 4), (21, 4), (21, 2), (22, 4), (23, 3)])
+def test_4step_inverse_without_transpose_kernel(logn, batch):
+    """Inverse, both contracts, against NTT_4STEP_CPU::intt.  Fused contract with n1 >= 64: the first pass reads y as a strided
+    pass with a transposing store; reference contract: the product pass stores the n1 x n2 matrix and the last stages run along
+    its rows.  Batches of four or more take the position-major product kernel (pairs resident in shared memory), smaller ones
+    the per-tile kernel in column-chunk-major order."""
+    bits = 64
+    P = O.fourstep_params(logn, O.X_N_minus, bits)
+    n = P.n
+    lg1, lg2 = P.n1.bit_length() - 1, P.n2.bit_length() - 1
+    z = O.example_input(P.modulus, batch * n, seed=11 * logn + batch).reshape(batch, n)
+    want = _threaded(O.fourstep_intt, z, P)
+    it1, it2, iW = tables(P, bits, True)
+    da = lg2 if lg2 <= 8 else max(lg2 - 8, 12 - lg1, 4)
+    db = lg2 - da
+    tuned = (db == 0 and da >= 4) or (db >= 4 and da <= 8)
+    try:
+        for knob in (1, 0):
+            capi.tune(3, knob)
+            zd = to_dev(z, bits)
+            zo = torch.zeros_like(zd)
+            kinds = _kinds_of(lambda: capi.fourstep_ntt(zd.view(batch, n), it1, it2, iW, P.modulus, logn, direction=capi.INVERSE,
+                                                        mod_inverse=P.n_inv, out=zo.view(batch, n)))
+            got = to_host(zo, bits)
+            assert (got == want).all(), f"fused knob={knob}: {int((got != want).sum())} words differ"
+            if knob == 1 and tuned and lg1 >= 6:
+                assert 9 not in kinds, kinds
+            capi.fourstep_ntt(zd.view(batch, n), it1, it2, iW, P.modulus, logn, direction=capi.INVERSE, mod_inverse=P.n_inv)
+            torch.cuda.synchronize()
+            assert (to_host(zd, bits) == want).all(), f"fused in place knob={knob}"
+            pre = to_dev(O.fourstep_intt_first_transpose(z, P), bits)
+            r = torch.zeros_like(pre)
+            kinds = _kinds_of(lambda: capi.fourstep_ntt(pre.view(batch, n), it1, it2, iW, P.modulus, logn, direction=capi.INVERSE,
+                                                        mod_inverse=P.n_inv, io_contract=capi.FOURSTEP_REFERENCE, out=r.view(batch, n)))
+            got = transposed(to_host(r, bits), P.n1, P.n2)
+            assert (got == want).all(), f"reference knob={knob}: {int((got != want).sum())} words differ"
+            if knob == 1 and tuned and da >= 5 and (db == 0 or da + db >= 12):
+                assert 9 not in kinds, kinds
+    finally:
+        capi.tune(3, 1)
