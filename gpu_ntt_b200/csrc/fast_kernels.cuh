@@ -155,7 +155,11 @@ namespace gpuntt_b200
         static constexpr int G1 = 1 << (KTW - LB1 - R1), G2 = 1 << (KTW - LB2 - R2); // twiddle groups
         static constexpr int G3 = R3 > 0 ? (1 << (KTW - LB3 - R3)) : 1;
         static constexpr int TW1 = ((1 << R1) - 1) * G1, TW2 = ((1 << R2) - 1) * G2, TW3 = ((1 << R3) - 1) * G3;
-        static constexpr int TW_SMEM = (TW1 + TW2 + TW3) * (int) sizeof(Twiddle<T>);
+        // inverse: a second copy of the high round's pairs, multiplied by n^-1 (the last round of an inverse transform folds the
+        // scaling into its twiddles, see fast_round)
+        static constexpr int TW1C = INV_ ? TW1 : 0;
+        static constexpr int TWN = TW1 + TW2 + TW3 + TW1C;
+        static constexpr int TW_SMEM = TWN * (int) sizeof(Twiddle<T>);
         static constexpr int SMEM = 2 * TILE_SMEM + TW_SMEM + 128 + 1024; // barriers, segment constants + slack to align the tiles to 1 KiB
         static_assert(LB2 == 0 || LB2 >= CB, "low round must start at bit 0 or on a row boundary");
         static_assert(LB1 >= CB, "high round must start on a row boundary");
@@ -413,25 +417,59 @@ namespace gpuntt_b200
             else
             {
                 if constexpr (WMUL) w_product(false);
-#pragma unroll
-                for (int ab = 0; ab < R; ab++)
-                {
-#pragma unroll
-                    for (int x = 0; x < (E >> (ab + 1)); x++)
-                    {
-                        const Twiddle<T> w = tg[((E >> (ab + 1)) - 1 + x) * G];
-#pragma unroll
-                        for (int y = 0; y < (1 << ab); y++)
-                        {
-                            const int a0 = (x << (ab + 1)) | y;
-                            M.gs(e[a0], e[a0 | (1 << ab)], w);
-                        }
-                    }
-                }
                 if constexpr (FINAL)
                 {
+                    // Last round of the transform: the scaling by n^-1 rides in the twiddles.  A value picks the factor up at the
+                    // first stage of this round in which it is the multiplied output of its butterfly (both inputs of a butterfly
+                    // whose low index bits y are non-zero already carry it), so only element 0 -- never multiplied -- needs a
+                    // product of its own: 1 instead of 2^R extra multiplies per item.  tgc: the round's pairs times n^-1
+                    // (build_twiddles).  TRIV (X^N-1, top of the transform): the twiddle in slot 0 of every stage is 1, so the
+                    // butterflies with x == 0 and y != 0 need no multiply at all.
+                    const Twiddle<T>* tgc = tg + (S::TW1 + S::TW2 + S::TW3);
 #pragma unroll
-                    for (int a = 0; a < E; a++) e[a] = M.canon_inv(e[a], ninv);
+                    for (int ab = 0; ab < R; ab++)
+                    {
+#pragma unroll
+                        for (int x = 0; x < (E >> (ab + 1)); x++)
+                        {
+                            const int slot = (E >> (ab + 1)) - 1 + x;
+                            const Twiddle<T> wc = tgc[slot * G];
+                            Twiddle<T> w = wc;
+                            if (ab > 0 && !(TRIV && x == 0)) w = tg[slot * G];
+#pragma unroll
+                            for (int y = 0; y < (1 << ab); y++)
+                            {
+                                const int a0 = (x << (ab + 1)) | y;
+                                if (y == 0)
+                                    M.gs(e[a0], e[a0 | (1 << ab)], wc);
+                                else if (TRIV && x == 0)
+                                    M.gs_one(e[a0], e[a0 | (1 << ab)]);
+                                else
+                                    M.gs(e[a0], e[a0 | (1 << ab)], w);
+                            }
+                        }
+                    }
+                    e[0] = M.canon_inv(e[0], ninv);
+#pragma unroll
+                    for (int a = 1; a < E; a++) e[a] = M.canon_lazy_inv(e[a]);
+                }
+                else
+                {
+#pragma unroll
+                    for (int ab = 0; ab < R; ab++)
+                    {
+#pragma unroll
+                        for (int x = 0; x < (E >> (ab + 1)); x++)
+                        {
+                            const Twiddle<T> w = tg[((E >> (ab + 1)) - 1 + x) * G];
+#pragma unroll
+                            for (int y = 0; y < (1 << ab); y++)
+                            {
+                                const int a0 = (x << (ab + 1)) | y;
+                                M.gs(e[a0], e[a0 | (1 << ab)], w);
+                            }
+                        }
+                    }
                 }
             }
 
@@ -499,10 +537,11 @@ namespace gpuntt_b200
     // (w, w') pairs for the rounds of shape S, slot-major: entry (slot, group) at slot*G + group; tw1 / tw2 / tw3 are
     // consecutive.  `range`: the index bits above this pass's stage window (see fast_pass_body); lo / plus / n / n_tw as in
     // FastArgs.  Called by every thread of the CTA (thread t of nthreads).
+    // scaled (inverse shapes, the pass that ends the transform): the high round's pairs times n^-1 go behind the three tables.
     template <typename S>
     __device__ __forceinline__ void build_twiddles(Twiddle<typename S::T>* tw1, const typename S::T* __restrict__ seg_table, int range, int n,
                                                    int n_tw, int lo, int plus, typename S::T seg_p, uint64_t seg_mu, int seg_pbits, int t,
-                                                   int nthreads)
+                                                   int nthreads, bool scaled = false, Twiddle<typename S::T> ninv = Twiddle<typename S::T>{0, 0})
     {
         using T = typename S::T;
         Twiddle<T>* tw2 = tw1 + S::TW1;
@@ -528,6 +567,18 @@ namespace gpuntt_b200
                 (hi ? tw1 : (third ? tw3 : tw2))[ii] = Twiddle<T>{wv, shoup_companion_mu(wv, seg_p, seg_mu, seg_pbits)};
             else
                 (hi ? tw1 : (third ? tw3 : tw2))[ii] = Twiddle<T>{wv, shoup_companion_mu32(wv, seg_p, seg_mu)};
+            if constexpr (S::INV)
+            {
+                if (scaled && hi)
+                {
+                    const Mod<T, false> Mx(seg_p);
+                    const T wc = csub(Mx.mul(wv, ninv), seg_p); // w * n^-1 mod p
+                    if constexpr (sizeof(T) == 8)
+                        tw3[S::TW3 + ii] = Twiddle<T>{wc, shoup_companion_mu(wc, seg_p, seg_mu, seg_pbits)};
+                    else
+                        tw3[S::TW3 + ii] = Twiddle<T>{wc, shoup_companion_mu32(wc, seg_p, seg_mu)};
+                }
+            }
         }
     }
 
@@ -581,7 +632,10 @@ namespace gpuntt_b200
 #ifdef GPUNTT_EXPERIMENT_NOCANON // timing experiment only (lazy outputs): what the final canonicalisation costs
             constexpr bool FIN1 = false, FIN2 = false;
 #else
-            constexpr bool FIN1 = (SFIN || !S::STRIDED) && S::R2 == 0, FIN2 = (SFIN || !S::STRIDED) && S::R3 == 0;
+            // (a contiguous pass that carries the twiddle-matrix product is not the end of the transform: the product takes any
+            // 64-bit value and does the range reduction itself)
+            constexpr bool ENDS = SFIN || (!S::STRIDED && !WMUL);
+            constexpr bool FIN1 = ENDS && S::R2 == 0, FIN2 = ENDS && S::R3 == 0;
 #endif
             constexpr bool TS1 = TS && S::R2 == 0, TS2 = TS && S::R2 > 0;
             if constexpr (S::STRIDED && S::POL == 2 && S::G1 == 1)
@@ -617,9 +671,12 @@ namespace gpuntt_b200
                 fast_round<S, S::R2, S::LB2, S::G2, false, false, W2, false, WL>(buf, tw2, M, tid, ninv, wtile, a.lo, 1, false, bar);
                 consumer_sync(bar);
             }
+            // (triv: X^N-1 and this round is the top of the transform -- its slot-0 twiddles are 1)
             if constexpr (S::STRIDED)
             {
-                if (a.last)
+                if (a.last && S::G1 == 1 && triv)
+                    fast_round<S, S::R1, S::LB1, S::G1, true, S::G1 == 1, W1, TS, WL>(buf, tw1, M, tid, ninv, wtile, a.lo, 1, false, bar);
+                else if (a.last)
                     fast_round<S, S::R1, S::LB1, S::G1, true, false, W1, TS, WL>(buf, tw1, M, tid, ninv, wtile, a.lo, 1, false, bar);
                 else
                     fast_round<S, S::R1, S::LB1, S::G1, false, false, W1, TS, WL>(buf, tw1, M, tid, ninv, wtile, a.lo, 1, false, bar);
@@ -627,7 +684,9 @@ namespace gpuntt_b200
             else if constexpr (S::NT > 0)
             {
                 // whole transforms in the tile: the top round is the last one of a single-pass inverse (n^-1 there)
-                if (a.last)
+                if (a.last && S::G1 == 1 && triv)
+                    fast_round<S, S::R1, S::LB1, S::G1, true, S::G1 == 1>(buf, tw1, M, tid, ninv, nullptr, 0, 1, false, bar);
+                else if (a.last)
                     fast_round<S, S::R1, S::LB1, S::G1, true>(buf, tw1, M, tid, ninv, nullptr, 0, 1, false, bar);
                 else
                     fast_round<S, S::R1, S::LB1, S::G1, false>(buf, tw1, M, tid, ninv);
@@ -741,7 +800,9 @@ namespace gpuntt_b200
         int seg_pbits = a.pbits;
         // first pass of a cyclic transform: slot 0 of every stage of the high round is table[0]; when that is 1
         // (it is omega^0 in the reference's tables) those butterflies need no multiply
-        bool triv = S::STRIDED && !S::INV && !a.plus && a.first && (a.lo + S::D == a.n) && a.table[0] == T(1); // inputs canonical by contract
+        // (inverse: the LAST round of a cyclic transform -- the top round of the top strided pass, or of a whole-transform tile)
+        bool triv = S::INV ? ((S::STRIDED ? (a.lo + S::D == a.n) : S::NT > 0) && !a.plus && a.last && a.table[0] == T(1))
+                           : (S::STRIDED && !a.plus && a.first && (a.lo + S::D == a.n) && a.table[0] == T(1)); // inputs canonical by contract
         uint32_t uses0 = 0, uses1 = 0; // how often each buffer has been filled so far (phase tracking)
 
         long long w = w_begin;
@@ -846,9 +907,11 @@ namespace gpuntt_b200
                 ninv = Twiddle<T>{segc->ninv_w, segc->ninv_wq};
                 seg_table = a.table + ((size_t) segc->mi << a.n);
                 M = typename ModOf<S>::type(seg_p);
-                triv = S::STRIDED && !S::INV && !a.plus && a.first && (a.lo + S::D == a.n) && seg_table[0] == T(1);
+                triv = S::INV ? ((S::STRIDED ? (a.lo + S::D == a.n) : S::NT > 0) && !a.plus && a.last && seg_table[0] == T(1))
+                              : (S::STRIDED && !a.plus && a.first && (a.lo + S::D == a.n) && seg_table[0] == T(1));
             }
-            build_twiddles<S>(tw1, seg_table, a.tw_fixed ? 0 : range, n, a.n_tw, a.lo, a.plus, seg_p, seg_mu, seg_pbits, tid, kFastThreads);
+            build_twiddles<S>(tw1, seg_table, a.tw_fixed ? 0 : range, n, a.n_tw, a.lo, a.plus, seg_p, seg_mu, seg_pbits, tid, kFastThreads,
+                              S::INV && a.last, ninv);
             __syncthreads();
 
             if (tid >= kConsumers)

@@ -162,7 +162,7 @@ namespace gpuntt_b200
         unsigned char* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
         unsigned char* bufs = smem;
         Twiddle<T>* twS = reinterpret_cast<Twiddle<T>*>(smem + NB * TILE);
-        Twiddle<T>* twC = twS + (SS::TW1 + SS::TW2);
+        Twiddle<T>* twC = twS + SS::TWN;
         FusedCtl* ctl = reinterpret_cast<FusedCtl*>(smem + NB * TILE + SS::TW_SMEM + SC::TW_SMEM);
 
         const int tid = threadIdx.x;
@@ -362,8 +362,9 @@ namespace gpuntt_b200
             typename ModOf<SS>::type MS(seg_p);
             typename ModOf<SC>::type MC(seg_p);
             const Twiddle<T> ninv = RNS ? Twiddle<T>{(T) ctl->seg_ninv_w, (T) ctl->seg_ninv_wq} : Twiddle<T>{f.s.ninv_w, f.s.ninv_wq};
-            const bool triv = !SS::INV && !f.s.plus && f.s.first && (f.s.lo + SS::D == n) && tabS[0] == T(1);
-            if (doS) build_twiddles<SS>(twS, tabS, 0, n, f.s.n_tw, f.s.lo, f.s.plus, seg_p, seg_mu, seg_pbits, tid, kFusedConsumers);
+            // forward: the strided pass opens a cyclic transform; inverse: it ends one (its last round folds n^-1 into the twiddles)
+            const bool triv = !f.s.plus && (SS::INV ? f.s.last : f.s.first) && (f.s.lo + SS::D == n) && tabS[0] == T(1);
+            if (doS) build_twiddles<SS>(twS, tabS, 0, n, f.s.n_tw, f.s.lo, f.s.plus, seg_p, seg_mu, seg_pbits, tid, kFusedConsumers, SS::INV && f.s.last, ninv);
             if (doC) build_twiddles<SC>(twC, tabC, range, n, f.c.n_tw, 0, f.c.plus, seg_p, seg_mu, seg_pbits, tid, kFusedConsumers);
             asm volatile("bar.sync 3, %0;" ::"n"(kFusedConsumers) : "memory");
             // tile claims run one ahead: the leader takes the NEXT index before the group starts on the current tile, so the

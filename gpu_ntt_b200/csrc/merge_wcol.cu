@@ -57,7 +57,7 @@ namespace gpuntt_b200
         static_assert(sizeof(T) == 8 && S::POL != 0, "64-bit lazy-policy passes");
         static_assert(S::STRIDED || (S::NT > 0 && S::NPLOG == 1 && !TS), "contiguous form: whole transforms inside a tile of two chunks");
         constexpr int TILE = S::TILE_SMEM, NB = kWcolBufs;
-        constexpr int TWN = S::TW1 + S::TW2 + S::TW3;
+        constexpr int TWN = S::TWN;
         extern __shared__ __align__(128) unsigned char smem_raw[];
         unsigned char* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
         unsigned char* bufs = smem;
@@ -164,7 +164,7 @@ namespace gpuntt_b200
             const int g = tid / kConsumers, ctid = tid % kConsumers;
             typename ModOf<S>::type M(a.p);
             const Twiddle<T> ninv{a.ninv_w, a.ninv_wq};
-            const bool triv = S::STRIDED && !S::INV && !a.plus && a.first && (lo + S::D == n) && a.table[0] == T(1);
+            const bool triv = S::STRIDED && !a.plus && (S::INV ? a.last : a.first) && (lo + S::D == n) && a.table[0] == T(1);
             FastArgs<T> aw = a;
             aw.lo = S::STRIDED ? S::C : 0; // the pairs of a tile sit in shared memory in tile order: pair of local element l at index l
             if (ctid == 0) ctl->bcast[g][0] = atomicAdd(&ctl->next_t, 1);
@@ -185,7 +185,8 @@ namespace gpuntt_b200
                 mbar_wait(smem_u32(&ctl->full[b]), (unsigned) (t / NB) & 1u);
                 if (opens)
                 {
-                    build_twiddles<S>(tws, a.table, a.tw_fixed ? 0 : range, n, a.n_tw, lo, a.plus, a.p, a.mu, a.pbits, ctid, kConsumers);
+                    build_twiddles<S>(tws, a.table, a.tw_fixed ? 0 : range, n, a.n_tw, lo, a.plus, a.p, a.mu, a.pbits, ctid, kConsumers,
+                                      S::INV && a.last, ninv);
                     mbar_arrive(smem_u32(&ctl->tw_ready[ri & 1]));
                 }
                 mbar_wait(smem_u32(&ctl->tw_ready[ri & 1]), (unsigned) (ri >> 1) & 1u);

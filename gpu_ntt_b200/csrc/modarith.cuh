@@ -102,10 +102,26 @@ namespace gpuntt_b200
             }
             Y = mul(d, tw);
         }
+        // Gentleman-Sande butterfly with twiddle 1 (the top stages of an inverse X^N-1 transform): no multiply
+        __device__ __forceinline__ void gs_one(T& X, T& Y) const
+        {
+            const T d = X + two_p - Y;
+            const T s = X + Y;
+            if constexpr (sizeof(T) == 4)
+                X = csub(s, two_p);
+            else
+            {
+                const T g = (s >= two_p) ? T(0) - two_p : T(0);
+                X = X + Y + g;
+            }
+            Y = csub(d, two_p);
+        }
         // forward lazy value -> canonical
         __device__ __forceinline__ T canon_fwd(T x) const { return csub(csub(x, two_p), p); }
         // inverse lazy value * n^-1 -> canonical
         __device__ __forceinline__ T canon_inv(T x, const Twiddle<T>& ninv) const { return csub(mul(x, ninv), p); }
+        // inverse lazy value (n^-1 already folded into the twiddles of the last round, see fast_round) -> canonical
+        __device__ __forceinline__ T canon_lazy_inv(T x) const { return csub(x, p); }
     };
 
     // ------------------------------------------------------------------ fast policy (u64, p < 2^60.5)
@@ -220,6 +236,16 @@ namespace gpuntt_b200
         {
             return csub(csub(mul(x, ninv), p + p), p);
         }
+        // twiddle 1: the difference only needs its range back in [0, 4p)
+        __device__ __forceinline__ void gs_one(T& X, T& Y) const
+        {
+            const T d = X + four_p - Y;
+            const T s = X + Y;
+            const T g = (s >= four_p) ? neg_four_p : T(0);
+            X = X + Y + g;
+            Y = csub(d, four_p);
+        }
+        __device__ __forceinline__ T canon_lazy_inv(T x) const { return csub(csub(x, p + p), p); } // [0, 4p) -> [0, p)
     };
 
     // ------------------------------------------------------------------ "F60" forward policy (u64, 2^40 <= p < 2^60 - 2^31)
