@@ -185,13 +185,12 @@ namespace gpuntt_b200
                 mbar_wait(smem_u32(&ctl->full[b]), (unsigned) (t / NB) & 1u);
                 if (opens)
                 {
-                    build_twiddles<S>(tws, a.table, a.tw_fixed ? 0 : range, n, a.n_tw, lo, a.plus, a.p, a.mu, a.pbits, ctid, kConsumers,
-                                      S::INV && a.last, ninv);
+                    build_twiddles<S>(tws, a.table, a.tw_fixed ? 0 : range, n, a.n_tw, lo, a.plus, a.p, a.mu, a.pbits, ctid, kConsumers);
                     mbar_arrive(smem_u32(&ctl->tw_ready[ri & 1]));
                 }
                 mbar_wait(smem_u32(&ctl->tw_ready[ri & 1]), (unsigned) (ri >> 1) & 1u);
                 mbar_wait(smem_u32(&ctl->pairs_full), (unsigned) k & 1u); // this position's pairs are in shared memory
-                tile_rounds<S, true, false, TS, true>(bufs + b * TILE, tws, tws + S::TW1, tws + S::TW1 + S::TW2, M, ctid, ninv, pairs, aw, triv, 1 + g);
+                tile_rounds<S, true, false, TS, true, 0>(bufs + b * TILE, tws, tws + S::TW1, tws + S::TW1 + S::TW2, M, ctid, ninv, pairs, aw, triv, 1 + g);
                 fence_async();
                 mbar_arrive(smem_u32(&ctl->done[b]));
                 consumer_sync(1 + g);
@@ -252,6 +251,7 @@ namespace gpuntt_b200
             cached_sms[dev].store(sms, std::memory_order_release);
         }
         if (a.batch < 4) return cudaErrorNotSupported; // too little reuse to pay for the position-major order (and see the twiddle sets)
+        if (S::INV && a.last) return cudaErrorNotSupported; // (the kernel carries no last-round code: tile_rounds LASTC = 0)
         if (TS && a.in == a.out) return cudaErrorNotSupported;
         alignas(64) CUtensorMap m_in, m_out, m_pairs;
         long long npos;

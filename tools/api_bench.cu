@@ -163,10 +163,32 @@ static void merge_case(const char* name, int logn, int batch, bool inverse, bool
     double ms = round_trip ? time_ms([&]() { fwd(); inv(); }, iters) : (inverse ? time_ms(inv, iters) : time_ms(fwd, iters));
     double ntts = (double) batch * (round_trip ? 2 : 1);
     double gbs = 2.0 * n * sizeof(T) * ntts / (ms * 1e-3) / 1e9;
+    // launch-bound cases: what one call costs the HOST thread (enqueue only, nothing waited for) and what a call costs in a
+    // stream of back-to-back calls (the larger of host and device time per call)
+    double host_us = 0, stream_us = 0;
+    if (batch <= 128 && !round_trip)
+    {
+        const int reps = 300;
+        auto one = [&]() { if (inverse) inv(); else fwd(); };
+        CK(cudaDeviceSynchronize());
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        CK(cudaEventRecord(e0, 0));
+        auto t0 = std::chrono::steady_clock::now();
+        for (int i = 0; i < reps; i++) one();
+        auto t1 = std::chrono::steady_clock::now();
+        CK(cudaEventRecord(e1, 0));
+        CK(cudaEventSynchronize(e1));
+        float sm = 0;
+        CK(cudaEventElapsedTime(&sm, e0, e1));
+        host_us = std::chrono::duration<double, std::micro>(t1 - t0).count() / reps;
+        stream_us = sm * 1e3 / reps;
+    }
     printf("{\"lib\": \"%s\", \"case\": \"%s\", \"bits\": %d, \"logn\": %d, \"batch\": %d, \"ring\": \"%s\", \"mod_count\": %d, \"op\": \"%s\", "
-           "\"parity_vs_NTTCPU\": %s, \"ms\": %.4f, \"ntt_per_s\": %.1f, \"alg_GBps\": %.1f}\n",
+           "\"parity_vs_NTTCPU\": %s, \"host_us_per_call\": %.2f, \"stream_us_per_call\": %.2f, \"ms\": %.4f, \"ntt_per_s\": %.1f, \"alg_GBps\": %.1f}\n",
            g_label, name, (int) sizeof(T) * 8, logn, batch, ring == ReductionPolynomial::X_N_minus ? "X^N-1" : "X^N+1", mod_count, round_trip ? "fwd+inv" : (inverse ? "inv" : "fwd"), ok ? "true" : "false",
-           ms, ntts / (ms * 1e-3), gbs);
+           host_us, stream_us, ms, ntts / (ms * 1e-3), gbs);
     fflush(stdout);
     cudaFree(d);
     cudaFree(dft);

@@ -14,18 +14,18 @@ for logn, batch in ((12, 4), (16, 4), (17, 5)):
     P = O.fourstep_params(logn, O.X_N_minus, 64)
     n = P.n
     x = O.example_input(P.modulus, batch * n, seed=logn).reshape(batch, n)
-    want = np.stack([O.fourstep_ntt(r, P) for r in x]).reshape(-1)
+    want = np.stack([O.fourstep_ntt(r, P) for r in x])
     t1, t2, W = tables(P, 64, False)
     xt = to_dev(transposed(x, P.n1, P.n2), 64); r = torch.zeros_like(xt)
     capi.fourstep_ntt(xt.view(batch, n), t1, t2, W, P.modulus, logn, io_contract=capi.FOURSTEP_REFERENCE, out=r.view(batch, n)); torch.cuda.synchronize()
-    assert (transposed(to_host(r, 64), P.n1, P.n2) == want).all()
+    assert (transposed(to_host(r, 64), P.n1, P.n2).reshape(-1) == want.reshape(-1)).all()
     it1, it2, iW = tables(P, 64, True)
     y = to_dev(want, 64); o = torch.zeros_like(y)
     capi.fourstep_ntt(y.view(batch, n), it1, it2, iW, P.modulus, logn, direction=capi.INVERSE, mod_inverse=P.n_inv, out=o.view(batch, n)); torch.cuda.synchronize()
-    assert (to_host(o, 64) == x.reshape(-1)).all()
-    pre = to_dev(np.stack([O.fourstep_intt_first_transpose(r_, P) for r_ in want.reshape(batch, n)]), 64); r2 = torch.zeros_like(pre)
+    assert (to_host(o, 64).reshape(-1) == x.reshape(-1)).all()
+    pre = to_dev(np.stack([O.fourstep_intt_first_transpose(r_, P) for r_ in want]), 64); r2 = torch.zeros_like(pre)
     capi.fourstep_ntt(pre.view(batch, n), it1, it2, iW, P.modulus, logn, direction=capi.INVERSE, mod_inverse=P.n_inv, io_contract=capi.FOURSTEP_REFERENCE, out=r2.view(batch, n)); torch.cuda.synchronize()
-    assert (transposed(to_host(r2, 64), P.n1, P.n2) == x.reshape(-1)).all()
+    assert (transposed(to_host(r2, 64), P.n1, P.n2).reshape(-1) == x.reshape(-1)).all()
     print("ok", logn, batch, flush=True)
 PY
 for tool in memcheck racecheck; do
