@@ -568,7 +568,7 @@ namespace gpuntt_b200
                 (hi ? tw1 : (third ? tw3 : tw2))[ii] = Twiddle<T>{wv, shoup_companion_mu(wv, seg_p, seg_mu, seg_pbits)};
             else
                 (hi ? tw1 : (third ? tw3 : tw2))[ii] = Twiddle<T>{wv, shoup_companion_mu32(wv, seg_p, seg_mu)};
-            if constexpr (S::INV)
+            if constexpr (S::TW1C > 0)
             {
                 if (scaled && hi)
                 {

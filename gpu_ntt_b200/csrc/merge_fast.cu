@@ -20,6 +20,17 @@ namespace gpuntt_b200
     {
         return element_bits == 64 ? (n_power >= 7 && n_power <= 11) : (n_power >= 8 && n_power <= 12);
     }
+    // Rings of exactly one tile (64-bit 2^12, 32-bit 2^13): the whole polynomial in ONE tile, three register rounds, one launch and
+    // one HBM round trip with nothing handed from CTA to CTA -- the shortest critical path this library has for these sizes
+    // (every twiddle pair of the transform sits in shared memory: 64 KiB beside the two 32 KiB tile buffers, so one CTA per
+    // SM).  Taken for batches of at most g_one_tile_batch polynomials (the launch-bound regime); above that the two-pass
+    // plan with twice the resident warps has the higher throughput.
+    static std::atomic<int> g_one_tile_batch{296};
+    void fast_set_one_tile_batch(int v) { g_one_tile_batch.store(v < 0 ? 0 : v); }
+    static bool fast_one_tile(int n_power, int element_bits, int batch)
+    {
+        return n_power == (element_bits == 64 ? 12 : 13) && batch <= g_one_tile_batch.load();
+    }
 
     // text form of the tuned plan for gpuntt_b200_describe_plan; returns the number of launches (0: not covered)
     int fast_describe(int n_power, int element_bits, char* buf, size_t len)
@@ -56,6 +67,7 @@ namespace gpuntt_b200
                 case 9: return launch_fast<Shape<T, INV, POL, false, 2, 3, 12, 1, 9, 4>>(s, st);
                 case 10: return launch_fast<Shape<T, INV, POL, false, 3, 3, 12, 1, 10, 4>>(s, st);
                 case 11: return launch_fast<Shape<T, INV, POL, false, 3, 4, 12, 1, 11, 4>>(s, st);
+                case 12: return launch_fast<Shape<T, INV, POL, false, 4, 4, 12, 0, 12, 4>>(s, st);
                 default: return cudaErrorNotSupported;
             }
         }
@@ -68,6 +80,7 @@ namespace gpuntt_b200
                 case 10: return launch_fast<Shape<T, INV, POL, false, 5, 5, 13, 1, 10>>(s, st);
                 case 11: return launch_fast<Shape<T, INV, POL, false, 3, 3, 13, 1, 11, 5>>(s, st);
                 case 12: return launch_fast<Shape<T, INV, POL, false, 3, 4, 13, 1, 12, 5>>(s, st);
+                case 13: return launch_fast<Shape<T, INV, POL, false, 4, 4, 13, 0, 13, 5>>(s, st);
                 default: return cudaErrorNotSupported;
             }
         }
@@ -77,7 +90,9 @@ namespace gpuntt_b200
     static cudaError_t fast_small(const FastArgs<T>& a, const T* in, T* out, int n_power, bool inverse, int batch, cudaStream_t st, int* launched,
                                   void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t))
     {
-        constexpr int KC = sizeof(T) == 8 ? 11 : 12; // chunk = one row group of a two-group tile
+        // chunk = one row group of a two-group tile; the one-tile rings: chunk = tile = polynomial
+        const bool one_tile = n_power == (sizeof(T) == 8 ? 12 : 13);
+        const int KC = (sizeof(T) == 8 ? 11 : 12) + (one_tile ? 1 : 0);
         const long long elems = (long long) batch << n_power;
         if (elems & ((1LL << KC) - 1)) return cudaSuccess;
         const long long chunks = elems >> KC;
@@ -91,7 +106,7 @@ namespace gpuntt_b200
         s.first = 1;
         s.last = 1;
         s.batch = (int) chunks;
-        s.work = (chunks + 1) >> 1;
+        s.work = one_tile ? chunks : (chunks + 1) >> 1;
         // arithmetic policy: 64-bit forward F60, inverse lazy; 32-bit forward lazy (p <= 2^29), inverse exact
         bool covered;
         if constexpr (sizeof(T) == 8)
@@ -122,7 +137,7 @@ namespace gpuntt_b200
     {
         *launched = 0;
         if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return cudaSuccess;
-        if (fast_small_supported(n_power, (int) sizeof(T) * 8))
+        if (fast_small_supported(n_power, (int) sizeof(T) * 8) || fast_one_tile(n_power, (int) sizeof(T) * 8, batch))
         {
             if (sizeof(T) == 4 && ((uint32_t) p >= (1u << 30) || (uint32_t) p < 3)) return cudaSuccess;
             if (sizeof(T) == 8 && ((uint64_t) p >= (1ull << 62) || (uint64_t) p < 3)) return cudaSuccess;
@@ -145,7 +160,9 @@ namespace gpuntt_b200
             a.plus = plus;
             a.in_bound = 1;
             a.signed_io = signed_io;
-            return fast_small<T>(a, in, out, n_power, inverse, batch, st, launched, prof_begin, prof_end);
+            const cudaError_t e = fast_small<T>(a, in, out, n_power, inverse, batch, st, launched, prof_begin, prof_end);
+            if (e != cudaSuccess || *launched > 0 || fast_small_supported(n_power, (int) sizeof(T) * 8)) return e;
+            // (a one-tile ring the single-tile kernel declined: the two-pass plan below)
         }
         if (!fast_supported(n_power, (int) sizeof(T) * 8)) return cudaSuccess;
         // TMA coordinates are signed 32-bit: the matrix-row index of the finest strided pass must fit

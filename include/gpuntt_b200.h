@@ -205,6 +205,10 @@ void gpuntt_b200_force_generic_path(int on);
 /*   4STEP_RESIDENT_PAIRS  1 (default): the transposing column pass walks the batch through one tile position at a time with
  *                 that position's (W, W') pairs resident in shared memory (merge_wcol.cu); 0: pairs fetched per tile. */
 #define GPUNTT_B200_TUNE_4STEP_RESIDENT_PAIRS 5
+/*   ONE_TILE_BATCH  64-bit N = 2^12 and 32-bit N = 2^13 are exactly one tile: calls of at most this many polynomials (default 296
+ *                 = two per SM) run the whole transform inside one tile -- one launch, one HBM round trip, no hand-off between
+ *                 CTAs, the shortest critical path -- larger ones the two-pass plan (twice the resident warps).  0: never. */
+#define GPUNTT_B200_TUNE_ONE_TILE_BATCH 6
 void gpuntt_b200_tune(int knob, int value);
 
 /* Batch-slice helpers for callers whose whole batch lives on ONE GPU: device g of ndev owns the
