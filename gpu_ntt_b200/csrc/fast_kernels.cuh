@@ -549,35 +549,60 @@ namespace gpuntt_b200
         Twiddle<T>* tw3 = tw2 + S::TW2;
         const int j0 = S::STRIDED ? (range << S::D) : (S::NT ? 0 : (range << S::KC)); // index (>> lo) of the tile's first row
         const int ntw = n_tw ? n_tw : n;
-        for (int i = t; i < S::TW1 + S::TW2 + S::TW3; i += nthreads)
+        constexpr int TOTAL = S::TW1 + S::TW2 + S::TW3;
+        // position of entry i in the caller's table (G1 / G2 / G3 are powers of two)
+        auto locate = [&](int i, int& ii, bool& hi, bool& third) -> long long
         {
-            const bool hi = i < S::TW1, third = S::R3 > 0 && i >= S::TW1 + S::TW2;
-            const int ii = hi ? i : (third ? i - S::TW1 - S::TW2 : i - S::TW1);
-            const int R = hi ? S::R1 : (third ? S::R3 : S::R2), LB = hi ? S::LB1 : (third ? S::LB3 : S::LB2),
-                      G = hi ? S::G1 : (third ? S::G3 : S::G2);
-            const int slot = ii / G, group = ii % G;
+            hi = i < S::TW1;
+            third = S::R3 > 0 && i >= S::TW1 + S::TW2;
+            ii = hi ? i : (third ? i - S::TW1 - S::TW2 : i - S::TW1);
+            const int R = hi ? S::R1 : (third ? S::R3 : S::R2), LB = hi ? S::LB1 : (third ? S::LB3 : S::LB2);
+            const int lg = hi ? (S::KTW - S::LB1 - S::R1) : (third ? (S::KTW - S::LB3 - S::R3) : (S::KTW - S::LB2 - S::R2)); // log2 G
+            const int slot = ii >> lg, group = ii & ((1 << lg) - 1);
             // slot -> (ab, x): slot = 2^(R-1-ab) - 1 + x
             const int lvl = 31 - __clz(slot + 1); // = R-1-ab
             const int ab = R - 1 - lvl, x = slot + 1 - (1 << lvl);
             const int rb0 = LB - S::C;
-            const int s = ntw - 1 - lo - (rb0 + ab);
+            const int sft = ntw - 1 - lo - (rb0 + ab);
             const int J = j0 | (group << (LB + R - S::C));
-            const long long idx = ((long long) plus << s) + (J >> (rb0 + ab + 1)) + x;
-            const T wv = seg_table[idx];
-            if constexpr (sizeof(T) == 8)
-                (hi ? tw1 : (third ? tw3 : tw2))[ii] = Twiddle<T>{wv, shoup_companion_mu(wv, seg_p, seg_mu, seg_pbits)};
-            else
-                (hi ? tw1 : (third ? tw3 : tw2))[ii] = Twiddle<T>{wv, shoup_companion_mu32(wv, seg_p, seg_mu)};
-            if constexpr (S::TW1C > 0)
+            return ((long long) plus << sft) + (J >> (rb0 + ab + 1)) + x;
+        };
+        // UN table loads are in flight together: a CTA with few tiles (the launch-bound regime) has this loop on its critical
+        // path, and one global-memory latency per ENTRY was most of a small call's kernel time
+        constexpr int UN = 4;
+        for (int i0 = t; i0 < TOTAL; i0 += UN * nthreads)
+        {
+            T wv[UN];
+            int ii[UN];
+            bool hi[UN], third[UN];
+#pragma unroll
+            for (int u = 0; u < UN; u++)
             {
-                if (scaled && hi)
+                const int i = i0 + u * nthreads;
+                wv[u] = T(0);
+                if (i < TOTAL) wv[u] = seg_table[locate(i, ii[u], hi[u], third[u])];
+            }
+#pragma unroll
+            for (int u = 0; u < UN; u++)
+            {
+                const int i = i0 + u * nthreads;
+                if (i >= TOTAL) break;
+                Twiddle<T>* dst = hi[u] ? tw1 : (third[u] ? tw3 : tw2);
+                if constexpr (sizeof(T) == 8)
+                    dst[ii[u]] = Twiddle<T>{wv[u], shoup_companion_mu(wv[u], seg_p, seg_mu, seg_pbits)};
+                else
+                    dst[ii[u]] = Twiddle<T>{wv[u], shoup_companion_mu32(wv[u], seg_p, seg_mu)};
+                if constexpr (S::TW1C > 0)
                 {
-                    const Mod<T, false> Mx(seg_p);
-                    const T wc = csub(Mx.mul(wv, ninv), seg_p); // w * n^-1 mod p
-                    if constexpr (sizeof(T) == 8)
-                        tw3[S::TW3 + ii] = Twiddle<T>{wc, shoup_companion_mu(wc, seg_p, seg_mu, seg_pbits)};
-                    else
-                        tw3[S::TW3 + ii] = Twiddle<T>{wc, shoup_companion_mu32(wc, seg_p, seg_mu)};
+                    if (scaled && hi[u])
+                    {
+                        const Mod<T, false> Mx(seg_p);
+                        const T wc = csub(Mx.mul(wv[u], ninv), seg_p); // w * n^-1 mod p
+                        if constexpr (sizeof(T) == 8)
+                            tw3[S::TW3 + ii[u]] = Twiddle<T>{wc, shoup_companion_mu(wc, seg_p, seg_mu, seg_pbits)};
+                        else
+                            tw3[S::TW3 + ii[u]] = Twiddle<T>{wc, shoup_companion_mu32(wc, seg_p, seg_mu)};
+                    }
                 }
             }
         }
@@ -1282,6 +1307,7 @@ namespace gpuntt_b200
     cudaError_t fused_merge_rns(const FastArgs<T>& a, const FastPlan& pl, bool inverse, unsigned* counters, cudaStream_t st,
                                 void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t));
     void fused_set_lag_steps(int v);
+    void fused_set_small_tile_elems(long long v); // 64-bit calls of at most this many elements run on 1024-element tiles
     void fused_set_policy(int v); // 1: where measured faster, 2: wherever the shapes allow
 
     struct FastPlan

@@ -1,6 +1,8 @@
 // gpu_ntt_b200/csrc/merge_fast.cu -- tuned Merge-NTT entry points for single-modulus calls (unsigned data, PerPolynomial layout):
 //   fast_merge   GPU_NTT / GPU_INTT: 64-bit rings 2^7..2^24, 32-bit 2^8..2^26 (small rings in one pass: fast_small)
 // Kernels and the launch helper live in fast_kernels.cuh.
+#include <cstdlib>
+
 #include "fast_kernels.cuh"
 
 namespace gpuntt_b200
@@ -25,7 +27,12 @@ namespace gpuntt_b200
     // (every twiddle pair of the transform sits in shared memory: 64 KiB beside the two 32 KiB tile buffers, so one CTA per
     // SM).  Taken for batches of at most g_one_tile_batch polynomials (the launch-bound regime); above that the two-pass
     // plan with twice the resident warps has the higher throughput.
-    static std::atomic<int> g_one_tile_batch{296};
+    static int one_tile_default()
+    {
+        const char* e = getenv("GPUNTT_B200_ONE_TILE_BATCH"); // (A/B runs of binaries that cannot call gpuntt_b200_tune)
+        return e ? atoi(e) : 296;
+    }
+    static std::atomic<int> g_one_tile_batch{one_tile_default()};
     void fast_set_one_tile_batch(int v) { g_one_tile_batch.store(v < 0 ? 0 : v); }
     static bool fast_one_tile(int n_power, int element_bits, int batch)
     {

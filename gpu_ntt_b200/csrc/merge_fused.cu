@@ -26,6 +26,27 @@
 namespace gpuntt_b200
 {
 
+#ifdef GPUNTT_TIMELINE
+    // Lab build only (tools/build_variant.sh timeline -DGPUNTT_TIMELINE): SM cycle counter at the hand-off points of a CTA's FIRST
+    // tile, read back by tools/fused_timeline.py -- where the microseconds of a launch-bound call go.
+    __device__ long long g_timeline[512][16];
+    __device__ __forceinline__ void tl_mark(int slot)
+    {
+        if (blockIdx.x < 512) g_timeline[blockIdx.x][slot] = clock64();
+    }
+    __device__ __forceinline__ void tl_mark_global(int slot)
+    {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (blockIdx.x < 512) g_timeline[blockIdx.x][slot] = (long long) t;
+    }
+#define TL(slot) tl_mark(slot)
+#define TLG(slot) tl_mark_global(slot)
+#else
+#define TL(slot)
+#define TLG(slot)
+#endif
+
     template <typename T> struct FusedArgs
     {
         FastArgs<T> s, c;     // the strided pass / the contiguous pass (in, out, work, rr, cta_per_seg unused)
@@ -205,6 +226,11 @@ namespace gpuntt_b200
                 cur.q_step = kk;
             }
         }
+        if (tid == 0)
+        {
+            TL(0);
+            TLG(15);
+        }
         const bool doS = cur.s_next < cur.s_end, doC = cur.q_next < cur.q_end;
         const int total = (doS ? (int) ((cur.s_end - 1 - cur.s_next) / cur.s_step + 1) : 0) + (doC ? (cur.q_end - 1 - cur.q_next) / cur.q_step + 1 : 0);
 
@@ -255,6 +281,7 @@ namespace gpuntt_b200
             fence_async();
         }
         __syncthreads();
+        if (tid == 0) TL(1);
         const T seg_p = RNS ? (T) ctl->seg_p : f.s.p;
         const uint64_t seg_mu = RNS ? ctl->seg_mu : f.s.mu;
         const int seg_pbits = RNS ? ctl->seg_pbits : f.s.pbits;
@@ -272,6 +299,7 @@ namespace gpuntt_b200
                 const bool second = fwd ? (tl.kind == 1) : (tl.kind == 0);
                 const int b = t % NB;
                 if (t >= NB) mbar_wait(smem_u32(&ctl->free_[b]), (unsigned) (t / NB - 1) & 1u); // the storer released this buffer
+                if (t == 0) TL(2);
                 if (second)
                 {
                     // every first-pass tile of the polynomials this tile touches has been stored
@@ -297,6 +325,7 @@ namespace gpuntt_b200
                     }
                     asm volatile("fence.proxy.async.global;" ::: "memory"); // the bulk read below is ordered after the acquire loads
                 }
+                if (t == 0) TL(3);
                 const uint32_t bar = smem_u32(&ctl->full[b]);
                 const uint32_t dst = smem_u32(bufs + b * TILE);
                 ctl->kind[b] = tl.kind; // (released by the arrive below, acquired by the consumers' wait)
@@ -324,6 +353,7 @@ namespace gpuntt_b200
                 const bool second = fwd ? (tl.kind == 1) : (tl.kind == 0);
                 const int b = t % NB;
                 mbar_wait(smem_u32(&ctl->done[b]), (unsigned) (t / NB) & 1u); // a consumer group finished this tile
+                if (t == 0) TL(7);
                 const uint32_t src = smem_u32(bufs + b * TILE);
                 const CUtensorMap* mp = second ? &mapB : &mapA_out;
                 if (tl.kind == 0)
@@ -337,6 +367,7 @@ namespace gpuntt_b200
                     tma_store_3d(mp, 0, range << (SC::KC - SC::CB), (int) (tl.id << SC::NPLOG), src);
                 bulk_commit();
                 bulk_wait_read0();
+                if (t == 0) TL(8);
                 mbar_arrive(smem_u32(&ctl->free_[b])); // the loader may refill the buffer
                 if (!second)
                 {
@@ -351,9 +382,11 @@ namespace gpuntt_b200
                         if (p1 > batch) p1 = batch;
                         for (long long p = p0; p < p1; p++) red_release_add(f.counters + p * mc + mslot, 1u);
                     }
+                    if (t == 0) TL(9);
                 }
             }
             bulk_wait0();
+            TL(10);
         }
         else if (tid < kFusedConsumers)
         {
@@ -367,6 +400,7 @@ namespace gpuntt_b200
             if (doS) build_twiddles<SS>(twS, tabS, 0, n, f.s.n_tw, f.s.lo, f.s.plus, seg_p, seg_mu, seg_pbits, tid, kFusedConsumers, SS::INV && f.s.last, ninv);
             if (doC) build_twiddles<SC>(twC, tabC, range, n, f.c.n_tw, 0, f.c.plus, seg_p, seg_mu, seg_pbits, tid, kFusedConsumers);
             asm volatile("bar.sync 3, %0;" ::"n"(kFusedConsumers) : "memory");
+            if (tid == 0) TL(4);
             // tile claims run one ahead: the leader takes the NEXT index before the group starts on the current tile, so the
             // shared-memory atomic and its broadcast are off the critical path
             if (ctid == 0) ctl->bcast[g][0] = atomicAdd(&ctl->next_t, 1);
@@ -378,11 +412,13 @@ namespace gpuntt_b200
                 const int b = t % NB;
                 unsigned char* buf = bufs + b * TILE;
                 mbar_wait(smem_u32(&ctl->full[b]), (unsigned) (t / NB) & 1u); // tile landed
+                if (t == 0 && ctid == 0) TL(5);
                 if (ctl->kind[b] == 0)
                     tile_rounds<SS, false>(buf, twS, twS + SS::TW1, twS + SS::TW1 + SS::TW2, MS, ctid, ninv, nullptr, f.s, triv, 1 + g);
                 else
                     tile_rounds<SC, false>(buf, twC, twC + SC::TW1, twC + SC::TW1 + SC::TW2, MC, ctid, ninv, nullptr, f.c, false, 1 + g);
                 fence_async(); // make the generic-proxy writes visible to the bulk store
+                if (t == 0 && ctid == 0) TL(6);
                 mbar_arrive(smem_u32(&ctl->done[b]));
                 consumer_sync(1 + g);
                 t = ctl->bcast[g][(it + 1) & 1];
@@ -390,6 +426,7 @@ namespace gpuntt_b200
         }
         // ---- the counters go back to zero: the last CTA to finish (every other CTA has made all its observations) clears them
         __syncthreads();
+        if (tid == 0) TL(11);
         if (tid == 0)
         {
             __threadfence();
@@ -402,6 +439,7 @@ namespace gpuntt_b200
             for (long long i = tid; i < (long long) batch * mc; i += kFusedThreads) f.counters[i] = 0u;
             if (tid == 0) f.counters[f.ticket_off] = 0u;
         }
+        if (tid == 0) TL(12);
     }
 
     template <typename SS, typename SC>
@@ -574,6 +612,15 @@ namespace gpuntt_b200
         return cudaGetLastError();
     }
 
+    // Launch-bound calls (64-bit): what such a call costs is the critical path through ONE tile of each pass -- tile load, two
+    // register rounds of 32 butterflies per thread, store (profiles/r2_fused_timeline.txt: 5.2 of the 10.5 us of a 2^12 x 8 call
+    // are the rounds of one 4096-element tile per CTA, bound by the SM's own multiplier pipes, while 130 SMs idle).  Calls of
+    // at most g_small_tile_elems elements therefore run on 1024-element tiles (K = 10): four times the CTAs, a quarter of the
+    // arithmetic on each tile's critical path.  Rings 2^12 .. 2^14 (a strided tile needs 2^(10 - d) >= 16 adjacent elements).
+    static std::atomic<long long> g_small_tile_elems{1LL << 19};
+    void fused_set_small_tile_elems(long long v) { g_small_tile_elems.store(v < 0 ? 0 : v); }
+    static bool small_tiles(long long polys, int n, int d) { return d >= 4 && d <= 6 && (polys << n) <= g_small_tile_elems.load(); }
+
     // Two-pass plans in one launch.  Returns cudaErrorNotSupported when the shape / modulus is not covered.
     template <typename T>
     cudaError_t fused_merge(const FastArgs<T>& a, const FastPlan& pl, bool inverse, bool f60_or_l32, bool lazy_inv, unsigned* counters,
@@ -585,6 +632,24 @@ namespace gpuntt_b200
         {
             using Cf = Shape<T, false, 2, false, 4, 4, 12, 1>;
             using Ci = Shape<T, true, 1, false, 4, 4, 12, 1>;
+            if (small_tiles(a.batch, a.n, d) && (inverse ? lazy_inv : f60_or_l32))
+            {
+                using Cfs = Shape<T, false, 2, false, 4, 4, 10, 0>;
+                using Cis = Shape<T, true, 1, false, 4, 4, 10, 0>;
+                if (!inverse)
+                    switch (d)
+                    {
+                        case 4: return launch_fused<Shape<T, false, 2, true, 4, 0, 10, 0>, Cfs>(a, lo, false, counters, st, prof_begin, prof_end);
+                        case 5: return launch_fused<Shape<T, false, 2, true, 3, 2, 10, 0>, Cfs>(a, lo, false, counters, st, prof_begin, prof_end);
+                        default: return launch_fused<Shape<T, false, 2, true, 3, 3, 10, 0>, Cfs>(a, lo, false, counters, st, prof_begin, prof_end);
+                    }
+                switch (d)
+                {
+                    case 4: return launch_fused<Shape<T, true, 1, true, 4, 0, 10, 0>, Cis>(a, lo, true, counters, st, prof_begin, prof_end);
+                    case 5: return launch_fused<Shape<T, true, 1, true, 3, 2, 10, 0>, Cis>(a, lo, true, counters, st, prof_begin, prof_end);
+                    default: return launch_fused<Shape<T, true, 1, true, 3, 3, 10, 0>, Cis>(a, lo, true, counters, st, prof_begin, prof_end);
+                }
+            }
             if (!inverse)
             {
                 if (!f60_or_l32) return cudaErrorNotSupported;
@@ -667,6 +732,25 @@ namespace gpuntt_b200
             using Cfx = Shape<T, false, 0, false, 4, 4, 12, 1>;
             using Ci = Shape<T, true, 1, false, 4, 4, 12, 1>;
             using Cix = Shape<T, true, 0, false, 4, 4, 12, 1>;
+            if (small_tiles((long long) a.batch * a.mod_count, a.n, d))
+            {
+                using Cfs = Shape<T, false, 2, false, 4, 4, 10, 0>;
+                using Cfxs = Shape<T, false, 0, false, 4, 4, 10, 0>;
+                using Cis = Shape<T, true, 1, false, 4, 4, 10, 0>;
+                using Cixs = Shape<T, true, 0, false, 4, 4, 10, 0>;
+#define GPUNTT_FUSED_RNS64S(R1, R2)                                                                                                              \
+    (inverse ? launch_fused<Shape<T, true, 1, true, R1, R2, 10, 0>, Cis, Shape<T, true, 0, true, R1, R2, 10, 0>, Cixs>(a, lo, true, counters, st,    \
+                                                                                                                      prof_begin, prof_end)       \
+             : launch_fused<Shape<T, false, 2, true, R1, R2, 10, 0>, Cfs, Shape<T, false, 0, true, R1, R2, 10, 0>, Cfxs>(a, lo, false, counters, st, \
+                                                                                                                        prof_begin, prof_end))
+                switch (d)
+                {
+                    case 4: return GPUNTT_FUSED_RNS64S(4, 0);
+                    case 5: return GPUNTT_FUSED_RNS64S(3, 2);
+                    default: return GPUNTT_FUSED_RNS64S(3, 3);
+                }
+#undef GPUNTT_FUSED_RNS64S
+            }
 #define GPUNTT_FUSED_RNS64(R1, R2)                                                                                                               \
     (inverse ? launch_fused<Shape<T, true, 1, true, R1, R2, 12, 0>, Ci, Shape<T, true, 0, true, R1, R2, 12, 0>, Cix>(a, lo, true, counters, st,      \
                                                                                                                     prof_begin, prof_end)         \
@@ -708,6 +792,20 @@ namespace gpuntt_b200
                                                    void (*)(int, cudaStream_t), void (*)(cudaStream_t));
     template cudaError_t fused_merge_rns<uint32_t>(const FastArgs<uint32_t>&, const FastPlan&, bool, unsigned*, cudaStream_t,
                                                    void (*)(int, cudaStream_t), void (*)(cudaStream_t));
+
+#ifdef GPUNTT_TIMELINE
+    extern "C" int gpuntt_b200_timeline_read(long long* out, int clear)
+    {
+        if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+        if (cudaMemcpyFromSymbol(out, g_timeline, sizeof(g_timeline)) != cudaSuccess) return -1;
+        if (clear)
+        {
+            static long long zeros[512][16];
+            cudaMemcpyToSymbol(g_timeline, zeros, sizeof(zeros));
+        }
+        return 512 * 16;
+    }
+#endif
 
     template cudaError_t fused_merge<uint64_t>(const FastArgs<uint64_t>&, const FastPlan&, bool, bool, bool, unsigned*, cudaStream_t,
                                                void (*)(int, cudaStream_t), void (*)(cudaStream_t));

@@ -641,6 +641,7 @@ namespace gpuntt_b200
                            void (*prof_end)(cudaStream_t), int in_bound = 1, unsigned* counters = nullptr, int signed_io = 0);
     void fused_set_lag_steps(int v); // merge_fused.cu
     void fused_set_policy(int v);
+    void fused_set_small_tile_elems(long long v);
     void fourstep_set_resident_pairs(int on); // merge_fast_4step.cu
     void fast_set_one_tile_batch(int v);      // merge_fast.cu
     bool fast_supported(int n_power, int element_bits);
@@ -1251,6 +1252,7 @@ extern "C"
             case GPUNTT_B200_TUNE_4STEP_MODULUS_CACHE: g_fourstep_modcache.store(value); break;
             case GPUNTT_B200_TUNE_4STEP_RESIDENT_PAIRS: fourstep_set_resident_pairs(value); break;
             case GPUNTT_B200_TUNE_ONE_TILE_BATCH: fast_set_one_tile_batch(value); break;
+            case GPUNTT_B200_TUNE_SMALL_TILE_ELEMS: fused_set_small_tile_elems(value); break;
             default: break;
         }
     }

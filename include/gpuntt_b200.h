@@ -209,6 +209,10 @@ void gpuntt_b200_force_generic_path(int on);
  *                 = two per SM) run the whole transform inside one tile -- one launch, one HBM round trip, no hand-off between
  *                 CTAs, the shortest critical path -- larger ones the two-pass plan (twice the resident warps).  0: never. */
 #define GPUNTT_B200_TUNE_ONE_TILE_BATCH 6
+/*   SMALL_TILE_ELEMS  64-bit rings 2^12 .. 2^14: calls of at most this many elements in total (default 2^19) run the single-launch
+ *                 kernel on 1024-element tiles instead of 4096-element ones -- four times the CTAs, a quarter of the work on the
+ *                 critical path of a launch-bound call.  0: never. */
+#define GPUNTT_B200_TUNE_SMALL_TILE_ELEMS 7
 void gpuntt_b200_tune(int knob, int value);
 
 /* Batch-slice helpers for callers whose whole batch lives on ONE GPU: device g of ndev owns the

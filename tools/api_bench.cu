@@ -26,6 +26,26 @@ using namespace gpuntt;
 
 static const char* g_label = "?";
 
+// A/B runs: GPUNTT_TUNE="knob=value,knob=value" is applied through gpuntt_b200_tune when the library behind the API has it
+// (this repository's; the reference build leaves the weak symbol null)
+extern "C" void gpuntt_b200_tune(int knob, int value) __attribute__((weak));
+static void apply_tune_env()
+{
+    const char* e = getenv("GPUNTT_TUNE");
+    if (!e || !gpuntt_b200_tune) return;
+    std::string s(e);
+    size_t pos = 0;
+    while (pos < s.size())
+    {
+        size_t c = s.find(',', pos);
+        if (c == std::string::npos) c = s.size();
+        const std::string kv = s.substr(pos, c - pos);
+        const size_t eq = kv.find('=');
+        if (eq != std::string::npos) gpuntt_b200_tune(atoi(kv.substr(0, eq).c_str()), atoi(kv.substr(eq + 1).c_str()));
+        pos = c + 1;
+    }
+}
+
 #define CK(x)                                                                                                          \
     do                                                                                                                 \
     {                                                                                                                  \
@@ -266,6 +286,7 @@ int main(int argc, char** argv)
         return 1;
     }
     g_label = argv[1];
+    apply_tune_env();
     CudaDevice();
     CK(cudaSetDevice(0));
     std::vector<std::string> cases;
