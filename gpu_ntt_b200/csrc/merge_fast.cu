@@ -23,20 +23,26 @@ namespace gpuntt_b200
         return element_bits == 64 ? (n_power >= 7 && n_power <= 11) : (n_power >= 8 && n_power <= 12);
     }
     // Rings of exactly one tile (64-bit 2^12, 32-bit 2^13): the whole polynomial in ONE tile, three register rounds, one launch and
-    // one HBM round trip with nothing handed from CTA to CTA -- the shortest critical path this library has for these sizes
-    // (every twiddle pair of the transform sits in shared memory: 64 KiB beside the two 32 KiB tile buffers, so one CTA per
-    // SM).  Taken for batches of at most g_one_tile_batch polynomials (the launch-bound regime); above that the two-pass
-    // plan with twice the resident warps has the higher throughput.
+    // one HBM round trip with nothing handed from CTA to CTA (every twiddle pair of the transform sits in shared memory: 64 KiB
+    // beside the two 32 KiB tile buffers, so one CTA per SM with half the resident warps of the two-pass kernel).  Measured
+    // (profiles/r2_one_tile_ab.jsonl): inverse transforms gain at every device-bound batch (64-bit +4 %, 32-bit +22 % at
+    // 16384 polynomials), forward ones lose 10 %, and in the launch-bound regime the small-tile two-pass kernel is the
+    // quicker of the two.  Mode 1 (default): inverse transforms, 64-bit only above the small-tile range; 0: never; 2: always.
     static int one_tile_default()
     {
-        const char* e = getenv("GPUNTT_B200_ONE_TILE_BATCH"); // (A/B runs of binaries that cannot call gpuntt_b200_tune)
-        return e ? atoi(e) : 296;
+        const char* e = getenv("GPUNTT_B200_ONE_TILE"); // (A/B runs of binaries that cannot call gpuntt_b200_tune)
+        return e ? atoi(e) : 1;
     }
-    static std::atomic<int> g_one_tile_batch{one_tile_default()};
-    void fast_set_one_tile_batch(int v) { g_one_tile_batch.store(v < 0 ? 0 : v); }
-    static bool fast_one_tile(int n_power, int element_bits, int batch)
+    static std::atomic<int> g_one_tile_mode{one_tile_default()};
+    void fast_set_one_tile_mode(int v) { g_one_tile_mode.store(v); }
+    long long fused_small_tile_elems(); // merge_fused.cu
+    static bool fast_one_tile(int n_power, int element_bits, long long batch, bool inverse)
     {
-        return n_power == (element_bits == 64 ? 12 : 13) && batch <= g_one_tile_batch.load();
+        if (n_power != (element_bits == 64 ? 12 : 13)) return false;
+        const int mode = g_one_tile_mode.load();
+        if (mode == 2) return true;
+        if (mode != 1 || !inverse) return false;
+        return element_bits == 32 || (batch << n_power) > fused_small_tile_elems();
     }
 
     // text form of the tuned plan for gpuntt_b200_describe_plan; returns the number of launches (0: not covered)
@@ -144,7 +150,7 @@ namespace gpuntt_b200
     {
         *launched = 0;
         if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return cudaSuccess;
-        if (fast_small_supported(n_power, (int) sizeof(T) * 8) || fast_one_tile(n_power, (int) sizeof(T) * 8, batch))
+        if (fast_small_supported(n_power, (int) sizeof(T) * 8) || fast_one_tile(n_power, (int) sizeof(T) * 8, batch, inverse))
         {
             if (sizeof(T) == 4 && ((uint32_t) p >= (1u << 30) || (uint32_t) p < 3)) return cudaSuccess;
             if (sizeof(T) == 8 && ((uint64_t) p >= (1ull << 62) || (uint64_t) p < 3)) return cudaSuccess;

@@ -615,10 +615,11 @@ namespace gpuntt_b200
     // Launch-bound calls (64-bit): what such a call costs is the critical path through ONE tile of each pass -- tile load, two
     // register rounds of 32 butterflies per thread, store (profiles/r2_fused_timeline.txt: 5.2 of the 10.5 us of a 2^12 x 8 call
     // are the rounds of one 4096-element tile per CTA, bound by the SM's own multiplier pipes, while 130 SMs idle).  Calls of
-    // at most g_small_tile_elems elements therefore run on 1024-element tiles (K = 10): four times the CTAs, a quarter of the
+    // at most g_small_tile_elems (2^18) elements therefore run on 1024-element tiles (K = 10): four times the CTAs, a quarter of the
     // arithmetic on each tile's critical path.  Rings 2^12 .. 2^14 (a strided tile needs 2^(10 - d) >= 16 adjacent elements).
-    static std::atomic<long long> g_small_tile_elems{1LL << 19};
+    static std::atomic<long long> g_small_tile_elems{1LL << 18};
     void fused_set_small_tile_elems(long long v) { g_small_tile_elems.store(v < 0 ? 0 : v); }
+    long long fused_small_tile_elems() { return g_small_tile_elems.load(); }
     static bool small_tiles(long long polys, int n, int d) { return d >= 4 && d <= 6 && (polys << n) <= g_small_tile_elems.load(); }
 
     // Two-pass plans in one launch.  Returns cudaErrorNotSupported when the shape / modulus is not covered.

@@ -205,11 +205,11 @@ void gpuntt_b200_force_generic_path(int on);
 /*   4STEP_RESIDENT_PAIRS  1 (default): the transposing column pass walks the batch through one tile position at a time with
  *                 that position's (W, W') pairs resident in shared memory (merge_wcol.cu); 0: pairs fetched per tile. */
 #define GPUNTT_B200_TUNE_4STEP_RESIDENT_PAIRS 5
-/*   ONE_TILE_BATCH  64-bit N = 2^12 and 32-bit N = 2^13 are exactly one tile: calls of at most this many polynomials (default 296
- *                 = two per SM) run the whole transform inside one tile -- one launch, one HBM round trip, no hand-off between
- *                 CTAs, the shortest critical path -- larger ones the two-pass plan (twice the resident warps).  0: never. */
-#define GPUNTT_B200_TUNE_ONE_TILE_BATCH 6
-/*   SMALL_TILE_ELEMS  64-bit rings 2^12 .. 2^14: calls of at most this many elements in total (default 2^19) run the single-launch
+/*   ONE_TILE      64-bit N = 2^12 and 32-bit N = 2^13 are exactly one tile and can run with the whole transform inside it (one
+ *                 launch, one HBM round trip, no hand-off between CTAs; one CTA per SM).  1 (default): inverse transforms -- the
+ *                 measured win -- (64-bit: calls above the small-tile range below); 0: never; 2: every call of these sizes. */
+#define GPUNTT_B200_TUNE_ONE_TILE 6
+/*   SMALL_TILE_ELEMS  64-bit rings 2^12 .. 2^14: calls of at most this many elements in total (default 2^18) run the single-launch
  *                 kernel on 1024-element tiles instead of 4096-element ones -- four times the CTAs, a quarter of the work on the
  *                 critical path of a launch-bound call.  0: never. */
 #define GPUNTT_B200_TUNE_SMALL_TILE_ELEMS 7

@@ -137,9 +137,9 @@ def test_default_policy_launch_counts():
 
 
 @pytest.mark.parametrize("poly", [O.X_N_minus, O.X_N_plus])
-@pytest.mark.parametrize("logn,batches", [(12, [1, 3, 64, 128, 129]), (13, [1, 5, 64, 65]), (14, [2, 7, 32, 33])])
+@pytest.mark.parametrize("logn,batches", [(12, [1, 3, 64, 65]), (13, [1, 5, 32, 33]), (14, [2, 7, 16, 17])])
 def test_small_tile_variant_for_launch_bound_calls(logn, batches, poly):
-    """64-bit calls of at most 2^19 elements (knob SMALL_TILE_ELEMS) run the single-launch kernel on 1024-element tiles; one
+    """64-bit calls of at most 2^18 elements (knob SMALL_TILE_ELEMS) run the single-launch kernel on 1024-element tiles; one
     polynomial more and the call is back on 4096-element tiles.  Same words either way, forward and inverse, one launch."""
     bits = 64
     P = O.merge_params(logn, poly, bits)
@@ -149,7 +149,7 @@ def test_small_tile_variant_for_launch_bound_calls(logn, batches, poly):
         for batch in batches:
             x = O.example_input(P.modulus, batch << logn, seed=logn * 17 + batch)
             want = _threaded_oracle(O.merge_ntt, x, P)
-            for knob in (1 << 19, 0):
+            for knob in (1 << 18, 0):
                 capi.tune(7, knob)
                 d = to_dev(x, bits)
                 capi.ntt(d.view(batch, -1), tab, P.modulus, logn, poly)
@@ -162,5 +162,5 @@ def test_small_tile_variant_for_launch_bound_calls(logn, batches, poly):
                 torch.cuda.synchronize()
                 assert (to_host(out, bits) == x).all(), (batch, knob)
     finally:
-        capi.tune(6, 296)
-        capi.tune(7, 1 << 19)
+        capi.tune(6, 1)
+        capi.tune(7, 1 << 18)

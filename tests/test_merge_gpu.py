@@ -688,23 +688,26 @@ def test_small_rings_single_pass_tuned_kernels(bits, poly, logn):
 
 @pytest.mark.parametrize("bits", [64, 32])
 @pytest.mark.parametrize("poly", [O.X_N_minus, O.X_N_plus])
-def test_one_tile_rings_small_batches(bits, poly):
-    """64-bit N = 2^12 and 32-bit N = 2^13 are exactly one tile: calls of at most 296 polynomials (knob ONE_TILE_BATCH) run the
-    whole transform inside the tile (three register rounds, one launch, no hand-off between CTAs -- the launch-bound regime of
-    an RNS-FHE caller); knob 0 and larger batches take the two-pass plan.  Both paths against the oracle, every word."""
+def test_one_tile_rings(bits, poly):
+    """64-bit N = 2^12 and 32-bit N = 2^13 are exactly one tile: knob ONE_TILE = 2 runs every call of these sizes with the whole
+    transform inside the tile (three register rounds, one launch, no hand-off between CTAs), 1 (default) the inverse ones,
+    0 none.  All settings against the oracle, every word; ragged and larger-than-the-grid batches."""
     logn = 12 if bits == 64 else 13
     P = O.merge_params(logn, poly, bits)
     try:
-        for batch in (1, 3, 150, 296, 297):
+        for batch in (1, 3, 150, 297, 700):
             x = O.example_input(P.modulus, batch << logn, seed=logn + batch)
             want = O.merge_ntt(x, P)
-            for knob in (296, 0):
+            for knob in (2, 1, 0):
                 capi.tune(6, knob)
                 for inplace in (True, False):
                     got = run_fwd(x, P, bits, poly, inplace=inplace)
                     assert (got == want).all(), (batch, knob, inplace)
+                    if knob == 2:
+                        assert capi.lib().gpuntt_b200_last_launch_count() == 1
                     back = run_inv(want, P, bits, poly, inplace=inplace)
                     assert (back == x).all(), (batch, knob, inplace)
-                    assert capi.lib().gpuntt_b200_last_launch_count() in (1, 2)
+                    if knob == 2:
+                        assert capi.lib().gpuntt_b200_last_launch_count() == 1
     finally:
-        capi.tune(6, 296)
+        capi.tune(6, 1)

@@ -22,6 +22,7 @@ NAMES = ["entry", "init done", "loader: at tile 0", "loader: dependency met, TMA
          "CTA: all roles done", "exit"]
 mhz = 1965.0
 capi.tune(6, 0)  # (the one-tile path would bypass the kernel under study)
+capi.tune(7, int(os.environ.get('SMALL_TILE_ELEMS', 1 << 18)))
 for bits, logn, batch, poly in ((64, 12, 8, X_N_plus), (64, 13, 8, X_N_plus), (64, 14, 8, X_N_plus), (32, 14, 8, X_N_minus), (64, 16, 8, X_N_plus)):
     P = NTTParameters(logn, poly, bits)
     tab = dev(P.gpu_root_of_unity_table_generator(P.forward_root_of_unity_table), bits)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """One-tile rings (64-bit 2^12, 32-bit 2^13): whole-polynomial-in-a-tile kernel against the two-pass plan over batch sizes
-(knob GPUNTT_B200_TUNE_ONE_TILE_BATCH); one JSON line per (width, batch, op)."""
+(knob GPUNTT_B200_TUNE_ONE_TILE); one JSON line per (width, batch, op)."""
 import json
 import os
 import sys
@@ -23,9 +23,9 @@ for bits, logn in ((64, 12), (32, 13)):
         for op in ("fwd", "inv"):
             fn = (lambda: capi.ntt(x, tab, P.modulus, logn, X_N_minus)) if op == "fwd" else (lambda: capi.intt(x, itab, P.modulus, P.n_inv, logn, X_N_minus))
             res = {}
-            for name, knob in (("two_pass", 0), ("one_tile", 1 << 30)):
+            for name, knob in (("two_pass", 0), ("one_tile", 2)):
                 capi.tune(6, knob)
                 res[name] = round(time_ms(fn, 30) * 1e3, 2)
-            capi.tune(6, 296)
+            capi.tune(6, 1)
             print(json.dumps({"bits": bits, "logn": logn, "batch": batch, "op": op, "us_two_pass_plan": res["two_pass"], "us_one_tile": res["one_tile"],
                               "ratio": round(res["two_pass"] / res["one_tile"], 3)}), flush=True)

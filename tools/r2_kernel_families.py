@@ -80,7 +80,13 @@ print("11 RNS forward 4 x 59-bit, 2^16 x 1024 (fast_pass_dual_kernel)"); rns(16,
 print("12 RNS forward 4 x 59-bit, 2^14 x 32 (fused2_rns_kernel)"); rns(14, 32, 4, 2)
 print("13 generic path 64-bit 2^16 x 256 (twiddle_prep_kernel + merge_pass_kernel x 2)"); merge(16, 256, 64, generic=1)
 print("14 generic path 32-bit 2^14 x 1024"); merge(14, 1024, 32, generic=1)
-print("15 C4 fused contract forward (w_pairs_kernel, wcol_kernel, two strided row passes)"); fourstep(24, 16, capi.FOURSTEP_FUSED)
+print("15 C4 fused contract forward (w_pairs_kernel, wcol_kernel strided + transposing store, two strided row passes)"); fourstep(24, 16, capi.FOURSTEP_FUSED)
 print("16 C4 fused forward with per-tile pairs (fast_pass_kernel WMUL + TS)"); fourstep(24, 16, capi.FOURSTEP_FUSED, resident=0)
-print("17 C4 reference contract forward (transpose_kernel first)"); fourstep(24, 16, capi.FOURSTEP_REFERENCE)
-print("18 C4 fused inverse (transpose, pairs, contiguous n1 pass, two strided passes)"); fourstep(24, 16, capi.FOURSTEP_FUSED, inverse=True)
+print("17 C4 reference contract forward (w_pairs_tile_kernel, wcol_kernel contiguous, strided row pass, strided row pass + transposing store)"); fourstep(24, 16, capi.FOURSTEP_REFERENCE)
+print("18 C4 fused inverse (pairs, strided n1 pass + transposing store, wcol_kernel inverse product pass, last strided pass)"); fourstep(24, 16, capi.FOURSTEP_FUSED, inverse=True)
+print("19 C4 reference contract inverse (pairs, contiguous n1 pass, wcol_kernel inverse product pass + transposing store, last pass along the rows)"); fourstep(24, 16, capi.FOURSTEP_REFERENCE, inverse=True)
+capi.tune(3, 0)
+print("20 C4 reference contract forward with knob 4STEP_TRANSPOSED = 0 (transpose_kernel, column pass, row passes)"); fourstep(24, 16, capi.FOURSTEP_REFERENCE)
+capi.tune(3, 1)
+print("21 one-tile ring, 32-bit 2^13 x 16384 inverse (whole transform in a tile)"); merge(13, 16384, 32, inverse=True)
+print("22 small-tile single-launch kernel, 64-bit 2^13 x 8 forward (1024-element tiles)"); merge(13, 8, 64)
