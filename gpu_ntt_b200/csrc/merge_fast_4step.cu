@@ -465,4 +465,99 @@ namespace gpuntt_b200
         return cudaSuccess;
     }
 
+    // NTTLayout::PerCoefficient on the tuned kernels (replaces ForwardCoreTranspose / InverseCoreTranspose, ntt.cu:1554-2074 of the
+    // reference; like it: power-of-two batch, n_power <= 9).  The buffer is one [2^n_power][2^col_log] row-major matrix whose
+    // COLUMNS are the transforms, i.e. strided passes over the top n_power index bits of one array of 2^(n_power + col_log)
+    // elements -- the same kernels as the 4-step column phase, without a transposition anywhere.  One pass up to 2^8, two for 2^9
+    // (5 + 4 stages); the pass that ends a forward transform canonicalises (SFIN), the one that ends an inverse applies n^-1.
+    // 64-bit, single modulus, F60 moduli forward / lazy-policy moduli inverse, 2^(12 - stages) <= batch; *launched = 0 otherwise.
+    cudaError_t fast_per_coefficient(const uint64_t* in, uint64_t* out, const uint64_t* table, uint64_t p, uint64_t ninv, int n_power,
+                                     int col_log, int plus, bool inverse, int signed_io, cudaStream_t st, int* launched,
+                                     void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t))
+    {
+        using T = uint64_t;
+        *launched = 0;
+        if (n_power < 4 || n_power > 9 || col_log < 1) return cudaSuccess;
+        const int n = n_power + col_log;
+        if (n > 40 || (1LL << n_power) >= (1LL << 31)) return cudaSuccess;
+        if (inverse ? !(p < kFastModulusLimit && p >= 5) : !(p >= kF60ModulusMin && p < kF60ModulusLimit)) return cudaSuccess;
+        if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return cudaSuccess;
+        // stages of the pass on the high bits / on the low bits (forward order)
+        const int da = n_power <= 8 ? n_power : 5, db = n_power - da;
+        if (12 - da > col_log + db || (db > 0 && 12 - db > col_log)) return cudaSuccess; // a tile is 2^(12 - stages) adjacent columns wide
+        FastArgs<T> a{};
+        a.table = table;
+        a.p = p;
+        a.ninv_w = ninv;
+        a.ninv_wq = inverse ? shoup_companion(ninv, p) : 0;
+        a.pbits = 64 - __builtin_clzll((unsigned long long) p);
+        {
+            const unsigned __int128 m = (((unsigned __int128) 1) << (63 + a.pbits)) / (unsigned __int128) p;
+            a.mu = (m >> 64) ? ~0ull : (uint64_t) m;
+        }
+        a.n = n;
+        a.plus = plus;
+        a.batch = 1;
+        a.in_bound = 1;
+        a.signed_io = signed_io;
+        auto pass = [&](int d, int lo, bool first, bool last, const T* src) -> cudaError_t
+        {
+            FastArgs<T> s = a;
+            s.in = src;
+            s.out = out;
+            s.lo = lo;
+            s.first = first ? 1 : 0;
+            s.last = last ? 1 : 0;
+            s.work = (1LL << (lo - (12 - d))) << (n - lo - d);
+            s.rr = (n == lo + d && lo > 10) ? 1 : 0;
+            if (inverse) return launch_strided<T, true, 1>(d, s, st);
+            if (last)
+                switch (d)
+                {
+                    case 4: return launch_rows_t<4, true>(s, st);
+                    case 5: return launch_rows_t<5, true>(s, st);
+                    case 6: return launch_rows_t<6, true>(s, st);
+                    case 7: return launch_rows_t<7, true>(s, st);
+                    default: return launch_rows_t<8, true>(s, st);
+                }
+            return launch_strided<T, false, 2>(d, s, st);
+        };
+        cudaError_t e;
+        int k = 0;
+        if (db == 0)
+        {
+            prof_begin(++k, st);
+            e = pass(da, col_log, true, true, in);
+            prof_end(st);
+        }
+        else if (!inverse)
+        {
+            prof_begin(++k, st);
+            e = pass(da, col_log + db, true, false, in);
+            prof_end(st);
+            if (e == cudaSuccess)
+            {
+                prof_begin(++k, st);
+                e = pass(db, col_log, false, true, out);
+                prof_end(st);
+            }
+        }
+        else
+        {
+            prof_begin(++k, st);
+            e = pass(db, col_log, true, false, in);
+            prof_end(st);
+            if (e == cudaSuccess)
+            {
+                prof_begin(++k, st);
+                e = pass(da, col_log + db, false, true, out);
+                prof_end(st);
+            }
+        }
+        if (e == cudaErrorNotSupported && k == 1) return cudaSuccess; // no tensor maps: generic path
+        if (e != cudaSuccess) return e;
+        *launched = k;
+        return cudaSuccess;
+    }
+
 } // namespace gpuntt_b200

@@ -639,6 +639,9 @@ namespace gpuntt_b200
     cudaError_t fast_merge(const T* in, T* out, const T* table, T p, T ninv, int n_power, int plus, bool inverse,
                            int batch, cudaStream_t st, int* launched, void (*prof_begin)(int, cudaStream_t),
                            void (*prof_end)(cudaStream_t), int in_bound = 1, unsigned* counters = nullptr, int signed_io = 0);
+    cudaError_t fast_per_coefficient(const uint64_t* in, uint64_t* out, const uint64_t* table, uint64_t p, uint64_t ninv, int n_power,
+                                     int col_log, int plus, bool inverse, int signed_io, cudaStream_t st, int* launched,
+                                     void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t));
     void fused_set_lag_steps(int v); // merge_fused.cu
     void fused_set_policy(int v);
     void fused_set_small_tile_elems(long long v);
@@ -931,6 +934,19 @@ namespace gpuntt_b200
         int col_log = 0;
         if (d->ntt_layout == GPUNTT_B200_PER_COEFFICIENT)
             while ((1 << col_log) < d->batch_size) col_log++;
+        if constexpr (sizeof(T) == 8)
+        {
+            if (col_log > 0 && !rns && !g_force_generic.load())
+            {
+                int launched = 0;
+                cudaError_t fe = fast_per_coefficient(reinterpret_cast<const uint64_t*>(d->in), reinterpret_cast<uint64_t*>(d->out),
+                                                      reinterpret_cast<const uint64_t*>(d->root_of_unity_table), (uint64_t) d->modulus_value,
+                                                      (uint64_t) d->mod_inverse_value, n, col_log, plus ? 1 : 0, inv, d->is_signed ? 1 : 0, st,
+                                                      &launched, prof_begin, prof_end);
+                if (fe != cudaSuccess) return cuda_fail(fe, "fast_pass_kernel (PerCoefficient) launch");
+                if (launched > 0) return GPUNTT_B200_OK;
+            }
+        }
         CoreCall<T> cc;
         cc.in = d->in;
         cc.out = reinterpret_cast<T*>(d->out);

@@ -586,6 +586,42 @@ def test_per_coefficient_layout(bits, poly, logh, w):
     assert (to_host(out, bits).reshape(h, w) == x).all()
 
 
+@pytest.mark.parametrize("poly", [O.X_N_plus, O.X_N_minus])
+@pytest.mark.parametrize("logh,w,launches", [(4, 256, 1), (5, 128, 1), (6, 64, 1), (7, 4096, 1), (8, 16, 1), (8, 2048, 1), (9, 256, 2), (9, 4096, 2)])
+def test_per_coefficient_on_tuned_kernels(poly, logh, w, launches):
+    """64-bit PerCoefficient calls whose batch is at least one tile wide run as strided passes of the tuned kernels (one pass up
+    to H = 256, two for H = 512): launch count asserted, every word against the oracle, in place and out of place, and the
+    generic kernel gives the same words."""
+    bits = 64
+    h = 1 << logh
+    P = O.merge_params(logh, poly, bits)
+    x = O.example_input(P.modulus, h * w, seed=logh * 3 + w).reshape(h, w)
+    want = O.merge_ntt(np.ascontiguousarray(x.T), P).reshape(w, h).T
+    s = torch.cuda.current_stream().cuda_stream
+    tab, itab = to_dev(P.fwd_br, bits), to_dev(P.inv_br, bits)
+    for generic in (0, 1):
+        capi.lib().gpuntt_b200_force_generic_path(generic)
+        try:
+            d = to_dev(x, bits)
+            out = torch.zeros_like(d)
+            capi.merge_ntt(in_ptr=d.data_ptr(), out_ptr=out.data_ptr(), table_ptr=tab.data_ptr(), n_power=logh, batch=w, element_bits=bits,
+                           direction=capi.FORWARD, reduction_poly=poly, layout=capi.PerCoefficient, modulus=P.modulus, stream=s)
+            if not generic:
+                assert capi.lib().gpuntt_b200_last_launch_count() == launches
+            torch.cuda.synchronize()
+            assert (to_host(out, bits).reshape(h, w) == want).all(), generic
+            assert (to_host(d, bits).reshape(h, w) == x).all(), "out-of-place call modified its input"
+            capi.merge_ntt(in_ptr=out.data_ptr(), out_ptr=out.data_ptr(), table_ptr=itab.data_ptr(), n_power=logh, batch=w, element_bits=bits,
+                           direction=capi.INVERSE, reduction_poly=poly, layout=capi.PerCoefficient, modulus=P.modulus, mod_inverse=P.n_inv,
+                           stream=s)
+            if not generic:
+                assert capi.lib().gpuntt_b200_last_launch_count() == launches
+            torch.cuda.synchronize()
+            assert (to_host(out, bits).reshape(h, w) == x).all(), generic
+        finally:
+            capi.lib().gpuntt_b200_force_generic_path(0)
+
+
 def test_per_coefficient_rns_and_limits():
     """RNS PerCoefficient: column j uses modulus[j % mod_count] (ntt.cu:1737-1741); n_power > 9 is rejected like the
     reference (ntt.cu:2230-2233)."""
