@@ -118,8 +118,10 @@ int gpuntt_b200_merge_ntt(const gpuntt_b200_merge_desc* desc);
  *        in == out allowed.
  * RNS form (mod_count >= 1): polynomial b uses modulus_dev[b % mod_count]; like the reference's kernels all
  * moduli index the SAME tables (ntt_4step.cu:150-229), which is only meaningful for mod_count == 1 or moduli
- * sharing their roots.  The fused contract and every inverse use an engine-owned scratch buffer of
- * batch_size * N elements (cached per device and stream, see gpuntt_b200_release_workspaces). */
+ * sharing their roots.  Every call on the tuned kernels (64-bit, one modulus) is a (W, W') pair table + three data passes and no
+ * transpose kernel: where a contract asks for a transposed layout a pass STORES transposed.  They use an engine-owned scratch
+ * buffer of batch_size * N elements and a pair table of 16 * N bytes (cached per device and stream, see
+ * gpuntt_b200_release_workspaces); a reference-contract forward call of fewer than four polynomials needs neither. */
 enum { GPUNTT_B200_4STEP_REFERENCE = 0, GPUNTT_B200_4STEP_FUSED = 1 };
 typedef struct gpuntt_b200_4step_desc
 {

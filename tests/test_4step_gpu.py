@@ -320,3 +320,113 @@ def test_4step_inverse_without_transpose_kernel(logn, batch):
                 assert 9 not in kinds, kinds
     finally:
         capi.tune(3, 1)
+
+
+def test_4step_errors():
+    t = torch.zeros(1 << 12, dtype=torch.int64, device="cuda")
+    with pytest.raises(capi.GpuNttError) as ei:
+        capi.fourstep_ntt(t.view(1, -1), t, t, t, 17, 11)
+    assert ei.value.status == capi.ERR_N_POWER
+    with pytest.raises(capi.GpuNttError):
+        capi.fourstep_ntt(t.view(1, -1), t, t, t, 576460752303415297, 12, io_contract=capi.FOURSTEP_REFERENCE)  # in == out
+
+
+def test_4step_rns_overload_one_modulus_takes_the_tuned_kernels_and_can_be_captured():
+    """With exactly one device modulus the RNS overload reads that Modulus back (32 bytes) and continues as the
+    single-modulus form -- same launches, same kernels; under stream capture no read-back is possible and the
+    device-modulus kernels run instead.  Both must equal the oracle."""
+    bits, logn, batch = 64, 16, 2
+    P = O.fourstep_params(logn, O.X_N_minus, bits)
+    x = O.example_input(P.modulus, batch * P.n, seed=11).reshape(batch, P.n)
+    want = O.fourstep_ntt(x, P)
+    t1, t2, W = tables(P, bits, False)
+    bit, mu = O.modulus(P.modulus, bits)
+    mods = to_dev(np.array([P.modulus, bit, mu], dtype=np.uint64), bits)
+    d = to_dev(x, bits).view(batch, P.n)
+    out = torch.empty_like(d)
+    capi.fourstep_ntt(d, t1, t2, W, P.modulus, logn, out=out)
+    torch.cuda.synchronize()
+    single_launches = capi.lib().gpuntt_b200_last_launch_count()
+    assert (to_host(out, bits).reshape(batch, -1) == want).all()
+    out.zero_()
+    capi.fourstep_ntt(d, t1, t2, W, 0, logn, out=out, mod_count=1, modulus_dev=mods.data_ptr())
+    torch.cuda.synchronize()
+    assert capi.lib().gpuntt_b200_last_launch_count() == single_launches
+    assert (to_host(out, bits).reshape(batch, -1) == want).all()
+    # capture on an explicit stream whose cached scratch (generic-kernel twiddle companions, 4-step workspace) exists
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    capi.lib().gpuntt_b200_force_generic_path(1)
+    try:
+        with torch.cuda.stream(side):
+            capi.fourstep_ntt(d, t1, t2, W, 0, logn, out=out, mod_count=1, modulus_dev=mods.data_ptr())
+    finally:
+        capi.lib().gpuntt_b200_force_generic_path(0)
+    side.synchronize()
+    assert (to_host(out, bits).reshape(batch, -1) == want).all()
+    g = torch.cuda.CUDAGraph()
+    out.zero_()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g, stream=side):
+        capi.fourstep_ntt(d, t1, t2, W, 0, logn, out=out, mod_count=1, modulus_dev=mods.data_ptr())
+    g.replay()
+    torch.cuda.synchronize()
+    assert (to_host(out, bits).reshape(batch, -1) == want).all()
+
+
+def custom_fourstep_params(logn, p):
+    """FourStepParams for an arbitrary prime p = 1 (mod 2^logn) (what NTTParameters4Step builds from a factor set)."""
+    import copy
+    P = copy.copy(O.fourstep_params(logn, O.X_N_minus, 64, inverse_tables=False))
+    n = 1 << logn
+    assert (p - 1) % n == 0
+    omega = 0
+    for g in range(2, 1000):
+        c = pow(g, (p - 1) // n, p)
+        if pow(c, n // 2, p) == p - 1:      # order exactly N
+            omega = c
+            break
+    assert omega
+    P.modulus, P.omega, P.root, P.inv_root, P.n_inv = p, omega, omega, pow(omega, p - 2, p), pow(n, p - 2, p)
+    P.t1 = np.empty(P.n1 // 2, dtype=np.uint64)
+    P.t2 = np.empty(P.n2 // 2, dtype=np.uint64)
+    O.lib().ora_4step_small_tables(P.root, p, P.n, P.n1, P.n2, 0, P.t1, P.t2)
+    P.W = np.empty(P.n, dtype=np.uint64)
+    O.lib().ora_4step_w_table(P.root, p, P.n1, P.n2, 0, P.W)
+    P.t1_inv = np.empty(P.n1 // 2, dtype=np.uint64)
+    P.t2_inv = np.empty(P.n2 // 2, dtype=np.uint64)
+    O.lib().ora_4step_small_tables(P.root, p, P.n, P.n1, P.n2, 1, P.t1_inv, P.t2_inv)
+    P.W_inv = np.empty(P.n, dtype=np.uint64)
+    O.lib().ora_4step_w_table(P.inv_root, p, P.n1, P.n2, 1, P.W_inv)
+    return P
+
+
+@pytest.mark.parametrize("logn", [16, 17, 18, 19])
+def test_4step_moduli_at_the_top_of_the_lazy_range(logn):
+    """Primes just below 2^60 - 2^31 (the top of the F60 policy): 20p exceeds 2^64 there, so any stage that lets a value
+    pass 16p wraps.  logn 18 is the shape whose row phase opens with a three-stage first round on inputs below 2p
+    (Shape<3,2>, in_bound 2) -- the case the round-1 advisor found; extreme inputs (all p-1) maximise the lazy values."""
+    from tests.test_moduli_gpu import ntt_prime_below
+    p = ntt_prime_below((1 << 60) - (1 << 31), 1 << logn)
+    P = custom_fourstep_params(logn, p)
+    batch = 4       # (four: the reference-contract call below takes the position-major kernels)
+    rng = np.random.default_rng(logn)
+    x = rng.integers(0, p, size=(batch, P.n), dtype=np.uint64)
+    x[1, :] = p - 1
+    x[2, ::2] = p - 1
+    x[2, 1::2] = 0
+    want = O.fourstep_ntt(x, P)
+    t1, t2, W = tables(P, 64, False)
+    d = to_dev(x, 64)
+    capi.fourstep_ntt(d.view(batch, P.n), t1, t2, W, p, logn)
+    torch.cuda.synchronize()
+    assert (to_host(d, 64).reshape(batch, -1) == want).all()
+    xt = to_dev(transposed(x, P.n1, P.n2), 64)
+    r = torch.zeros_like(xt)
+    capi.fourstep_ntt(xt.view(batch, P.n), t1, t2, W, p, logn, io_contract=capi.FOURSTEP_REFERENCE, out=r.view(batch, P.n))
+    torch.cuda.synchronize()
+    assert (transposed(to_host(r, 64), P.n1, P.n2).reshape(batch, -1) == want).all()
+    it1, it2, iW = tables(P, 64, True)
+    capi.fourstep_ntt(d.view(batch, P.n), it1, it2, iW, p, logn, direction=capi.INVERSE, mod_inverse=P.n_inv)
+    torch.cuda.synchronize()
+    assert (to_host(d, 64).reshape(batch, -1) == x).all()
