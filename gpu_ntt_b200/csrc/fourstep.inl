@@ -101,6 +101,7 @@ template <typename T> static int fourstep_execute_t(const gpuntt_b200_4step_desc
     const T* in = reinterpret_cast<const T*>(d->in);
     T* out = reinterpret_cast<T*>(d->out);
     if ((long long) batch * n2 > 0x7fffffffLL) return fail(GPUNTT_B200_ERR_ARGUMENT, "batch_size * n2 exceeds 2^31 - 1 rows");
+    StreamEnqueueLock enqueue_lock(d->stream); // the passes of a call share the scratch buffer and the pair table
 
     // scratch for the contracts that cannot run in `out` alone
     T* ws = nullptr;

@@ -35,8 +35,45 @@ namespace gpuntt_b200
         }
     }
 
-    // GPU_NTT / GPU_INTT RNS overloads (ntt.cu:2560-3058) for the two-pass ring sizes (64-bit 2^12..2^16, 32-bit
-    // 2^14..2^18), batch a multiple of mod_count.  The moduli are device data, so for 64-bit every pass is ONE launch of
+    bool fast_small_supported(int n_power, int element_bits); // merge_fast.cu
+
+    // Small rings (64-bit 2^7..2^11, 32-bit 2^8..2^12) in the RNS form: ONE contiguous pass whose tiles hold 2^(K - n) whole
+    // polynomials of ONE modulus slot (4-D tensor map {row, rows, slot, polynomial within the slot}: the polynomials of a slot are
+    // mod_count apart in the caller's array, ntt.cu:613-619 of the reference), two or three register rounds, a segment per slot.
+    template <typename T, bool INV> static cudaError_t launch_small_rns(int n_power, const FastArgs<T>& s, cudaStream_t st)
+    {
+        if constexpr (sizeof(T) == 8)
+        {
+            constexpr int PL = INV ? 1 : 2; // lazy inverse / F60 forward; the exact twin is picked on the device
+#define GPUNTT_SMALL_RNS64(R1, R2, NP, NT, R3)                                                                                                    \
+    launch_fast<Shape<T, INV, PL, false, R1, R2, 12, NP, NT, R3>, false, true, Shape<T, INV, 0, false, R1, R2, 12, NP, NT, R3>>(s, st)
+            switch (n_power)
+            {
+                case 7: return GPUNTT_SMALL_RNS64(3, 4, 5, 7, 0);
+                case 8: return GPUNTT_SMALL_RNS64(4, 4, 4, 8, 0);
+                case 9: return GPUNTT_SMALL_RNS64(2, 3, 3, 9, 4);
+                case 10: return GPUNTT_SMALL_RNS64(3, 3, 2, 10, 4);
+                case 11: return GPUNTT_SMALL_RNS64(3, 4, 1, 11, 4);
+                default: return cudaErrorNotSupported;
+            }
+#undef GPUNTT_SMALL_RNS64
+        }
+        else
+        {
+            switch (n_power)
+            {
+                case 8: return launch_fast<Shape<T, INV, 0, false, 3, 5, 13, 5, 8>, false, true>(s, st);
+                case 9: return launch_fast<Shape<T, INV, 0, false, 4, 5, 13, 4, 9>, false, true>(s, st);
+                case 10: return launch_fast<Shape<T, INV, 0, false, 5, 5, 13, 3, 10>, false, true>(s, st);
+                case 11: return launch_fast<Shape<T, INV, 0, false, 3, 3, 13, 2, 11, 5>, false, true>(s, st);
+                case 12: return launch_fast<Shape<T, INV, 0, false, 3, 4, 13, 1, 12, 5>, false, true>(s, st);
+                default: return cudaErrorNotSupported;
+            }
+        }
+    }
+
+    // GPU_NTT / GPU_INTT RNS overloads (ntt.cu:2560-3058) for the small rings (one pass, above) and the two- and three-pass ring
+    // sizes, batch a multiple of mod_count.  The moduli are device data, so for 64-bit every pass is ONE launch of
     // fast_pass_dual_kernel, which holds the lazy-policy and the exact-policy body and picks from the modulus array.
     // flag_ws: unused (kept for the call signature).  *launched = 0 when not covered.
     template <typename T>
@@ -48,6 +85,37 @@ namespace gpuntt_b200
         *launched = 0;
         constexpr int bits = (int) sizeof(T) * 8;
         constexpr int K = bits == 64 ? 12 : 13;
+        if (fast_small_supported(n_power, bits) && mod_count >= 1 && batch % mod_count == 0 &&
+            ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0)
+        {
+            FastArgs<T> s{};
+            s.in = in;
+            s.out = out;
+            s.table = table;
+            s.p = (T) ((1ull << (bits - 5)) + 1); // placeholder until the first segment reads its modulus
+            s.n = n_power;
+            s.lo = 0;
+            s.plus = plus;
+            s.first = 1;
+            s.last = 1;
+            s.in_bound = 1;
+            s.batch = batch / mod_count;
+            s.mod_count = mod_count;
+            s.mod_dev = mod_dev;
+            s.ninv_dev = ninv_dev;
+            s.mod_order = mod_order;
+            s.poly_order = poly_order;
+            s.policy_flag = nullptr;
+            const int nplog = K - n_power;
+            s.work = (long long) mod_count * (((long long) s.batch + (1 << nplog) - 1) >> nplog);
+            prof_begin(1, st);
+            const cudaError_t e = inverse ? launch_small_rns<T, true>(n_power, s, st) : launch_small_rns<T, false>(n_power, s, st);
+            prof_end(st);
+            if (e == cudaErrorNotSupported) return cudaSuccess; // generic path
+            if (e != cudaSuccess) return e;
+            *launched = 1;
+            return cudaSuccess;
+        }
         if (!fast_supported(n_power, bits) || mod_count < 1 || batch % mod_count != 0) return cudaSuccess;
         if (((long long) batch << (n_power - (bits == 64 ? 8 : 10))) >= (1LL << 31)) return cudaSuccess;
         const FastPlan pl = make_fast_plan(n_power, bits);

@@ -20,6 +20,7 @@
 #include <mutex>
 #include <random>
 #include <map>
+#include <memory>
 #include <string>
 #include <thread>
 #include <tuple>
@@ -677,6 +678,35 @@ namespace gpuntt_b200
         return WsKey(dev, stream, slot, th);
     }
 
+    // A scratch buffer is written by one kernel of a call and read by later ones (twiddle companions by the generic passes,
+    // the 4-step scratch and pair table by its passes).  The stream orders kernels in ENQUEUE order, so two host threads that
+    // issue calls on the same stream handle (the legacy default stream, say) must not interleave their enqueues: every call
+    // that uses such scratch holds this per-(device, stream) lock while it enqueues (microseconds; calls never wait for the
+    // device under it unless a buffer has to grow).  Recursive: the 4-step call re-enters the merge call for its row phase.
+    static std::map<WsKey, std::unique_ptr<std::recursive_mutex>> g_stream_locks; // under g_ws_mutex
+    struct StreamEnqueueLock
+    {
+        std::recursive_mutex* m = nullptr;
+        explicit StreamEnqueueLock(void* stream)
+        {
+            int dev = 0;
+            if (cudaGetDevice(&dev) != cudaSuccess) return;
+            {
+                std::lock_guard<std::mutex> lk(g_ws_mutex);
+                auto& slot = g_stream_locks[ws_key(dev, stream, -1)];
+                if (!slot) slot.reset(new std::recursive_mutex);
+                m = slot.get();
+            }
+            m->lock();
+        }
+        ~StreamEnqueueLock()
+        {
+            if (m) m->unlock();
+        }
+        StreamEnqueueLock(const StreamEnqueueLock&) = delete;
+        StreamEnqueueLock& operator=(const StreamEnqueueLock&) = delete;
+    };
+
     // slot 0: twiddle companions; slots 1,2: host-convenience staging buffers
     static cudaError_t get_workspace(void* stream, int slot, size_t bytes, void** out)
     {
@@ -814,6 +844,7 @@ namespace gpuntt_b200
 
     template <typename T> static int run_core(const CoreCall<T>& cc)
     {
+        StreamEnqueueLock enqueue_lock((void*) cc.st); // twiddle_prep_kernel -> passes share the companion buffer
         const bool rns = cc.mod_count > 0;
         const int slices = rns ? cc.mod_count : 1;
         const int tw_stride_log = cc.shared_tables ? 0 : cc.stride_log;

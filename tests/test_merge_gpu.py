@@ -257,6 +257,26 @@ def test_rns_form_tuned_kernels(bits, logn, batch, mod_count, tops, fused):
     assert capi.lib().gpuntt_b200_last_launch_count() == ((1 if fused else 2) if logn <= (16 if bits == 64 else 18) else 3)
 
 
+@pytest.mark.parametrize("bits,logn,batch,mod_count,tops", [
+    (64, 7, 6, 3, (59, 59, 59)),         # 32 polynomials of a slot per tile, two of them present
+    (64, 8, 200, 4, (59, 58, 50, 45)),   # several tiles per slot, ragged last one
+    (64, 9, 10, 2, (59, 61)),            # one modulus outside the lazy range: the exact body
+    (64, 10, 9, 3, (61, 61, 61)),
+    (64, 11, 12, 4, (59, 59, 59, 59)),
+    (64, 11, 2, 2, (59, 60)),            # one polynomial per slot: half-empty tiles
+    (32, 8, 96, 3, (29, 29, 29)),
+    (32, 10, 14, 2, (29, 25)),
+    (32, 12, 6, 3, (29, 28, 27)),
+])
+def test_rns_small_rings_tuned_kernels(bits, logn, batch, mod_count, tops):
+    """RNS overloads on rings of 2^7..2^11 (64-bit) / 2^8..2^12 (32-bit): ONE launch whose tiles hold whole polynomials of one
+    modulus slot (4-D tensor map {row, rows, slot, polynomial within the slot}); forward and inverse against the oracle."""
+    primes = [rns_primes(bits, logn, 1 + i, t)[i] for i, t in enumerate(tops)]
+    assert len({p for p, _ in primes}) == mod_count
+    _rns_roundtrip(bits, logn, batch, mod_count, primes)
+    assert capi.lib().gpuntt_b200_last_launch_count() == 1
+
+
 def _rns_roundtrip(bits, logn, batch, mod_count, primes):
     n = 1 << logn
     fwd_tab = np.zeros(mod_count << logn, dtype=np.uint64)
