@@ -717,6 +717,11 @@ namespace gpuntt_b200
         Workspace& w = g_ws[ws_key(dev, stream, slot)];
         if (w.bytes < bytes)
         {
+            // growing means cudaMalloc (and a stream synchronisation): neither is legal while the stream is being captured, and
+            // attempting them would invalidate the capture -- decline cleanly (run the call once outside the capture first)
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            if (cudaStreamIsCapturing((cudaStream_t) stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone)
+                return cudaErrorStreamCaptureUnsupported;
             if (w.ptr)
             {
                 // in-flight kernels of earlier calls may still read the old buffer
