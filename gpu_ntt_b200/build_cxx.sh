@@ -9,7 +9,10 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -I$ROOT/include -I$HERE/csrc"
 OBJ="$HERE/lib/obj"
 mkdir -p "$OBJ"
-for f in csrc/merge_ntt csrc/merge_fast csrc/merge_fast_rns csrc/merge_fast_4step csrc/merge_fused csrc/merge_wcol cxx/common cxx/nttparameters cxx/ntt_cpu cxx/ntt_api cxx/ntt_4step_api; do
+# the kernels and the C ABI (csrc/*.cu) are the objects build.sh compiles for the shared library (same flags, -fPIC): reuse them
+bash "$HERE/build.sh" > /dev/null
+rm -f "$OBJ"/merge_*.o
+for f in cxx/common cxx/nttparameters cxx/ntt_cpu cxx/ntt_api cxx/ntt_4step_api; do
     o="$OBJ/$(basename $f).o"
     if [ ! -f "$o" ] || [ "$HERE/$f.cu" -nt "$o" ] || [ -n "$(find "$HERE/csrc" "$ROOT/include" -newer "$o" -name '*.*h' -o -newer "$o" -name '*.inl' | head -1)" ]; then
         $NVCC $FLAGS -c -o "$o" "$HERE/$f.cu" &
@@ -17,7 +20,7 @@ for f in csrc/merge_ntt csrc/merge_fast csrc/merge_fast_rns csrc/merge_fast_4ste
 done
 wait
 rm -f "$HERE/lib/libntt-1.0.a"
-ar rcs "$HERE/lib/libntt-1.0.a" "$OBJ"/*.o
+ar rcs "$HERE/lib/libntt-1.0.a" "$HERE/lib/obj_so"/merge_*.o "$OBJ"/*.o
 echo "built $HERE/lib/libntt-1.0.a"
 for ex in gpu_merge_examples gpu_4step_examples; do
     if [ -f "$ROOT/examples/$ex.cu" ]; then

@@ -767,3 +767,38 @@ def test_one_tile_rings(bits, poly):
                         assert capi.lib().gpuntt_b200_last_launch_count() == 1
     finally:
         capi.tune(6, 1)
+
+
+def test_two_host_threads_on_one_stream_do_not_share_scratch_mid_call():
+    """scratch (the generic kernel's twiddle companions) is cached per (device, stream); two host threads that issue
+    calls on the SAME stream handle must not interleave twiddle_prep_kernel and pass launches.  Every call holds the
+    per-stream enqueue lock: both threads' results stay exact (ctypes releases the GIL, so the calls really overlap)."""
+    import threading
+    bits, logn, batch, rounds = 64, 13, 3, 40
+    Ps = [O.merge_params(logn, O.X_N_minus, bits), O.merge_params(logn, O.X_N_plus, bits)]
+    xs = [O.example_input(P.modulus, batch << logn, seed=50 + i) for i, P in enumerate(Ps)]
+    wants = [O.merge_ntt(x, P) for x, P in zip(xs, Ps)]
+    tabs = [to_dev(P.fwd_br, bits) for P in Ps]
+    polys = [O.X_N_minus, O.X_N_plus]
+    stream = torch.cuda.current_stream().cuda_stream
+    bad = []
+    capi.lib().gpuntt_b200_force_generic_path(1)
+    try:
+        def work(i):
+            src = to_dev(xs[i], bits)
+            out = torch.zeros_like(src)
+            for _ in range(rounds):
+                capi.merge_ntt(in_ptr=src.data_ptr(), out_ptr=out.data_ptr(), table_ptr=tabs[i].data_ptr(), n_power=logn, batch=batch,
+                               element_bits=bits, direction=capi.FORWARD, reduction_poly=polys[i], modulus=Ps[i].modulus, stream=stream)
+                torch.cuda.synchronize()
+                if not (to_host(out, bits) == wants[i]).all():
+                    bad.append(i)
+                    return
+        threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    finally:
+        capi.lib().gpuntt_b200_force_generic_path(0)
+    assert not bad, f"thread(s) {sorted(set(bad))} read another call's twiddle companions"

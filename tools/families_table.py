@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""families.csv (ncu --csv metrics log of tools/r2_kernel_families.py, long format) -> one block per library kernel launch.
-usage: families_table.py gpurun_out/families.csv gpurun_out/families.log > profiles/r2_kernel_families_ncu.txt"""
+"""families.csv (ncu --csv metrics log of tools/kernel_families.py, long format) -> one block per library kernel launch.
+usage: families_table.py gpurun_out/families.csv gpurun_out/families.log > profiles/r2_v3_kernel_families_ncu.txt"""
 import csv
 import re
 import sys
@@ -42,7 +42,7 @@ def num(v):
         return float("nan")
 
 
-print("# one row block per kernel launch of tools/r2_kernel_families.py under ncu (--clock-control none; serialised, cold caches:")
+print("# one row block per kernel launch of tools/kernel_families.py under ncu (--clock-control none; serialised, cold caches:")
 print("# durations are for shares, not for bench values).  torch's own kernels (random fills) are dropped.")
 print("# cases in launch order:")
 for l in labels:

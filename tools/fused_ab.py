@@ -2,7 +2,7 @@
 """A/B of the single-launch two-pass kernels (merge_fused.cu) against one launch per pass, same box, same data:
 C2, C3 and a ring-size sweep; lag sweep for C2/C3.  One JSON object per line.
 
-    python tools/r2_fused_ab.py [--quick]
+    python tools/fused_ab.py [--quick]
 """
 import argparse
 import json

@@ -1,7 +1,7 @@
 #!/bin/bash
-# round 2, GPU pass 10: transposeless 4-step forms (reference-contract forward, both inverse contracts) -- parity, sanitizer, timings
+# compute-sanitizer memcheck + racecheck over the transposeless 4-step forms (reference-contract forward, both inverse contracts;
+# position-major product kernel with one and with several twiddle ranges, transposing stores) -> profiles/r2_compute_sanitizer_4step.txt
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_4step_gpu.py -q -x > gpurun_out/pytest_4step.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_4step.txt; tail -15 gpurun_out/pytest_4step.txt
 cat > /tmp/san_4step.py <<'PY'
 import sys
 sys.path.insert(0, ".")
@@ -32,22 +32,3 @@ for tool in memcheck racecheck; do
   timeout 600 compute-sanitizer --tool $tool python /tmp/san_4step.py > gpurun_out/sanitizer_4step_$tool.txt 2>&1
   echo "== $tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|Error|hazard|Traceback|assert" gpurun_out/sanitizer_4step_$tool.txt | head -10; grep -c "^ok " gpurun_out/sanitizer_4step_$tool.txt
 done
-cat > /tmp/perf4.py <<'PY'
-import sys
-sys.path.insert(0, "."); sys.path.insert(0, "tools")
-from gpu_ntt_b200 import capi
-import perf_configs as pc
-it = 8
-for knob in (1, 0):
-    capi.tune(3, knob)
-    tag = "" if knob else " [knob 3 = 0: transpose kernels]"
-    pc.fourstep_case("C4 4-step fused" + tag, 24, 16, it, capi.FOURSTEP_FUSED)
-    pc.fourstep_case("C4 4-step reference contract" + tag, 24, 16, it, capi.FOURSTEP_REFERENCE)
-    pc.fourstep_case("C4 4-step inverse fused" + tag, 24, 16, it, capi.FOURSTEP_FUSED, inverse=True)
-    pc.fourstep_case("C4 4-step inverse reference contract" + tag, 24, 16, it, capi.FOURSTEP_REFERENCE, inverse=True)
-    pc.fourstep_case("4-step fused logN=20" + tag, 20, 64, it, capi.FOURSTEP_FUSED)
-    pc.fourstep_case("4-step reference logN=20" + tag, 20, 64, it, capi.FOURSTEP_REFERENCE)
-    pc.fourstep_case("4-step inverse fused logN=22" + tag, 22, 16, it, capi.FOURSTEP_FUSED, inverse=True)
-    pc.fourstep_case("4-step inverse reference logN=20" + tag, 20, 64, it, capi.FOURSTEP_REFERENCE, inverse=True)
-PY
-timeout 600 python /tmp/perf4.py > gpurun_out/perf_4step.jsonl 2> gpurun_out/perf_4step_err.txt; tail -3 gpurun_out/perf_4step_err.txt; cut -c1-330 gpurun_out/perf_4step.jsonl
