@@ -12,7 +12,11 @@
 //   inverse  = batched size-n1 Merge-INTT over the batch*n2 contiguous rows (no n^-1), then strided
 //              Gentleman-Sande passes over the top log2(n2) index bits with the n2 table, the W^-1 product
 //              applied as the first of them loads (transposed index) and n^-1 as the last one stores.
-// Only the I/O contracts that ask for it pay a transpose (see gpuntt_b200_4step_desc::io_contract).
+// On the tuned kernels (64-bit, one modulus: merge_fast_4step.cu, merge_wcol.cu) no call pays a transpose kernel: where an I/O
+// contract asks for a transposed layout, one of the three data passes STORES transposed (TMA box, fast_round TS) -- forward fused:
+// the column pass; forward reference: the last row pass (the column transforms are contiguous runs of the caller's transposed
+// input); inverse fused: the size-n1 pass (read from y as a strided pass); inverse reference: the product pass.  The generic
+// kernel (32-bit data, several moduli) and a few small shapes still use transpose_kernel below.
 
 // matrix_dimention() of the reference (nttparameters.cu:305-354), index logn - 12
 static const int k4StepN1[] = {32, 32, 32, 64, 128, 32, 32, 32, 32, 64, 128, 128, 256};

@@ -1,7 +1,10 @@
 // gpu_ntt_b200/csrc/merge_fast_4step.cu -- 4-step phases on the tuned kernels:
-//   fast_fourstep_columns  forward column phase with the twiddle-matrix product as epilogue
-//   fast_fourstep_inverse  inverse (row phase + strided passes with the product as prologue)
-// Kernels and the launch helper live in fast_kernels.cuh.
+//   fast_fourstep_columns                forward column phase on the natural matrix, twiddle-matrix product as epilogue
+//   fast_fourstep_rows_t                 forward row phase along the n2 x n1 layout (optionally storing the n1 x n2 matrix)
+//   fast_fourstep_forward_transposed_in  forward, reference contract: contiguous column phase on the caller's transposed input
+//   fast_fourstep_inverse                inverse, either contract (size-n1 pass, product pass, last pass)
+//   fast_per_coefficient                 NTTLayout::PerCoefficient as strided passes of the same kernels
+// Kernels and the launch helper live in fast_kernels.cuh, the position-major product kernel in merge_wcol.cu.
 #include "fast_kernels.cuh"
 
 namespace gpuntt_b200
