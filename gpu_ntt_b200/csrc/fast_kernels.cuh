@@ -1313,34 +1313,30 @@ namespace gpuntt_b200
     struct FastPlan
     {
         int npass = 0;     // forward order
-        int d[3] = {0, 0, 0}, lo[3] = {0, 0, 0};
-        bool strided[3] = {false, false, false};
+        int d[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
+        bool strided[4] = {false, false, false, false};
     };
     // (an 8-stage contiguous pass for the small 32-bit rings -- a "balanced" split -- measured no faster than 4 + 10:
     // profiles/r1_ab_experiments.txt)
+    // The contiguous pass takes the low dc stages; the stages above it go to one, two or three strided passes of at most 8
+    // (replaces the reference's two- and three-kernel plans, ntt.cuh:628-697; three strided passes: rings of 2^25 .. 2^28).
     inline FastPlan make_fast_plan(int n, int element_bits)
     {
         FastPlan pl;
         const int dc = element_bits == 64 ? 8 : 10, rest = n - dc;
-        if (rest <= 8)
+        const int ns = rest <= 8 ? 1 : (rest <= 16 ? 2 : 3); // strided passes
+        pl.npass = ns + 1;
+        int left = rest, top = n;
+        for (int i = 0; i < ns; i++)
         {
-            pl.npass = 2;
-            pl.d[0] = rest;
-            pl.lo[0] = dc;
-            pl.strided[0] = true;
+            pl.d[i] = (left + (ns - i) - 1) / (ns - i); // the larger shares first
+            left -= pl.d[i];
+            top -= pl.d[i];
+            pl.lo[i] = top;
+            pl.strided[i] = true;
         }
-        else
-        {
-            pl.npass = 3;
-            pl.d[0] = (rest + 1) / 2;
-            pl.lo[0] = n - pl.d[0];
-            pl.strided[0] = true;
-            pl.d[1] = rest - pl.d[0];
-            pl.lo[1] = dc;
-            pl.strided[1] = true;
-        }
-        pl.d[pl.npass - 1] = dc;
-        pl.lo[pl.npass - 1] = 0;
+        pl.d[ns] = dc;
+        pl.lo[ns] = 0;
         return pl;
     }
 

@@ -9,12 +9,12 @@ namespace gpuntt_b200
 {
 
     // which (n_power, element width) the fast path covers.  64-bit: the last forward pass is the contiguous
-    // 8-stage pass, the n - 8 stages above it are one (n <= 16) or two (n <= 24) strided passes of 4..8 stages.
+    // 8-stage pass, the n - 8 stages above it are one (n <= 16), two (n <= 24) or three (n <= 28) strided passes of 4..8 stages.
     // 32-bit: contiguous 10-stage pass (two radix-32 rounds on 8192-element tiles), strided passes of 3..8 stages.
     bool fast_supported(int n_power, int element_bits)
     {
-        if (element_bits == 64) return n_power >= 12 && n_power <= 24;
-        return n_power >= 13 && n_power <= 26;
+        if (element_bits == 64) return n_power >= 12 && n_power <= 28;
+        return n_power >= 13 && n_power <= 28;
     }
 
     // single-pass small rings (fast_small below)

@@ -86,6 +86,83 @@ def test_large_rings_above_2_24(bits, logn):
     assert (to_host(d, bits) == x).all()
 
 
+@pytest.mark.parametrize("bits,logn,batch,poly", [(64, 25, 2, O.X_N_plus), (64, 26, 1, O.X_N_plus), (32, 27, 1, O.X_N_minus)])
+def test_large_rings_tuned_four_pass_plans(bits, logn, batch, poly):
+    """Rings above 2^24 (64-bit) / 2^26 (32-bit) take the tuned kernels as three strided passes + the contiguous pass: launch
+    count 4, every word against the oracle, inverse round trip (negacyclic rings and two polynomials per call as well; the
+    X^N-1 single-polynomial cases are in test_large_rings_above_2_24)."""
+    P = O.merge_params(logn, poly, bits)
+    x = O.example_input(P.modulus, batch << logn, seed=logn)
+    want = threaded_oracle(O.merge_ntt, x, P)
+    d = to_dev(x, bits)
+    tab = to_dev(P.fwd_br, bits)
+    capi.ntt(d.view(batch, -1), tab, P.modulus, logn, poly)
+    assert capi.lib().gpuntt_b200_last_launch_count() == 4
+    torch.cuda.synchronize()
+    got = to_host(d, bits)
+    assert (got == want).all(), f"{int((got != want).sum())} words differ"
+    del tab
+    itab = to_dev(P.inv_br, bits)
+    capi.intt(d.view(batch, -1), itab, P.modulus, P.n_inv, logn, poly)
+    assert capi.lib().gpuntt_b200_last_launch_count() == 4
+    torch.cuda.synchronize()
+    assert (to_host(d, bits) == x).all()
+
+
+def _sparse_closed_form(P, logn, nz, ks):
+    """X_k = sum_j x_j w^(j k) for the sparse input nz = {j: x_j}; NTTCPU::ntt leaves X_k at the bit-reversed position of k"""
+    p, w = P.modulus, P.root
+    out = {}
+    for k in ks:
+        pos = int(format(k, f"0{logn}b")[::-1], 2)
+        out[pos] = sum(v * pow(w, j * k, p) for j, v in nz.items()) % p
+    return out
+
+
+def test_ring_2_28_properties():
+    """N = 2^28, the largest ring the reference accepts (2 GiB per polynomial; the CPU oracle would need minutes): a sparse
+    input whose transform is known in closed form, sampled at 2000 outputs (the closed form itself is first checked against
+    the oracle at N = 2^10), the tuned plan's launch count, and the inverse round trip of a dense random input."""
+    bits = 64
+    small = O.merge_params(10, O.X_N_minus, bits)
+    nz = {0: 5, 1: 7, 77: 123456789, 600: small.modulus - 2}
+    xs = np.zeros(1 << 10, dtype=np.uint64)
+    for j, v in nz.items():
+        xs[j] = v
+    ys = O.merge_ntt(xs, small)
+    for pos, v in _sparse_closed_form(small, 10, nz, range(0, 1024, 37)).items():
+        assert int(ys[pos]) == v
+    logn = 28
+    n = 1 << logn
+    P = O.merge_params(logn, O.X_N_minus, bits)
+    p = P.modulus
+    nz = {0: 3, 1: 11, 12345: p - 1, (n >> 1) + 7: 987654321, n - 1: 42}
+    d = torch.zeros(n, dtype=torch.int64, device="cuda")
+    for j, v in nz.items():
+        d[j] = v if v < (1 << 63) else v - (1 << 64)
+    tab = to_dev(P.fwd_br, bits)
+    capi.ntt(d.view(1, -1), tab, p, logn, O.X_N_minus)
+    assert capi.lib().gpuntt_b200_last_launch_count() == 4
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(28)
+    ks = [0, 1, n - 1, n >> 1] + [int(k) for k in rng.integers(0, n, 2000)]
+    want = _sparse_closed_form(P, logn, nz, ks)
+    idx = torch.tensor(sorted(want), dtype=torch.int64, device="cuda")
+    got = d[idx].cpu().numpy().view(np.uint64)
+    assert [int(v) for v in got] == [want[k] for k in sorted(want)]
+    del tab, d
+    x = torch.randint(0, p, (n,), dtype=torch.int64, device="cuda")
+    y = x.clone()
+    tab = to_dev(P.fwd_br, bits)
+    capi.ntt(y.view(1, -1), tab, p, logn, O.X_N_minus)
+    del tab
+    itab = to_dev(P.inv_br, bits)
+    capi.intt(y.view(1, -1), itab, p, P.n_inv, logn, O.X_N_minus)
+    assert capi.lib().gpuntt_b200_last_launch_count() == 4
+    torch.cuda.synchronize()
+    assert bool((x == y).all())
+
+
 @pytest.mark.parametrize("logn,batch,poly", [(18, 3, O.X_N_plus), (19, 2, O.X_N_minus), (21, 2, O.X_N_plus),
                                              (22, 1, O.X_N_minus), (24, 1, O.X_N_plus), (24, 2, O.X_N_minus)])
 def test_large_rings_tuned_three_pass_plans(logn, batch, poly):
