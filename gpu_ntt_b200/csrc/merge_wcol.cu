@@ -13,7 +13,7 @@
 // prefetch: 64 KiB of pairs per 32 KiB tile, more than the L1 that is left beside two CTAs' tile buffers, and the ncu
 // capture shows the consumers stalled on those loads (profiles/r2_v1_ncu_summary.txt: long_scoreboard the top stall, 57 %
 // multiplier-pipe utilisation against 70 % for the row passes; the inverse pass, polynomial-major, re-read the whole pair
-// table from DRAM for every polynomial: 6.2 GB of reads for 2.1 GB of data, profiles/r2_kernel_families_ncu.txt).
+// table from DRAM for every polynomial: 6.2 GB of reads for 2.1 GB of data, profiles/r2_v4_kernel_families_ncu.txt).
 // This kernel turns the loop around: a CTA owns tile POSITIONS and walks every polynomial of the batch through one position
 // before it moves on, so the position's 64 KiB of pairs are loaded ONCE by the TMA engine into shared memory and reused
 // batch_size times; the product reads them with LDS.128 (conflict-free: a quarter warp reads 128 contiguous bytes).

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """families.csv (ncu --csv metrics log of tools/kernel_families.py, long format) -> one block per library kernel launch.
-usage: families_table.py gpurun_out/families.csv gpurun_out/families.log > profiles/r2_v3_kernel_families_ncu.txt"""
+usage: families_table.py gpurun_out/families.csv gpurun_out/families.log > profiles/r2_v4_kernel_families_ncu.txt"""
 import csv
 import re
 import sys

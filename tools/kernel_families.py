@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """One call of every kernel family of the library at a saturating size (run under ncu by tools/gpu_full_pass.sh: one metrics row per
-kernel for profiles/r2_v3_kernel_families_ncu.txt).  Random tables where parity does not matter (timing / counters only)."""
+kernel for profiles/r2_v4_kernel_families_ncu.txt).  Random tables where parity does not matter (timing / counters only)."""
 import os
 import sys
 
