@@ -27,7 +27,7 @@ namespace gpuntt_b200
     // beside the two 32 KiB tile buffers, so one CTA per SM with half the resident warps of the two-pass kernel).  Measured
     // (profiles/r2_one_tile_ab.jsonl): inverse transforms gain at every device-bound batch (64-bit +4 %, 32-bit +22 % at
     // 16384 polynomials), forward ones lose 10 %, and in the launch-bound regime the small-tile two-pass kernel is the
-    // quicker of the two.  Mode 1 (default): inverse transforms, 64-bit above the small-tile range, 32-bit from 512 polynomials; 0: never; 2: always.
+    // quicker of the two.  Mode 1 (default): inverse transforms, 64-bit only above the small-tile range; 0: never; 2: always.
     static int one_tile_default()
     {
         const char* e = getenv("GPUNTT_B200_ONE_TILE"); // (A/B runs of binaries that cannot call gpuntt_b200_tune)
@@ -42,9 +42,8 @@ namespace gpuntt_b200
         const int mode = g_one_tile_mode.load();
         if (mode == 2) return true;
         if (mode != 1 || !inverse) return false;
-        // 32-bit: the crossover against the single-launch two-pass kernel is near 600 polynomials (below it the call is
-        // launch-bound and the one-tile kernel's 8191-pair twiddle build is on its critical path)
-        return element_bits == 32 ? batch >= 512 : (batch << n_power) > fused_small_tile_elems();
+        // (32-bit: ahead or level at every batch size once the twiddle build issues its table loads in batches: 0.99-1.21x)
+        return element_bits == 32 || (batch << n_power) > fused_small_tile_elems();
     }
 
     // text form of the tuned plan for gpuntt_b200_describe_plan; returns the number of launches (0: not covered)

@@ -209,7 +209,7 @@ void gpuntt_b200_force_generic_path(int on);
 #define GPUNTT_B200_TUNE_4STEP_RESIDENT_PAIRS 5
 /*   ONE_TILE      64-bit N = 2^12 and 32-bit N = 2^13 are exactly one tile and can run with the whole transform inside it (one
  *                 launch, one HBM round trip, no hand-off between CTAs; one CTA per SM).  1 (default): inverse transforms -- the
- *                 measured win -- (64-bit: calls above the small-tile range below; 32-bit: from 512 polynomials); 0: never; 2: every call of these sizes. */
+ *                 measured win -- (64-bit: calls above the small-tile range below); 0: never; 2: every call of these sizes. */
 #define GPUNTT_B200_TUNE_ONE_TILE 6
 /*   SMALL_TILE_ELEMS  64-bit rings 2^12 .. 2^14: calls of at most this many elements in total (default 2^18) run the single-launch
  *                 kernel on 1024-element tiles instead of 4096-element ones -- four times the CTAs, a quarter of the work on the
