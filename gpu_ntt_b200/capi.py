@@ -115,6 +115,7 @@ def lib():
 
 
 TUNE_FUSED_PASSES, TUNE_FUSED_LAG = 1, 2
+TUNE_SINGLE_POLY_TILES = 8
 
 
 def tune(knob: int, value: int) -> None:

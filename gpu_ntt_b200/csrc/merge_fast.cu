@@ -34,6 +34,8 @@ namespace gpuntt_b200
         return e ? atoi(e) : 1;
     }
     static std::atomic<int> g_one_tile_mode{one_tile_default()};
+    static std::atomic<int> g_single_poly_tiles{1}; // (A/B: GPUNTT_B200_TUNE_SINGLE_POLY_TILES)
+    void fast_set_single_poly_tiles(int v) { g_single_poly_tiles.store(v ? 1 : 0); }
     void fast_set_one_tile_mode(int v) { g_one_tile_mode.store(v); }
     long long fused_small_tile_elems(); // merge_fused.cu
     static bool fast_one_tile(int n_power, int element_bits, long long batch, bool inverse)
@@ -246,6 +248,14 @@ namespace gpuntt_b200
                                     : (f60 ? launch_strided<T, false, 2>(pl.d[i], s, st) : launch_strided<T, false, 1>(pl.d[i], s, st));
                     else
                         e = inverse ? launch_strided<T, true, 0>(pl.d[i], s, st) : launch_strided<T, false, 0>(pl.d[i], s, st);
+                }
+                else if (batch == 1 && pl.npass >= 3 && (inverse ? fast_inv : f60) && g_single_poly_tiles.load())
+                {
+                    // ONE polynomial of a large ring (the shape of a ZK prover's transform): every tile of this pass has its own
+                    // twiddle set, and half of a two-polynomial tile would be zero fill.  2048-element tiles of one polynomial:
+                    // the same 2040 pairs per tile, half the butterflies.
+                    s.work = 1LL << (n_power - 11);
+                    e = inverse ? launch_fast<Shape<T, true, 1, false, 4, 4, 11, 0>>(s, st) : launch_fast<Shape<T, false, 2, false, 4, 4, 11, 0>>(s, st);
                 }
                 else
                 {

@@ -648,6 +648,7 @@ namespace gpuntt_b200
     void fused_set_small_tile_elems(long long v);
     void fourstep_set_resident_pairs(int on); // merge_fast_4step.cu
     void fast_set_one_tile_mode(int v);       // merge_fast.cu
+    void fast_set_single_poly_tiles(int v);
     bool fast_supported(int n_power, int element_bits);
 
     static int fail(int code, const std::string& msg)
@@ -1305,6 +1306,7 @@ extern "C"
             case GPUNTT_B200_TUNE_4STEP_RESIDENT_PAIRS: fourstep_set_resident_pairs(value); break;
             case GPUNTT_B200_TUNE_ONE_TILE: fast_set_one_tile_mode(value); break;
             case GPUNTT_B200_TUNE_SMALL_TILE_ELEMS: fused_set_small_tile_elems(value); break;
+            case GPUNTT_B200_TUNE_SINGLE_POLY_TILES: fast_set_single_poly_tiles(value); break;
             default: break;
         }
     }
