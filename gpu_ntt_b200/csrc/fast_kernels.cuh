@@ -44,6 +44,9 @@ namespace gpuntt_b200
 #ifndef GPUNTT_FAST_P1_NPLOG
 #define GPUNTT_FAST_P1_NPLOG 1  // log2 polynomials per tile of the forward contiguous pass
 #endif
+#ifndef GPUNTT_FAST_SP_BLOCKS
+#define GPUNTT_FAST_SP_BLOCKS 2 // CTAs per SM of the single-polynomial contiguous pass (one tile per twiddle segment: latency-bound)
+#endif
     constexpr int kConsumers = 256;
     constexpr int kFastThreads = kConsumers + 32;
 
@@ -1053,7 +1056,9 @@ namespace gpuntt_b200
     }
 
     template <typename S, bool WMUL = false, bool RNS = false, bool SFIN = false, bool TS = false>
-    __global__ void __launch_bounds__(kFastThreads, (!S::INV && S::POL == 2) ? (S::STRIDED ? GPUNTT_FAST_P0_BLOCKS : GPUNTT_FAST_P1_BLOCKS) : 2)
+    __global__ void __launch_bounds__(kFastThreads, (!S::STRIDED && S::NPLOG == 0 && S::NT == 0)
+                                                        ? GPUNTT_FAST_SP_BLOCKS
+                                                        : ((!S::INV && S::POL == 2) ? (S::STRIDED ? GPUNTT_FAST_P0_BLOCKS : GPUNTT_FAST_P1_BLOCKS) : 2))
         fast_pass_kernel(const FastArgs<typename S::T> a, const __grid_constant__ CUtensorMap map_in,
                          const __grid_constant__ CUtensorMap map_out)
     {

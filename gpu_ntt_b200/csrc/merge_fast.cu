@@ -325,6 +325,13 @@ namespace gpuntt_b200
                     e = inverse ? launch_strided32<true>(pl.d[i], s, st)
                                 : (lazy ? launch_strided32<false, 2>(pl.d[i], s, st) : launch_strided32<false>(pl.d[i], s, st));
                 }
+                else if (batch == 1 && pl.npass >= 3 && g_single_poly_tiles.load())
+                {
+                    // one polynomial of a large ring: 4096-element tiles of that polynomial (see the 64-bit branch)
+                    s.work = 1LL << (n_power - 12);
+                    e = inverse ? launch_fast<Shape<T, true, 0, false, 5, 5, 12, 0>>(s, st)
+                                : (lazy ? launch_fast<Shape<T, false, 2, false, 5, 5, 12, 0>>(s, st) : launch_fast<Shape<T, false, 0, false, 5, 5, 12, 0>>(s, st));
+                }
                 else
                 {
                     const long long tpr = (batch + 1) >> 1;

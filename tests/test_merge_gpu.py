@@ -846,21 +846,23 @@ def test_one_tile_rings(bits, poly):
         capi.tune(6, 1)
 
 
-@pytest.mark.parametrize("logn,poly", [(17, O.X_N_minus), (19, O.X_N_plus), (21, O.X_N_minus)])
-def test_single_polynomial_tiles_of_large_rings(logn, poly):
-    """ONE 64-bit polynomial of a ring above 2^16 (the shape of a ZK prover's transform, and what the reference's nvbench harness
-    sweeps: bench_merge_ntt.cu:71-75) runs its contiguous pass on 2048-element tiles of that polynomial; knob SINGLE_POLY_TILES = 0
-    gives the usual two-polynomial tiles.  Both settings, both directions, in and out of place, every word against the oracle."""
-    P = O.merge_params(logn, poly, 64)
+@pytest.mark.parametrize("bits,logn,poly", [(64, 17, O.X_N_minus), (64, 19, O.X_N_plus), (64, 21, O.X_N_minus),
+                                            (32, 19, O.X_N_minus), (32, 20, O.X_N_plus), (32, 22, O.X_N_minus)])
+def test_single_polynomial_tiles_of_large_rings(bits, logn, poly):
+    """ONE polynomial of a three-pass ring (64-bit above 2^16, 32-bit above 2^18: the shape of a ZK prover's transform, and what the
+    reference's nvbench harness sweeps, bench_merge_ntt.cu:71-75) runs its contiguous pass on 2048- / 4096-element tiles of that
+    polynomial; knob SINGLE_POLY_TILES = 0 gives the usual two-polynomial tiles.  Both settings, both directions, in and out of
+    place, every word against the oracle."""
+    P = O.merge_params(logn, poly, bits)
     x = O.example_input(P.modulus, 1 << logn, seed=logn + 7)
     want = O.merge_ntt(x, P)
     try:
         for knob in (1, 0):
             capi.tune(8, knob)
             for inplace in (True, False):
-                assert (run_fwd(x, P, 64, poly, inplace=inplace) == want).all(), (knob, inplace)
+                assert (run_fwd(x, P, bits, poly, inplace=inplace) == want).all(), (knob, inplace)
                 assert capi.lib().gpuntt_b200_last_launch_count() == 3
-                assert (run_inv(want, P, 64, poly, inplace=inplace) == x).all(), (knob, inplace)
+                assert (run_inv(want, P, bits, poly, inplace=inplace) == x).all(), (knob, inplace)
                 assert capi.lib().gpuntt_b200_last_launch_count() == 3
     finally:
         capi.tune(8, 1)

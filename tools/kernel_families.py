@@ -66,27 +66,39 @@ def fourstep(logn, batch, contract, inverse=False, resident=1):
     capi.tune(5, 1)
 
 
-print("1 C2 forward, one launch per pass"); merge(16, 1024, 64, fused=0)
-print("2 C2 inverse, one launch per pass"); merge(16, 1024, 64, inverse=True, fused=0)
-print("3 C2 forward, single-launch kernel"); merge(16, 1024, 64, fused=2)
-print("4 C3 forward, one launch per pass (32-bit shapes)"); merge(14, 4096, 32, fused=0)
-print("5 C3 inverse, one launch per pass"); merge(14, 4096, 32, inverse=True, fused=0)
-print("6 C3 forward, single-launch kernel"); merge(14, 4096, 32, fused=2)
-print("7 C3 inverse, single-launch kernel"); merge(14, 4096, 32, inverse=True, fused=2)
-print("8 small ring 64-bit 2^10 x 65536 (fast_small, three rounds)"); merge(10, 65536, 64)
-print("9 small ring 32-bit 2^12 x 32768"); merge(12, 32768, 32)
-print("10 three-pass ring 64-bit 2^20 x 64"); merge(20, 64, 64)
-print("11 RNS forward 4 x 59-bit, 2^16 x 1024 (fast_pass_dual_kernel)"); rns(16, 1024, 4, 0)
-print("12 RNS forward 4 x 59-bit, 2^14 x 32 (fused2_rns_kernel)"); rns(14, 32, 4, 2)
-print("13 generic path 64-bit 2^16 x 256 (twiddle_prep_kernel + merge_pass_kernel x 2)"); merge(16, 256, 64, generic=1)
-print("14 generic path 32-bit 2^14 x 1024"); merge(14, 1024, 32, generic=1)
-print("15 C4 fused contract forward (w_pairs_kernel, wcol_kernel strided + transposing store, two strided row passes)"); fourstep(24, 16, capi.FOURSTEP_FUSED)
-print("16 C4 fused forward with per-tile pairs (fast_pass_kernel WMUL + TS)"); fourstep(24, 16, capi.FOURSTEP_FUSED, resident=0)
-print("17 C4 reference contract forward (w_pairs_tile_kernel, wcol_kernel contiguous, strided row pass, strided row pass + transposing store)"); fourstep(24, 16, capi.FOURSTEP_REFERENCE)
-print("18 C4 fused inverse (pairs, strided n1 pass + transposing store, wcol_kernel inverse product pass, last strided pass)"); fourstep(24, 16, capi.FOURSTEP_FUSED, inverse=True)
-print("19 C4 reference contract inverse (pairs, contiguous n1 pass, wcol_kernel inverse product pass + transposing store, last pass along the rows)"); fourstep(24, 16, capi.FOURSTEP_REFERENCE, inverse=True)
+only = set(os.environ.get("GPUNTT_FAMILIES_ONLY", "").split(",")) - {""}  # e.g. GPUNTT_FAMILIES_ONLY=23,24: just those cases
+
+
+def case(label, fn):
+    if only and label.split()[0] not in only:
+        return
+    print(label)
+    fn()
+
+
+case("1 C2 forward, one launch per pass", lambda: merge(16, 1024, 64, fused=0))
+case("2 C2 inverse, one launch per pass", lambda: merge(16, 1024, 64, inverse=True, fused=0))
+case("3 C2 forward, single-launch kernel", lambda: merge(16, 1024, 64, fused=2))
+case("4 C3 forward, one launch per pass (32-bit shapes)", lambda: merge(14, 4096, 32, fused=0))
+case("5 C3 inverse, one launch per pass", lambda: merge(14, 4096, 32, inverse=True, fused=0))
+case("6 C3 forward, single-launch kernel", lambda: merge(14, 4096, 32, fused=2))
+case("7 C3 inverse, single-launch kernel", lambda: merge(14, 4096, 32, inverse=True, fused=2))
+case("8 small ring 64-bit 2^10 x 65536 (fast_small, three rounds)", lambda: merge(10, 65536, 64))
+case("9 small ring 32-bit 2^12 x 32768", lambda: merge(12, 32768, 32))
+case("10 three-pass ring 64-bit 2^20 x 64", lambda: merge(20, 64, 64))
+case("11 RNS forward 4 x 59-bit, 2^16 x 1024 (fast_pass_dual_kernel)", lambda: rns(16, 1024, 4, 0))
+case("12 RNS forward 4 x 59-bit, 2^14 x 32 (fused2_rns_kernel)", lambda: rns(14, 32, 4, 2))
+case("13 generic path 64-bit 2^16 x 256 (twiddle_prep_kernel + merge_pass_kernel x 2)", lambda: merge(16, 256, 64, generic=1))
+case("14 generic path 32-bit 2^14 x 1024", lambda: merge(14, 1024, 32, generic=1))
+case("15 C4 fused contract forward (w_pairs_kernel, wcol_kernel strided + transposing store, two strided row passes)", lambda: fourstep(24, 16, capi.FOURSTEP_FUSED))
+case("16 C4 fused forward with per-tile pairs (fast_pass_kernel WMUL + TS)", lambda: fourstep(24, 16, capi.FOURSTEP_FUSED, resident=0))
+case("17 C4 reference contract forward (w_pairs_tile_kernel, wcol_kernel contiguous, strided row pass, strided row pass + transposing store)", lambda: fourstep(24, 16, capi.FOURSTEP_REFERENCE))
+case("18 C4 fused inverse (pairs, strided n1 pass + transposing store, wcol_kernel inverse product pass, last strided pass)", lambda: fourstep(24, 16, capi.FOURSTEP_FUSED, inverse=True))
+case("19 C4 reference contract inverse (pairs, contiguous n1 pass, wcol_kernel inverse product pass + transposing store, last pass along the rows)", lambda: fourstep(24, 16, capi.FOURSTEP_REFERENCE, inverse=True))
 capi.tune(3, 0)
-print("20 C4 reference contract forward with knob 4STEP_TRANSPOSED = 0 (transpose_kernel, column pass, row passes)"); fourstep(24, 16, capi.FOURSTEP_REFERENCE)
+case("20 C4 reference contract forward with knob 4STEP_TRANSPOSED = 0 (transpose_kernel, column pass, row passes)", lambda: fourstep(24, 16, capi.FOURSTEP_REFERENCE))
 capi.tune(3, 1)
-print("21 one-tile ring, 32-bit 2^13 x 16384 inverse (whole transform in a tile)"); merge(13, 16384, 32, inverse=True)
-print("22 small-tile single-launch kernel, 64-bit 2^13 x 8 forward (1024-element tiles)"); merge(13, 8, 64)
+case("21 one-tile ring, 32-bit 2^13 x 16384 inverse (whole transform in a tile)", lambda: merge(13, 16384, 32, inverse=True))
+case("22 small-tile single-launch kernel, 64-bit 2^13 x 8 forward (1024-element tiles)", lambda: merge(13, 8, 64))
+case("23 one polynomial of a three-pass ring, 64-bit 2^24 x 1 (contiguous pass on 2048-element single-polynomial tiles)", lambda: merge(24, 1, 64))
+case("24 one polynomial of a three-pass ring, 32-bit 2^24 x 1 (contiguous pass on 4096-element single-polynomial tiles)", lambda: merge(24, 1, 32))
