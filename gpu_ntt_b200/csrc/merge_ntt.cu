@@ -650,6 +650,7 @@ namespace gpuntt_b200
     void fast_set_one_tile_mode(int v);       // merge_fast.cu
     void fast_set_single_poly_tiles(int v);
     bool fast_supported(int n_power, int element_bits);
+    bool fast_small_supported(int n_power, int element_bits); // merge_fast.cu
 
     static int fail(int code, const std::string& msg)
     {
@@ -941,6 +942,26 @@ namespace gpuntt_b200
         const bool rns = d->mod_count > 0;
         const bool plus = d->reduction_poly == GPUNTT_B200_X_N_PLUS;
         cudaStream_t st = (cudaStream_t) d->stream;
+        if (!rns && !g_force_generic.load() && d->ntt_layout == GPUNTT_B200_PER_POLYNOMIAL && fast_small_supported(n, (int) sizeof(T) * 8))
+        {
+            // Small rings walk the array as whole 2048- / 4096-element chunks (fast_small).  A batch that ends inside a chunk is
+            // split: the polynomials of the whole chunks take the one-launch tuned kernel, the (fewer than 16) polynomials of the
+            // ragged tail the generic kernel -- instead of the whole batch falling back for one odd polynomial.
+            const int chunk_log = (sizeof(T) == 8 ? 11 : 12) - n; // log2 polynomials per chunk (one-tile rings: a polynomial is a chunk)
+            const int tail = chunk_log > 0 ? (d->batch_size & ((1 << chunk_log) - 1)) : 0;
+            if (tail > 0 && d->batch_size > tail)
+            {
+                gpuntt_b200_merge_desc part = *d;
+                part.batch_size = d->batch_size - tail;
+                int rc = merge_execute_t<T>(&part);
+                if (rc != GPUNTT_B200_OK) return rc;
+                const size_t skip = ((size_t) part.batch_size << n) * sizeof(T);
+                part.in = reinterpret_cast<const char*>(d->in) + skip;
+                part.out = reinterpret_cast<char*>(d->out) + skip;
+                part.batch_size = tail;
+                return merge_execute_t<T>(&part);
+            }
+        }
         if (!rns && !g_force_generic.load() && d->ntt_layout == GPUNTT_B200_PER_POLYNOMIAL)
         {
             // (signed data: same kernels -- the first forward round fixes negative inputs up as it loads, the last inverse

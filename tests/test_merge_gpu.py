@@ -812,11 +812,17 @@ def test_small_rings_single_pass_tuned_kernels(bits, poly, logn):
             assert (run_inv(want, P, bits, poly) == x).all()
         finally:
             capi.lib().gpuntt_b200_force_generic_path(0)
-    # a batch that does not fill whole chunks stays on the generic kernel and is still exact
-    batch = ((3 * chunk) >> logn) + 1
-    if (batch << logn) % chunk:
-        x = O.example_input(P.modulus, batch << logn, seed=99)
-        assert (run_fwd(x, P, bits, poly) == O.merge_ntt(x, P)).all()
+    # a batch that ends inside a chunk is split: whole chunks on the tuned kernel (one launch), the ragged tail (fewer polynomials
+    # than a chunk holds) on the generic kernel; a batch smaller than one chunk is the generic kernel alone
+    for batch in (((3 * chunk) >> logn) + 1, ((40 * chunk) >> logn) - 1, max(1, (chunk >> logn) - 1)):
+        if (batch << logn) % chunk:
+            x = O.example_input(P.modulus, batch << logn, seed=99 + batch)
+            want = O.merge_ntt(x, P)
+            for inplace in (True, False):
+                assert (run_fwd(x, P, bits, poly, inplace=inplace) == want).all(), (batch, inplace)
+                n_launch = capi.lib().gpuntt_b200_last_launch_count()
+                assert n_launch >= (2 if (batch << logn) > chunk else 1), (batch, n_launch)
+                assert (run_inv(want, P, bits, poly, inplace=inplace) == x).all(), (batch, inplace)
 
 
 @pytest.mark.parametrize("bits", [64, 32])
