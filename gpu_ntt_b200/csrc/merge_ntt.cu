@@ -935,6 +935,7 @@ namespace gpuntt_b200
         return GPUNTT_B200_OK;
     }
 
+    constexpr long long kRaggedSplitMinElems = 1LL << 22;
     template <typename T> static int merge_execute_t(const gpuntt_b200_merge_desc* d)
     {
         const int n = d->n_power;
@@ -946,10 +947,12 @@ namespace gpuntt_b200
         {
             // Small rings walk the array as whole 2048- / 4096-element chunks (fast_small).  A batch that ends inside a chunk is
             // split: the polynomials of the whole chunks take the one-launch tuned kernel, the (fewer than 16) polynomials of the
-            // ragged tail the generic kernel -- instead of the whole batch falling back for one odd polynomial.
+            // ragged tail the generic kernel -- instead of the whole batch falling back for one odd polynomial.  Only above 2^22
+            // elements: the tail costs two more launches, and a launch-bound call is quicker on the generic kernel alone
+            // (profiles/r2_ragged_small_ab.jsonl: 2.1-4.4x for 2^26-element batches, 0.7-0.9x for 2^12 .. 2^20 elements).
             const int chunk_log = (sizeof(T) == 8 ? 11 : 12) - n; // log2 polynomials per chunk (one-tile rings: a polynomial is a chunk)
             const int tail = chunk_log > 0 ? (d->batch_size & ((1 << chunk_log) - 1)) : 0;
-            if (tail > 0 && d->batch_size > tail)
+            if (tail > 0 && ((long long) (d->batch_size - tail) << n) >= kRaggedSplitMinElems)
             {
                 gpuntt_b200_merge_desc part = *d;
                 part.batch_size = d->batch_size - tail;

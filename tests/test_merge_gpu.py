@@ -812,16 +812,21 @@ def test_small_rings_single_pass_tuned_kernels(bits, poly, logn):
             assert (run_inv(want, P, bits, poly) == x).all()
         finally:
             capi.lib().gpuntt_b200_force_generic_path(0)
-    # a batch that ends inside a chunk is split: whole chunks on the tuned kernel (one launch), the ragged tail (fewer polynomials
-    # than a chunk holds) on the generic kernel; a batch smaller than one chunk is the generic kernel alone
-    for batch in (((3 * chunk) >> logn) + 1, ((40 * chunk) >> logn) - 1, max(1, (chunk >> logn) - 1)):
+    # a batch that ends inside a chunk: from 2^22 elements up it is split -- whole chunks on the tuned kernel (one launch), the ragged
+    # tail (fewer polynomials than a chunk holds) on the generic kernel; smaller ones are the generic kernel alone
+    for batch, split in ((((3 * chunk) >> logn) + 1, False), (((1 << 22) >> logn) + 1, True), (((1 << 22) >> logn) + (chunk >> logn) - 1, True)):
         if (batch << logn) % chunk:
-            x = O.example_input(P.modulus, batch << logn, seed=99 + batch)
+            x = O.example_input(P.modulus, batch << logn, seed=99 + batch % 7)
             want = O.merge_ntt(x, P)
             for inplace in (True, False):
                 assert (run_fwd(x, P, bits, poly, inplace=inplace) == want).all(), (batch, inplace)
-                n_launch = capi.lib().gpuntt_b200_last_launch_count()
-                assert n_launch >= (2 if (batch << logn) > chunk else 1), (batch, n_launch)
+                if split:
+                    capi.lib().gpuntt_b200_force_generic_path(1)
+                    run_fwd(x[: 1 << logn], P, bits, poly)
+                    generic_launches = capi.lib().gpuntt_b200_last_launch_count()
+                    capi.lib().gpuntt_b200_force_generic_path(0)
+                    run_fwd(x, P, bits, poly, inplace=inplace)
+                    assert capi.lib().gpuntt_b200_last_launch_count() == 1 + generic_launches, batch
                 assert (run_inv(want, P, bits, poly, inplace=inplace) == x).all(), (batch, inplace)
 
 
