@@ -438,3 +438,33 @@ def test_4step_moduli_at_the_top_of_the_lazy_range(logn):
     capi.fourstep_ntt(d.view(batch, P.n), it1, it2, iW, p, logn, direction=capi.INVERSE, mod_inverse=P.n_inv)
     torch.cuda.synchronize()
     assert (to_host(d, 64).reshape(batch, -1) == x).all()
+
+
+@pytest.mark.parametrize("limit", [1 << 30, (1 << 36) + (1 << 30), (1 << 40) - 1, (1 << 60) + (1 << 25), (1 << 60) + (1 << 58) + (1 << 40),
+                                   (1 << 62) - 1])
+@pytest.mark.parametrize("logn,batch", [(13, 4), (17, 4), (20, 2)])
+def test_4step_modulus_ranges(limit, logn, batch):
+    """Moduli outside the lazy policies of the tuned 4-step kernels (below 2^40, above 2^60 - 2^31, up to the reference's 2^62 limit,
+    modular_arith.cuh:66-67): whichever kernels a call lands on -- generic product passes, exact-policy row transforms -- both
+    contracts and both directions equal NTT_4STEP_CPU word for word."""
+    from tests.test_moduli_gpu import ntt_prime_below
+    p = ntt_prime_below(limit, 1 << logn)
+    P = custom_fourstep_params(logn, p)
+    rng = np.random.default_rng(logn + limit % 1009)
+    x = rng.integers(0, p, size=(batch, P.n), dtype=np.uint64)
+    x[1, :] = p - 1
+    want = O.fourstep_ntt(x, P)
+    t1, t2, W = tables(P, 64, False)
+    it1, it2, iW = tables(P, 64, True)
+    d = to_dev(x, 64)
+    capi.fourstep_ntt(d.view(batch, P.n), t1, t2, W, p, logn)
+    torch.cuda.synchronize()
+    assert (to_host(d, 64).reshape(batch, -1) == want).all(), f"fused forward p={p}"
+    capi.fourstep_ntt(d.view(batch, P.n), it1, it2, iW, p, logn, direction=capi.INVERSE, mod_inverse=P.n_inv)
+    torch.cuda.synchronize()
+    assert (to_host(d, 64).reshape(batch, -1) == x).all(), f"fused inverse p={p}"
+    xt = to_dev(transposed(x, P.n1, P.n2), 64)
+    r = torch.zeros_like(xt)
+    capi.fourstep_ntt(xt.view(batch, P.n), t1, t2, W, p, logn, io_contract=capi.FOURSTEP_REFERENCE, out=r.view(batch, P.n))
+    torch.cuda.synchronize()
+    assert (transposed(to_host(r, 64), P.n1, P.n2).reshape(batch, -1) == want).all(), f"reference-contract forward p={p}"

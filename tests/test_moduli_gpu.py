@@ -114,3 +114,45 @@ def test_modulus_ranges(limit, logn, poly):
         assert (to_host(d, 64).reshape(batch, -1) == x).all(), f"generic inverse mismatch p={p}"
     finally:
         capi.lib().gpuntt_b200_force_generic_path(0)
+
+
+# 32-bit data: the forward kernels are lazy (ModL32) up to p = 2^29 and exact above, the inverse kernels exact throughout; the
+# reference takes Data32 moduli up to 30 bits (modular_arith.cuh:66).  A prime on each side of 2^29, the top of the 30-bit range,
+# and the small primes lattice schemes use (12289 = 3 * 2^12 + 1, 7681, 40961 where the ring allows them).
+LIMITS32 = [1 << 13, 1 << 14, 1 << 17, 1 << 24, 1 << 29, (1 << 29) + (1 << 20), (1 << 29) + (1 << 28), (1 << 30) - 1]
+
+
+@pytest.mark.parametrize("limit", LIMITS32)
+@pytest.mark.parametrize("logn,poly,batch", [(8, O.X_N_plus, 48), (10, O.X_N_minus, 5), (11, O.X_N_plus, 8), (12, O.X_N_minus, 4),
+                                             (13, O.X_N_plus, 3), (14, O.X_N_minus, 6), (16, O.X_N_plus, 2), (19, O.X_N_minus, 2),
+                                             (20, O.X_N_plus, 1)])
+def test_modulus_ranges_32bit(limit, logn, poly, batch):
+    two_n = 2 << logn
+    if limit <= two_n:
+        pytest.skip("no prime p = 1 (mod 2N) below this limit")
+    try:
+        p = ntt_prime_below(limit, two_n)
+    except ValueError:
+        pytest.skip("no prime p = 1 (mod 2N) below this limit")
+    P = custom_params(logn, poly, p)
+    rng = np.random.default_rng(limit % 1000003 + logn)
+    x = rng.integers(0, p, size=(batch, 1 << logn), dtype=np.uint64)
+    x[0, :4] = (p - 1, 0, p - 1, 1)           # extremes
+    x[-1, :] = p - 1
+    want = O.merge_ntt(x, P)
+    tab, itab = to_dev(P.fwd_br, 32), to_dev(P.inv_br, 32)
+    for generic in (0, 1):
+        capi.lib().gpuntt_b200_force_generic_path(generic)
+        try:
+            for inplace in (True, False):
+                d = to_dev(x, 32)
+                out = d if inplace else torch.zeros_like(d)
+                capi.ntt(d, tab, p, logn, poly, out=out)
+                torch.cuda.synchronize()
+                assert (to_host(out, 32).reshape(batch, -1) == want).all(), f"forward mismatch p={p} generic={generic} inplace={inplace}"
+                back = out if inplace else torch.zeros_like(d)
+                capi.intt(out, itab, p, P.n_inv, logn, poly, out=back)
+                torch.cuda.synchronize()
+                assert (to_host(back, 32).reshape(batch, -1) == x).all(), f"inverse mismatch p={p} generic={generic} inplace={inplace}"
+        finally:
+            capi.lib().gpuntt_b200_force_generic_path(0)
