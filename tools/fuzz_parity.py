@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """Randomised differential test of the Merge-NTT entry point against the oracle (test infrastructure; run on a GPU box):
 random (width, ring size, ring type, batch, modulus anywhere in the accepted range, direction, in / out of place, signed I/O,
-tuned / generic kernels, single-launch knob; three cases in ten through the RNS overloads with 1..5 random moduli) with extreme
+tuned / generic kernels, single-launch knob; three cases in ten through the RNS overloads with 1..5 random moduli, a
+share through GPU_4STEP_NTT in both I/O contracts and directions) with extreme
 inputs mixed in; every output word is compared with NTTCPU's
-restatement.  Usage: fuzz_parity.py [seconds] [seed].  Prints one JSON line per mismatch and a summary line; exit code 1 on
+restatement.  Usage: fuzz_parity.py [seconds] [seed] [4-step share].  Prints one JSON line per mismatch and a summary line; exit code 1 on
 any mismatch."""
 import json
 import os
@@ -22,6 +23,7 @@ from tests.test_moduli_gpu import custom_params, ntt_prime_below  # noqa: E402
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+fourstep_share = float(sys.argv[3]) if len(sys.argv) > 3 else 0.1     # share of the cases that go through GPU_4STEP_NTT
 rng = np.random.default_rng(seed)
 lib = capi.lib()
 params_cache = {}
@@ -182,22 +184,87 @@ def run_rns_case(c):
         capi.tune(capi.TUNE_FUSED_PASSES, 1)
 
 
+fs_cache = {}
+
+
+def pick_4step_case():
+    bits = int(rng.choice([32, 64, 64]))
+    logn = int(rng.choice([int(rng.integers(12, 18)), int(rng.integers(12, 22))]))
+    n = 1 << logn
+    max_bits = 30 if bits == 32 else 62
+    if rng.random() < 0.4 and bits == 64:
+        edges = [1 << 40, (1 << 40) + (1 << 34), (1 << 60) - (1 << 31), (1 << 60) - (1 << 31) + (1 << 40), (1 << 60) + (1 << 58),
+                 (1 << 60) + (1 << 58) + (1 << 45), (1 << 62) - 1]
+        limit = int(edges[int(rng.integers(0, len(edges)))])
+    else:
+        b = int(rng.integers(logn + 3, max_bits + 1))
+        limit = (1 << b) - int(rng.integers(0, 1 << (b - 2)))
+    try:
+        p = ntt_prime_below(limit, n)
+    except ValueError:
+        return None
+    batch = int(rng.integers(1, max(2, min(9, ((1 << 22) >> logn) + 1))))
+    fused = bool(rng.integers(0, 2))
+    return dict(fourstep=True, bits=bits, logn=logn, p=p, batch=batch, inverse=bool(rng.integers(0, 2)), fused_contract=fused,
+                inplace=fused and bool(rng.integers(0, 2)), signed=False, generic=bool(rng.random() < 0.1),
+                transposed_knob=int(rng.choice([1, 1, 0])))
+
+
+def run_4step_case(c):
+    """GPU_4STEP_NTT in both I/O contracts (the reference's, between the caller's transposes, and the fused natural-order one)
+    against NTT_4STEP_CPU (test_4step_ntt.cu:147-166, test_4step_intt.cu:82-84, 155-166)."""
+    from tests.test_4step_gpu import custom_fourstep_params, tables, transposed
+    bits, logn, p, batch = c["bits"], c["logn"], c["p"], c["batch"]
+    if (logn, p) not in fs_cache:
+        if len(fs_cache) > 8:
+            fs_cache.clear()
+        fs_cache[(logn, p)] = custom_fourstep_params(logn, p)
+    P = fs_cache[(logn, p)]
+    n = P.n
+    x = rng.integers(0, p, size=(batch, n), dtype=np.uint64)
+    x[0, ::3] = p - 1
+    inv = c["inverse"]
+    want = O.fourstep_intt(x, P) if inv else O.fourstep_ntt(x, P)
+    t1, t2, W = tables(P, bits, inv)
+    lib.gpuntt_b200_force_generic_path(1 if c["generic"] else 0)
+    capi.tune(3, c["transposed_knob"])      # knob 3: transposing stores inside the passes / transpose kernels
+    try:
+        if c["fused_contract"]:
+            d = to_dev(x, bits)
+            out = d if c["inplace"] else torch.zeros_like(d)
+            capi.fourstep_ntt(d.view(batch, n), t1, t2, W, p, logn, direction=capi.INVERSE if inv else capi.FORWARD,
+                              mod_inverse=P.n_inv if inv else 0, out=out.view(batch, n))
+            torch.cuda.synchronize()
+            return bool((to_host(out, bits).reshape(batch, n) == want).all())
+        src = O.fourstep_intt_first_transpose(x, P) if inv else transposed(x, P.n1, P.n2)
+        d = to_dev(src, bits)
+        r = torch.zeros_like(d)
+        capi.fourstep_ntt(d.view(batch, n), t1, t2, W, p, logn, direction=capi.INVERSE if inv else capi.FORWARD,
+                          mod_inverse=P.n_inv if inv else 0, io_contract=capi.FOURSTEP_REFERENCE, out=r.view(batch, n))
+        torch.cuda.synchronize()
+        return bool((transposed(to_host(r, bits), P.n1, P.n2).reshape(batch, n) == want).all())
+    finally:
+        lib.gpuntt_b200_force_generic_path(0)
+        capi.tune(3, 1)
+
+
 def main():
     t0 = time.time()
     done = bad = 0
     kinds = {}
     while time.time() - t0 < budget:
-        rns = rng.random() < 0.3
-        c = pick_rns_case() if rns else pick_case()
+        u = rng.random()
+        rns, fs = u < 0.3, (u >= 0.3 and u < 0.3 + fourstep_share)
+        c = pick_rns_case() if rns else pick_4step_case() if fs else pick_case()
         if c is None:
             continue
         try:
-            ok = run_rns_case(c) if rns else run_case(c)
+            ok = run_rns_case(c) if rns else run_4step_case(c) if fs else run_case(c)
         except Exception as e:  # an error code from the library is a finding as well
             ok = False
             c["error"] = repr(e)[:200]
         done += 1
-        k = (c["bits"], "inv" if c["inverse"] else "fwd", "rns" if rns else "signed" if c["signed"] else "unsigned",
+        k = (c["bits"], "inv" if c["inverse"] else "fwd", "rns" if rns else "4step" if fs else "signed" if c["signed"] else "unsigned",
              "generic" if c["generic"] else "tuned")
         kinds[k] = kinds.get(k, 0) + 1
         if not ok:
