@@ -122,6 +122,33 @@ def test_fused_concurrent_streams():
         assert (to_host(d, 64) == w).all()
 
 
+def test_fused_streams_stress():
+    """Three streams issue forward / inverse single-launch calls back to back without any synchronisation while a fourth keeps
+    the SMs busy with unrelated kernels: full-grid persistent kernels of different calls queue behind each other (a later grid
+    starts as the earlier one drains), every stream's counters stay its own, and the round trips end on the input."""
+    cases = [(64, 13, 2500), (32, 14, 4096), (64, 15, 300)]
+    work = []
+    for (bits, logn, batch), seed in zip(cases, (11, 12, 13)):
+        P = O.merge_params(logn, O.X_N_plus, bits)
+        x = O.example_input(P.modulus, batch << logn, seed=seed)
+        work.append((bits, logn, batch, P, x, to_dev(x, bits), to_dev(P.fwd_br, bits), to_dev(P.inv_br, bits), torch.cuda.Stream()))
+    noise_stream = torch.cuda.Stream()
+    noise = torch.ones(1 << 26, device="cuda")
+    torch.cuda.synchronize()
+    for it in range(12):
+        with torch.cuda.stream(noise_stream):
+            noise.mul_(1.0001).add_(0.5)
+        for bits, logn, batch, P, x, d, tab, itab, s in work:
+            capi.ntt(d.view(batch, -1), tab, P.modulus, logn, O.X_N_plus, stream=s)
+            assert _launches() == 1
+            capi.intt(d.view(batch, -1), itab, P.modulus, P.n_inv, logn, O.X_N_plus, stream=s)
+    for bits, logn, batch, P, x, d, tab, itab, s in work:
+        capi.ntt(d.view(batch, -1), tab, P.modulus, logn, O.X_N_plus, stream=s)
+    torch.cuda.synchronize()
+    for bits, logn, batch, P, x, d, tab, itab, s in work:
+        assert (to_host(d, bits) == _threaded_oracle(O.merge_ntt, x, P)).all(), (bits, logn)
+
+
 def test_default_policy_launch_counts():
     """Default policy: 32-bit two-pass transforms are one launch at every batch size, 64-bit ones while the call is
     launch-bound (at most one strided tile per SM); results identical either way."""
