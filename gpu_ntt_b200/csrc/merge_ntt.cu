@@ -977,6 +977,24 @@ namespace gpuntt_b200
             if (fe != cudaSuccess) return cuda_fail(fe, "fast_pass_kernel launch");
             if (launched > 0) return GPUNTT_B200_OK;
         }
+        if (rns && !d->is_signed && !g_force_generic.load() && d->ntt_layout == GPUNTT_B200_PER_POLYNOMIAL && !d->modulus_order_dev &&
+            !d->poly_order_dev && d->mod_count > 1 && d->batch_size % d->mod_count != 0 &&
+            ((long long) (d->batch_size - d->batch_size % d->mod_count) << n) >= kRaggedSplitMinElems)
+        {
+            // The tuned RNS kernels give every modulus slot the same number of polynomials.  A batch that is not a multiple of
+            // mod_count is split the same way as a ragged small-ring batch: the whole rounds of slots on the tuned kernels, the last
+            // (fewer than mod_count) polynomials -- whose index modulo mod_count is their index in the tail -- on the generic kernel.
+            const int tail = d->batch_size % d->mod_count;
+            gpuntt_b200_merge_desc part = *d;
+            part.batch_size = d->batch_size - tail;
+            int rc = merge_execute_t<T>(&part);
+            if (rc != GPUNTT_B200_OK) return rc;
+            const size_t skip = ((size_t) part.batch_size << n) * sizeof(T);
+            part.in = reinterpret_cast<const char*>(d->in) + skip;
+            part.out = reinterpret_cast<char*>(d->out) + skip;
+            part.batch_size = tail;
+            return merge_execute_t<T>(&part);
+        }
         if (rns && !d->is_signed && !g_force_generic.load() && d->ntt_layout == GPUNTT_B200_PER_POLYNOMIAL)
         {
             void* flag = fused_counters(d->stream, d->batch_size); // progress counters of the single-launch kernels (may be null)

@@ -354,6 +354,20 @@ def test_rns_small_rings_tuned_kernels(bits, logn, batch, mod_count, tops):
     assert capi.lib().gpuntt_b200_last_launch_count() == 1
 
 
+@pytest.mark.parametrize("bits,logn,batch,mod_count,tops", [(64, 12, 1202, 3, (59, 61, 50)), (32, 14, 301, 2, (29, 27)),
+                                                            (64, 10, 4099, 4, (59, 59, 58, 45))])
+def test_rns_batch_not_a_multiple_of_mod_count_is_split(bits, logn, batch, mod_count, tops):
+    """From 2^22 elements up, an RNS batch that is not a multiple of mod_count runs its whole rounds of slots on the tuned kernels
+    and only the last (fewer than mod_count) polynomials on the generic kernel; below, the generic kernel takes the whole call."""
+    primes = [rns_primes(bits, logn, 1 + i, t)[i] for i, t in enumerate(tops)]
+    _rns_roundtrip(bits, logn, batch, mod_count, primes)
+    split_launches = capi.lib().gpuntt_b200_last_launch_count()
+    _rns_roundtrip(bits, logn, batch % mod_count, mod_count, primes)
+    tail_launches = capi.lib().gpuntt_b200_last_launch_count()
+    _rns_roundtrip(bits, logn, batch - batch % mod_count, mod_count, primes)
+    assert split_launches == capi.lib().gpuntt_b200_last_launch_count() + tail_launches
+
+
 def _rns_roundtrip(bits, logn, batch, mod_count, primes):
     n = 1 << logn
     fwd_tab = np.zeros(mod_count << logn, dtype=np.uint64)
