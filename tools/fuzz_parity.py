@@ -2,7 +2,7 @@
 """Randomised differential test of the Merge-NTT entry point against the oracle (test infrastructure; run on a GPU box):
 random (width, ring size, ring type, batch, modulus anywhere in the accepted range, direction, in / out of place, signed I/O,
 tuned / generic kernels, single-launch knob; three cases in ten through the RNS overloads with 1..5 random moduli, a
-share through GPU_4STEP_NTT in both I/O contracts and directions) with extreme
+share through GPU_4STEP_NTT in both I/O contracts and directions, one in ten in NTTLayout::PerCoefficient) with extreme
 inputs mixed in; every output word is compared with NTTCPU's
 restatement.  Usage: fuzz_parity.py [seconds] [seed] [4-step share].  Prints one JSON line per mismatch and a summary line; exit code 1 on
 any mismatch."""
@@ -184,6 +184,55 @@ def run_rns_case(c):
         capi.tune(capi.TUNE_FUSED_PASSES, 1)
 
 
+def pick_percoeff_case():
+    bits = int(rng.choice([32, 64, 64]))
+    logn = int(rng.integers(1, 10))
+    p = None
+    if bits == 64 and rng.random() < 0.4:
+        edges = [1 << 36, 1 << 40, (1 << 40) + (1 << 34), (1 << 60) - (1 << 31), (1 << 60) - (1 << 31) + (1 << 40), (1 << 60) + (1 << 58),
+                 (1 << 60) + (1 << 58) + (1 << 45), (1 << 62) - 1]
+        p = ntt_prime_below(int(edges[int(rng.integers(0, len(edges)))]), 2 << logn)
+    else:
+        p = random_prime(bits, 2 << logn, logn)
+    if p is None:
+        return None
+    w = 1 << int(rng.integers(0, 21 - logn))       # the reference's limit for this layout: a power-of-two batch (ntt.cu:2235)
+    signed = bool(rng.random() < 0.2)
+    return dict(percoeff=True, bits=bits, logn=logn, poly=int(rng.choice([O.X_N_minus, O.X_N_plus])), p=p, batch=w,
+                inverse=bool(rng.integers(0, 2)), inplace=bool(rng.integers(0, 2)) and not signed, signed=signed,
+                generic=bool(rng.random() < 0.15))
+
+
+def run_percoeff_case(c):
+    """NTTLayout::PerCoefficient (ForwardCoreTranspose / InverseCoreTranspose, ntt.cu:1554-2074): one [N][batch] matrix whose columns
+    are the transforms."""
+    bits, logn, poly, p, w = c["bits"], c["logn"], c["poly"], c["p"], c["batch"]
+    P = params(logn, poly, p)
+    h = 1 << logn
+    x = rng.integers(0, p, size=(h, w), dtype=np.uint64)
+    x[:, 0] = p - 1
+    fn = O.merge_intt if c["inverse"] else O.merge_ntt
+    want = fn(np.ascontiguousarray(x.T), P).reshape(w, h).T
+    lib.gpuntt_b200_force_generic_path(1 if c["generic"] else 0)
+    try:
+        if c["signed"] and not c["inverse"]:
+            sx = O.centered(x, p)
+            d = torch.from_numpy(np.ascontiguousarray(sx if bits == 64 else sx.astype(np.int32))).cuda()
+        else:
+            d = to_dev(x, bits)
+        out = d if c["inplace"] else torch.zeros_like(d)
+        capi.merge_ntt(in_ptr=d.data_ptr(), out_ptr=out.data_ptr(), table_ptr=to_dev(P.inv_br if c["inverse"] else P.fwd_br, bits).data_ptr(),
+                       n_power=logn, batch=w, element_bits=bits, direction=capi.INVERSE if c["inverse"] else capi.FORWARD,
+                       reduction_poly=poly, layout=capi.PerCoefficient, modulus=p, mod_inverse=P.n_inv if c["inverse"] else 0,
+                       is_signed=c["signed"], stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        if c["signed"] and c["inverse"]:
+            return bool((to_host_signed(out).reshape(h, w) == O.centered(want, p).reshape(h, w)).all())
+        return bool((to_host(out, bits).reshape(h, w) == want).all())
+    finally:
+        lib.gpuntt_b200_force_generic_path(0)
+
+
 fs_cache = {}
 
 
@@ -254,17 +303,17 @@ def main():
     kinds = {}
     while time.time() - t0 < budget:
         u = rng.random()
-        rns, fs = u < 0.3, (u >= 0.3 and u < 0.3 + fourstep_share)
-        c = pick_rns_case() if rns else pick_4step_case() if fs else pick_case()
+        rns, fs, pc = u < 0.3, (u >= 0.3 and u < 0.3 + fourstep_share), u >= 0.9
+        c = pick_rns_case() if rns else pick_4step_case() if fs else pick_percoeff_case() if pc else pick_case()
         if c is None:
             continue
         try:
-            ok = run_rns_case(c) if rns else run_4step_case(c) if fs else run_case(c)
+            ok = run_rns_case(c) if rns else run_4step_case(c) if fs else run_percoeff_case(c) if pc else run_case(c)
         except Exception as e:  # an error code from the library is a finding as well
             ok = False
             c["error"] = repr(e)[:200]
         done += 1
-        k = (c["bits"], "inv" if c["inverse"] else "fwd", "rns" if rns else "4step" if fs else "signed" if c["signed"] else "unsigned",
+        k = (c["bits"], "inv" if c["inverse"] else "fwd", "rns" if rns else "4step" if fs else "percoeff" if pc else "signed" if c["signed"] else "unsigned",
              "generic" if c["generic"] else "tuned")
         kinds[k] = kinds.get(k, 0) + 1
         if not ok:
