@@ -643,6 +643,9 @@ namespace gpuntt_b200
     cudaError_t fast_per_coefficient(const uint64_t* in, uint64_t* out, const uint64_t* table, uint64_t p, uint64_t ninv, int n_power,
                                      int col_log, int plus, bool inverse, int signed_io, cudaStream_t st, int* launched,
                                      void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t));
+    cudaError_t fast_per_coefficient32(const uint32_t* in, uint32_t* out, const uint32_t* table, uint32_t p, uint32_t ninv, int n_power,
+                                       int col_log, int plus, bool inverse, int signed_io, cudaStream_t st, int* launched,
+                                       void (*prof_begin)(int, cudaStream_t), void (*prof_end)(cudaStream_t)); // merge_fast_pc32.cu
     void fused_set_lag_steps(int v); // merge_fused.cu
     void fused_set_policy(int v);
     void fused_set_small_tile_elems(long long v);
@@ -1023,6 +1026,19 @@ namespace gpuntt_b200
                                                       (uint64_t) d->mod_inverse_value, n, col_log, plus ? 1 : 0, inv, d->is_signed ? 1 : 0, st,
                                                       &launched, prof_begin, prof_end);
                 if (fe != cudaSuccess) return cuda_fail(fe, "fast_pass_kernel (PerCoefficient) launch");
+                if (launched > 0) return GPUNTT_B200_OK;
+            }
+        }
+        else
+        {
+            if (col_log > 0 && !rns && !g_force_generic.load())
+            {
+                int launched = 0;
+                cudaError_t fe = fast_per_coefficient32(reinterpret_cast<const uint32_t*>(d->in), reinterpret_cast<uint32_t*>(d->out),
+                                                        reinterpret_cast<const uint32_t*>(d->root_of_unity_table), (uint32_t) d->modulus_value,
+                                                        (uint32_t) d->mod_inverse_value, n, col_log, plus ? 1 : 0, inv, d->is_signed ? 1 : 0, st,
+                                                        &launched, prof_begin, prof_end);
+                if (fe != cudaSuccess) return cuda_fail(fe, "fast_pass_kernel (PerCoefficient, 32-bit) launch");
                 if (launched > 0) return GPUNTT_B200_OK;
             }
         }

@@ -698,14 +698,22 @@ def test_per_coefficient_layout(bits, poly, logh, w):
 
 
 @pytest.mark.parametrize("poly", [O.X_N_plus, O.X_N_minus])
-@pytest.mark.parametrize("logh,w,launches", [(4, 256, 1), (5, 128, 1), (6, 64, 1), (7, 4096, 1), (8, 16, 1), (8, 2048, 1), (9, 256, 2), (9, 4096, 2)])
-def test_per_coefficient_on_tuned_kernels(poly, logh, w, launches):
-    """64-bit PerCoefficient calls whose batch is at least one tile wide run as strided passes of the tuned kernels (one pass up
-    to H = 256, two for H = 512): launch count asserted, every word against the oracle, in place and out of place, and the
-    generic kernel gives the same words."""
-    bits = 64
+@pytest.mark.parametrize("bits,logh,w,launches", [(64, 4, 256, 1), (64, 5, 128, 1), (64, 6, 64, 1), (64, 7, 4096, 1), (64, 8, 16, 1),
+                                                  (64, 8, 2048, 1), (64, 9, 256, 2), (64, 9, 4096, 2),
+                                                  (32, 3, 1024, 1), (32, 4, 512, 1), (32, 5, 256, 1), (32, 6, 128, 1), (32, 7, 4096, 1),
+                                                  (32, 8, 32, 1), (32, 8, 2048, 1), (32, 9, 512, 2), (32, 9, 4096, 2),
+                                                  (32, -7, 4096, 1), (32, -9, 1024, 2)])
+def test_per_coefficient_on_tuned_kernels(poly, bits, logh, w, launches):
+    """PerCoefficient calls whose batch is at least one tile wide run as strided passes of the tuned kernels (one pass up to H = 256,
+    two for H = 512): launch count asserted, every word against the oracle, in place and out of place, and the generic kernel gives
+    the same words.  (32-bit, negative logh: a 30-bit prime, i.e. the exact-policy forward kernels instead of the lazy ones.)"""
+    if logh < 0:
+        from tests.test_moduli_gpu import custom_params, ntt_prime_below
+        logh = -logh
+        P = custom_params(logh, poly, ntt_prime_below((1 << 30) - 1, 2 << logh))
+    else:
+        P = O.merge_params(logh, poly, bits)
     h = 1 << logh
-    P = O.merge_params(logh, poly, bits)
     x = O.example_input(P.modulus, h * w, seed=logh * 3 + w).reshape(h, w)
     want = O.merge_ntt(np.ascontiguousarray(x.T), P).reshape(w, h).T
     s = torch.cuda.current_stream().cuda_stream

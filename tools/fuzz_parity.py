@@ -4,7 +4,7 @@ random (width, ring size, ring type, batch, modulus anywhere in the accepted ran
 tuned / generic kernels, single-launch knob; three cases in ten through the RNS overloads with 1..5 random moduli, a
 share through GPU_4STEP_NTT in both I/O contracts and directions, one in ten in NTTLayout::PerCoefficient) with extreme
 inputs mixed in; every output word is compared with NTTCPU's
-restatement.  Usage: fuzz_parity.py [seconds] [seed] [4-step share].  Prints one JSON line per mismatch and a summary line; exit code 1 on
+restatement.  Usage: fuzz_parity.py [seconds] [seed] [4-step share] [PerCoefficient share].  Prints one JSON line per mismatch and a summary line; exit code 1 on
 any mismatch."""
 import json
 import os
@@ -24,6 +24,7 @@ from tests.test_moduli_gpu import custom_params, ntt_prime_below  # noqa: E402
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 fourstep_share = float(sys.argv[3]) if len(sys.argv) > 3 else 0.1     # share of the cases that go through GPU_4STEP_NTT
+percoeff_share = float(sys.argv[4]) if len(sys.argv) > 4 else 0.1     # ... in NTTLayout::PerCoefficient
 rng = np.random.default_rng(seed)
 lib = capi.lib()
 params_cache = {}
@@ -303,7 +304,7 @@ def main():
     kinds = {}
     while time.time() - t0 < budget:
         u = rng.random()
-        rns, fs, pc = u < 0.3, (u >= 0.3 and u < 0.3 + fourstep_share), u >= 0.9
+        rns, fs, pc = u < 0.3, (u >= 0.3 and u < 0.3 + fourstep_share), u >= 1.0 - percoeff_share
         c = pick_rns_case() if rns else pick_4step_case() if fs else pick_percoeff_case() if pc else pick_case()
         if c is None:
             continue

@@ -144,15 +144,15 @@ def fourstep_case(name, logn, batch, iters, contract, inverse=False):
     torch.cuda.empty_cache()
 
 
-def percoef_case(name, logh, w, iters):
+def percoef_case(name, logh, w, iters, bits=64):
     """NTTLayout::PerCoefficient: one [2^logh][w] matrix, every column a transform; tuned strided passes vs the generic kernel"""
-    P = NTTParameters(logh, X_N_plus, 64)
-    tab = dev(P.gpu_root_of_unity_table_generator(P.forward_root_of_unity_table), 64)
-    x = torch.randint(0, P.modulus, (1 << logh, w), dtype=torch.int64, device="cuda")
+    P = NTTParameters(logh, X_N_plus, bits)
+    tab = dev(P.gpu_root_of_unity_table_generator(P.forward_root_of_unity_table), bits)
+    x = torch.randint(0, P.modulus, (1 << logh, w), dtype=torch.int64 if bits == 64 else torch.int32, device="cuda")
     s = torch.cuda.current_stream().cuda_stream
 
     def fn():
-        capi.merge_ntt(in_ptr=x.data_ptr(), out_ptr=x.data_ptr(), table_ptr=tab.data_ptr(), n_power=logh, batch=w, element_bits=64,
+        capi.merge_ntt(in_ptr=x.data_ptr(), out_ptr=x.data_ptr(), table_ptr=tab.data_ptr(), n_power=logh, batch=w, element_bits=bits,
                        direction=capi.FORWARD, reduction_poly=X_N_plus, layout=capi.PerCoefficient, modulus=P.modulus, stream=s)
     res = {}
     for tag, generic in (("tuned", 0), ("generic", 1)):
@@ -161,9 +161,9 @@ def percoef_case(name, logh, w, iters):
         if not generic:
             launches = capi.lib().gpuntt_b200_last_launch_count()
     capi.lib().gpuntt_b200_force_generic_path(0)
-    bytes_alg = 2 * (1 << logh) * 8 * w
+    bytes_alg = 2 * (1 << logh) * (bits // 8) * w
     gbs = bytes_alg / (res["tuned"] * 1e-3) / 1e9
-    print(json.dumps({"case": name, "logn": logh, "batch": w, "bits": 64, "layout": "PerCoefficient", "ms": round(res["tuned"], 4),
+    print(json.dumps({"case": name, "logn": logh, "batch": w, "bits": bits, "layout": "PerCoefficient", "ms": round(res["tuned"], 4),
                       "ms_generic_kernel": round(res["generic"], 4), "launches": launches, "ntt_per_s": round(w / (res["tuned"] * 1e-3), 1),
                       "alg_GBps": round(gbs, 1), "frac_hbm": round(gbs / peak(), 4)}), flush=True)
 
@@ -171,9 +171,16 @@ def percoef_case(name, logh, w, iters):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--percoeff-only", action="store_true")
     args = ap.parse_args()
     it = 5 if args.quick else 20
     capi.lib()
+    if args.percoeff_only:
+        percoef_case("PerCoefficient 2^9 x 131072 (X^N+1)", 9, 131072, it)
+        percoef_case("PerCoefficient Data32 2^9 x 262144 (X^N+1)", 9, 262144, it, bits=32)
+        percoef_case("PerCoefficient Data32 2^8 x 524288 (X^N+1)", 8, 524288, it, bits=32)
+        percoef_case("PerCoefficient Data32 2^9 x 1024 (the reference example's shape)", 9, 1024, it, bits=32)
+        return
     merge_case("C2 fwd", 16, 1024, 64, X_N_minus, it)
     merge_case("C2 inv", 16, 1024, 64, X_N_minus, it, inverse=True)
     merge_case("C2 negacyclic fwd", 16, 1024, 64, X_N_plus, it)
@@ -188,6 +195,8 @@ def main():
     percoef_case("PerCoefficient 2^9 x 131072 (X^N+1)", 9, 131072, it)
     percoef_case("PerCoefficient 2^8 x 262144 (X^N+1)", 8, 262144, it)
     percoef_case("PerCoefficient 2^9 x 1024 (the reference example's shape)", 9, 1024, it)
+    percoef_case("PerCoefficient Data32 2^9 x 262144 (X^N+1)", 9, 262144, it, bits=32)
+    percoef_case("PerCoefficient Data32 2^8 x 524288 (X^N+1)", 8, 524288, it, bits=32)
     if not args.quick:
         for logn in (8, 10, 11, 12, 13, 14, 15, 17, 18, 20, 22, 24):
             merge_case(f"u64 logN={logn}", logn, max(1, (1 << 26) >> logn), 64, X_N_minus, it)
