@@ -111,6 +111,16 @@ def reference_gpu_same_box():
     return None
 
 
+def workload_config(world):
+    """`config` of the JSON line: the workload, identical for the GPU arm and the reference arm (what is specific to the GPU
+    implementation -- the launch plan -- sits beside it under "plan")."""
+    return {"workload": WORKLOAD, "batch_per_gpu": BATCH,
+            "l2": "inputs (512 MiB per GPU) larger than the 126 MB L2; no flush",
+            "input": "seed-0 std::mt19937 + uniform_int_distribution stream of the reference examples, polynomials "
+                     f"[{BATCH}*rank, {BATCH}*(rank+1)); timed steps re-run on the transformed data (values stay < p)",
+            "partition": f"batch slices, {world} x {BATCH} polynomials, no collective"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -126,13 +136,15 @@ def run_reference_arm(args):
         rate, _, kind = cpu_reference_rate(per_step, threads, seed=s)
         total_t += per_step / rate
     value = per_step * args.steps / total_t
-    sample = f"{per_step} of the {BATCH} polynomials per step, NTTCPU<Data64>::ntt N=2^16 on {threads} host threads"
+    sample = (f"{per_step} of the {BATCH} polynomials per step (the head of the examples' mt19937 stream, seeded with the step index), "
+              f"NTTCPU<Data64>::ntt N=2^16 on {threads} host threads")
     emit_line(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference CPU implementation on host cores; step = bounded sample"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "config": workload_config(args.gpus),   # the same workload as the GPU arm, key for key
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": sample + " (reference CPU implementation on host cores; step = bounded sample)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -398,11 +410,8 @@ def run_b200_arm(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "l2": "inputs (512 MiB per GPU) larger than the 126 MB L2; no flush",
-                   "plan": capi.describe_plan(LOGN, BITS).strip(), "batch_per_gpu": BATCH, "launches_per_step": launches_per_step,
-                   "input": "seed-0 std::mt19937 + uniform_int_distribution stream of the reference examples, polynomials "
-                            f"[{BATCH}*rank, {BATCH}*(rank+1)); timed steps re-run on the transformed data (values stay < p)",
-                   "partition": f"batch slices, {world} x {BATCH} polynomials, no collective"},
+        "config": workload_config(world),
+        "plan": {"passes": capi.describe_plan(LOGN, BITS).strip(), "launches_per_step": launches_per_step},
         "parity_gate": gate,
         "clocks": clocks,
         "e2e": {"value": world * BATCH * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": nbytes + h_tab.nbytes,
