@@ -215,8 +215,9 @@ void gpuntt_b200_force_generic_path(int on);
  *                 kernel on 1024-element tiles instead of 4096-element ones -- four times the CTAs, a quarter of the work on the
  *                 critical path of a launch-bound call.  0: never. */
 #define GPUNTT_B200_TUNE_SMALL_TILE_ELEMS 7
-/*   SINGLE_POLY_TILES  1 (default): a call with ONE 64-bit polynomial of a ring above 2^16 runs its contiguous pass on
- *                 2048-element tiles of that polynomial (a two-polynomial tile would be half zero fill); 0: the usual tiles. */
+/*   SINGLE_POLY_TILES  1 (default): a call with ONE polynomial of a ring that takes three or more passes (64-bit: above 2^16,
+ *                 32-bit: above 2^18) runs its contiguous pass on 2048- / 4096-element tiles of that polynomial (a two-polynomial
+ *                 tile would be half zero fill); 0: the usual tiles. */
 #define GPUNTT_B200_TUNE_SINGLE_POLY_TILES 8
 void gpuntt_b200_tune(int knob, int value);
 
