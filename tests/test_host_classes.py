@@ -1,0 +1,65 @@
+"""CPU-only: the host classes a GPU-NTT caller builds its tables with are the reference's, value for value.  tests/host_classes_probe.cu
+prints every public member of NTTParameters<T> / NTTParameters4Step<T> (primes, roots, n^-1, table hashes, the bit-reversed device
+tables) and hashes of what NTTCPU / NTT_4STEP_CPU / schoolbook_poly_multiplication compute, for Data32 and Data64, both ring types,
+logN 1..13 (merge) and 12..17 (4-step).  It is compiled against include/gpuntt + gpu_ntt_b200/lib/libntt-1.0.a and its output compared
+line for line with tests/golden/host_classes.txt -- the output of the SAME source compiled against the reference's headers and the
+reference's own CPU sources (nttparameters.cu, ntt_cpu.cu, ntt_4step_cpu.cu, common.cu), regenerated and re-checked live wherever
+/root/reference exists.  One member is masked: NTTParameters4Step::n_inv_gpu is never assigned by the reference's constructor
+(n_inverse_generator_gpu() is defined, nttparameters.cu:451-454, but not called), so the reference prints uninitialised memory there;
+this library sets it to n^-1."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+CUDA = "/usr/local/cuda"
+NVCC = os.path.join(CUDA, "bin", "nvcc")
+LIB = os.path.join(ROOT, "gpu_ntt_b200", "lib", "libntt-1.0.a")
+PROBE = os.path.join(ROOT, "tests", "host_classes_probe.cu")
+GOLDEN = os.path.join(ROOT, "tests", "golden", "host_classes.txt")
+
+pytestmark = pytest.mark.skipif(not os.path.exists(NVCC) or shutil.which("g++") is None, reason="needs g++ and nvcc (link of the static library)")
+
+
+def mask(text):
+    return re.sub(r"n_inv_gpu=\d+", "n_inv_gpu=*", text)
+
+
+def ours(tmp_path):
+    if not os.path.exists(LIB):
+        subprocess.check_call(["bash", os.path.join(ROOT, "gpu_ntt_b200", "build_cxx.sh")])
+    obj, exe = str(tmp_path / "probe_ours.o"), str(tmp_path / "probe_ours")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-w", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(CUDA, "include"),
+                           "-x", "c++", "-c", PROBE, "-o", obj])
+    subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe, obj, LIB, "-cudart", "static"])
+    return subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+
+
+def test_host_classes_equal_the_reference_golden(tmp_path):
+    out = ours(tmp_path)
+    want = open(GOLDEN).read()
+    got = mask(out).splitlines()
+    for i, (a, b) in enumerate(zip(want.splitlines(), got)):
+        assert a == b, f"line {i + 1}:\nreference: {a}\nthis repo: {b}"
+    assert len(got) == len(want.splitlines()) == 157
+    # the masked member: n^-1 here (the reference leaves it unassigned)
+    for ln in out.splitlines():
+        m = re.search(r" n_inv=(\d+) n_inv_gpu=(\d+)", ln)
+        if m:
+            assert m.group(1) == m.group(2), ln
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src", "lib")), reason="reference sources not present")
+def test_golden_is_what_the_reference_sources_print(tmp_path):
+    exe = str(tmp_path / "probe_ref")
+    srcs = [os.path.join(REF, "src", "lib", p) for p in ("common/common.cu", "common/nttparameters.cu", "ntt_merge/ntt_cpu.cu",
+                                                         "ntt_4step/ntt_4step_cpu.cu")]
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-w", "-I", os.path.join(REF, "src", "include"), "-I", os.path.join(CUDA, "include"),
+                           "-x", "c++", PROBE] + srcs + ["-o", exe, "-L", os.path.join(CUDA, "lib64"), "-lcudart_static", "-ldl", "-lrt",
+                                                         "-lpthread"])
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    assert mask(out) == open(GOLDEN).read()
