@@ -82,8 +82,60 @@ template <typename T> static void fourstep(const char* name, int logn)
                 (int) (cpu.intt(fa) == a));
 }
 
+// Modulus<T>(value) and the host Barrett helpers (modular_arith.cuh:28-158 of the reference) on canonical operands
+template <typename T> static void arith(const char* name, ull value)
+{
+    Modulus<T> m((T) value);
+    std::vector<T> a = input<T>(20000, (T) value, value % 1000), b = input<T>(20000, (T) value, value % 777 + 3);
+    a[0] = (T) (value - 1);
+    b[0] = (T) (value - 1);
+    a[1] = 0;
+    b[2] = 1;
+    ull h_add = 7, h_sub = 7, h_mul = 7, h_red = 7, h_exp = 7, h_inv = 7;
+    for (size_t i = 0; i < a.size(); i++)
+    {
+        h_add = h_add * 1000003ull + (ull) OPERATOR<T>::add(a[i], b[i], m);
+        h_sub = h_sub * 1000003ull + (ull) OPERATOR<T>::sub(a[i], b[i], m);
+        h_mul = h_mul * 1000003ull + (ull) OPERATOR<T>::mult(a[i], b[i], m);
+        h_red = h_red * 1000003ull + (ull) OPERATOR<T>::reduce(a[i], m);
+        if (i < 300)
+        {
+            h_exp = h_exp * 1000003ull + (ull) OPERATOR<T>::exp(a[i], b[i], m);
+            if (a[i] != 0) h_inv = h_inv * 1000003ull + (ull) OPERATOR<T>::modinv(a[i], m);
+        }
+    }
+    std::printf("%s modulus %llu bit=%llu mu=%llu | add %llu sub %llu mult %llu reduce %llu exp %llu modinv %llu\n", name, (ull) m.value,
+                (ull) m.bit, (ull) m.mu, h_add, h_sub, h_mul, h_red, h_exp, h_inv);
+}
+
+// NTTParameters(LOGN, NTTFactors, poly): the caller's own prime and roots (nttparameters.cu:51-78 of the reference)
+template <typename T> static void factors(const char* name, int logn, ReductionPolynomial poly)
+{
+    NTTParameters<T> D(logn, poly);
+    NTTFactors<T> f(D.modulus, D.omega, D.psi);
+    NTTParameters<T> P(logn, f, poly);
+    std::printf("%s factors logn=%d poly=%d | n=%llu p=%llu omega=%llu psi=%llu n_inv=%llu root=%llu iroot=%llu size=%llu tables %llu %llu same_as_default %d\n",
+                name, P.logn, (int) P.poly_reduction, (ull) P.n, (ull) P.modulus.value, (ull) P.omega, (ull) P.psi, (ull) P.n_inv,
+                (ull) P.root_of_unity, (ull) P.inverse_root_of_unity, (ull) P.root_of_unity_size, fold(P.forward_root_of_unity_table),
+                fold(P.inverse_root_of_unity_table), (int) (P.forward_root_of_unity_table == D.forward_root_of_unity_table));
+}
+
 int main()
 {
+    for (ull v : {12289ull, 65537ull, 469762049ull, 536870909ull, 1073741789ull /* largest prime below 2^30 */})
+        arith<Data32>("u32", v);
+    // (largest primes below 2^60 - 2^20, 2^61 - 2^20, 2^62 - 2^20.  Not closer to the power of two: the reference derives Modulus::bit
+    // from a floating-point log2, modular_arith.cuh:46, which rounds values within 2^(k-54) of 2^k up to k + 1 bits -- 2^61 - 1 gets
+    // bit = 62 and a mu that overflows 64 bits there; this library uses the exact bit length)
+    for (ull v : {12289ull, 469762049ull, 1099511627689ull, 576460756061519873ull, 1152921504605798393ull, 2305843009212645239ull,
+                  4611686018426339311ull})
+        arith<Data64>("u64", v);
+    for (int logn : {4, 11, 14})
+        for (ReductionPolynomial poly : {X_N_minus, X_N_plus})
+        {
+            factors<Data64>("u64", logn, poly);
+            factors<Data32>("u32", logn, poly);
+        }
     for (int logn : {1, 2, 3, 5, 8, 10, 12, 13})
         for (ReductionPolynomial poly : {X_N_minus, X_N_plus})
         {

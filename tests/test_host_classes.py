@@ -45,7 +45,7 @@ def test_host_classes_equal_the_reference_golden(tmp_path):
     got = mask(out).splitlines()
     for i, (a, b) in enumerate(zip(want.splitlines(), got)):
         assert a == b, f"line {i + 1}:\nreference: {a}\nthis repo: {b}"
-    assert len(got) == len(want.splitlines()) == 157
+    assert len(got) == len(want.splitlines()) == 181
     # the masked member: n^-1 here (the reference leaves it unassigned)
     for ln in out.splitlines():
         m = re.search(r" n_inv=(\d+) n_inv_gpu=(\d+)", ln)
