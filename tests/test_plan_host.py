@@ -26,6 +26,22 @@ def test_library_exports_every_declared_symbol():
     assert L.gpuntt_b200_version() == 100
 
 
+def test_plain_c_caller_compiles_links_and_runs(tmp_path):
+    """include/gpuntt_b200.h is valid C11 (-pedantic) and the shared library links into a C program: what a cgo / JNI / N-API
+    binding of INTEGRATION.md builds on.  tests/c_caller.c only makes calls that return before any CUDA work."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    capi.lib()
+    libdir = os.path.join(ROOT, "gpu_ntt_b200", "lib")
+    exe = str(tmp_path / "c_caller")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_caller.c"), "-o", exe, "-L", libdir, "-lgpuntt_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "c caller ok" in out.stdout, out.stdout + out.stderr
+
+
 def test_argument_validation_without_gpu():
     """Error behaviour mirrors the reference's exceptions (ntt.cu:2088-2091, 2253) as status codes."""
     with pytest.raises(G.GpuNttError) as e:
