@@ -63,3 +63,27 @@ def test_golden_is_what_the_reference_sources_print(tmp_path):
                                                          "-lpthread"])
     out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
     assert mask(out) == open(GOLDEN).read()
+
+
+ERRORS_PROBE = os.path.join(ROOT, "tests", "cxx_errors_probe.cu")
+REF_GPU_LIB = os.path.join(ROOT, "oracle", "_ref", "libntt_ref_gpu.a")
+
+
+def _errors_probe(tmp_path, inc, lib, arch, tag):
+    obj, exe = str(tmp_path / f"errors_{tag}.o"), str(tmp_path / f"errors_{tag}")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-w", "-I", inc, "-I", os.path.join(CUDA, "include"), "-x", "c++", "-c", ERRORS_PROBE,
+                           "-o", obj])
+    subprocess.check_call([NVCC, "-gencode", arch, "-o", exe, obj, lib, "-cudart", "static"])
+    return subprocess.run([exe], capture_output=True, text=True)
+
+
+def test_cxx_entry_points_throw_what_the_reference_throws(tmp_path):
+    """std::invalid_argument with the reference's messages, before any CUDA work (no GPU needed); where the reference's own library
+    was built here (oracle/_ref/libntt_ref_gpu.a, `make -C oracle refgpu`) the same probe linked against it prints the same lines."""
+    if not os.path.exists(LIB):
+        subprocess.check_call(["bash", os.path.join(ROOT, "gpu_ntt_b200", "build_cxx.sh")])
+    mine = _errors_probe(tmp_path, os.path.join(ROOT, "include"), LIB, "arch=compute_100a,code=sm_100a", "ours")
+    assert mine.returncode == 0 and "cxx errors ok" in mine.stdout, mine.stdout + mine.stderr
+    if os.path.exists(REF_GPU_LIB) and os.path.isdir(os.path.join(REF, "src", "include")):
+        ref = _errors_probe(tmp_path, os.path.join(REF, "src", "include"), REF_GPU_LIB, "arch=compute_100,code=sm_100", "ref")
+        assert ref.returncode == 0 and ref.stdout == mine.stdout, ref.stdout + ref.stderr
