@@ -15,24 +15,26 @@
 namespace gpuntt
 {
     // what(): "CUDA Error in <file> at line <n>: <cudaGetErrorString>"  (common.cuh:20-40 of the reference)
+    // Object layout = the reference's (file, line, error, text, in that order): the class is header-inline on both sides, so a
+    // caller object compiled against the reference's header and this library must agree on it (one vtable, one what()).
     class CudaException : public std::exception
     {
       public:
-        CudaException(const std::string& file, int line, cudaError_t error)
-            : text_("CUDA Error in " + file + " at line " + std::to_string(line) + ": " + cudaGetErrorString(error)), error_(error)
-        {
-        }
+        CudaException(const std::string& file, int line, cudaError_t error) : file_(file), line_(line), error_(error) {}
         // engine-side failures arrive as text from the C ABI (gpuntt_b200_last_error)
         CudaException(const std::string& file, int line, const std::string& message)
-            : text_("CUDA Error in " + file + " at line " + std::to_string(line) + ": " + message), error_(cudaErrorUnknown)
+            : file_(file), line_(line), error_(cudaErrorUnknown),
+              m_error_string("CUDA Error in " + file + " at line " + std::to_string(line) + ": " + message)
         {
         }
-        const char* what() const noexcept override { return text_.c_str(); }
+        const char* what() const noexcept override { return m_error_string.c_str(); }
         cudaError_t code() const noexcept { return error_; }
 
       private:
-        std::string text_;
+        std::string file_;
+        int line_;
         cudaError_t error_;
+        std::string m_error_string = "CUDA Error in " + file_ + " at line " + std::to_string(line_) + ": " + cudaGetErrorString(error_);
     };
 
 #define GPUNTT_CUDA_CHECK(err)                                                                                         \

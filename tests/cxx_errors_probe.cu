@@ -78,9 +78,46 @@ template <typename T, typename TS> static int run(const char* name)
     return bad;
 }
 
+// No usable device (the build container): a VALID call cannot run, and there is no CPU fallback -- it must end in
+// gpuntt::CudaException ("CUDA Error in <file> at line <n>: ...", common.cuh:20-50 of the reference).  The class is header-inline, so
+// this also runs as a MIXED build: this file compiled against the reference's header, linked against this repository's library.
+static int no_device()
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) == cudaSuccess && count > 0)
+    {
+        std::printf("-- a device is present: no-device section skipped\n");
+        return 0;
+    }
+    static Data64 buf[4096], tab[2048];
+    ntt_configuration<Data64> c{};
+    c.n_power = 12;
+    c.ntt_layout = PerPolynomial;
+    c.reduction_poly = X_N_minus;
+    c.stream = 0;
+    Modulus<Data64> m(576460756061519873ULL);
+    try
+    {
+        GPU_NTT_Inplace<Data64>(buf, tab, m, c, 1);
+    }
+    catch (const CudaException& e)
+    {
+        const bool ok = std::string(e.what()).rfind("CUDA Error in ", 0) == 0;
+        std::printf("%-58s %s\n", "valid call without a device: gpuntt::CudaException", ok ? "ok" : "WRONG TEXT");
+        return ok ? 0 : 1;
+    }
+    catch (const std::exception& e)
+    {
+        std::printf("valid call without a device: WRONG TYPE (\"%s\")\n", e.what());
+        return 1;
+    }
+    std::printf("valid call without a device: NO EXCEPTION\n");
+    return 1;
+}
+
 int main()
 {
-    int bad = run<Data64, Data64s>("Data64") + run<Data32, Data32s>("Data32");
+    int bad = run<Data64, Data64s>("Data64") + run<Data32, Data32s>("Data32") + no_device();
     std::printf("%s\n", bad ? "FAILED" : "cxx errors ok");
     return bad;
 }

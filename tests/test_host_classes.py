@@ -84,6 +84,11 @@ def test_cxx_entry_points_throw_what_the_reference_throws(tmp_path):
         subprocess.check_call(["bash", os.path.join(ROOT, "gpu_ntt_b200", "build_cxx.sh")])
     mine = _errors_probe(tmp_path, os.path.join(ROOT, "include"), LIB, "arch=compute_100a,code=sm_100a", "ours")
     assert mine.returncode == 0 and "cxx errors ok" in mine.stdout, mine.stdout + mine.stderr
-    if os.path.exists(REF_GPU_LIB) and os.path.isdir(os.path.join(REF, "src", "include")):
-        ref = _errors_probe(tmp_path, os.path.join(REF, "src", "include"), REF_GPU_LIB, "arch=compute_100,code=sm_100", "ref")
-        assert ref.returncode == 0 and ref.stdout == mine.stdout, ref.stdout + ref.stderr
+    if os.path.isdir(os.path.join(REF, "src", "include")):
+        # mixed build: the caller compiled against the REFERENCE's headers, linked against this library (an already-compiled
+        # GPU-NTT caller relinked) -- same lines, including the header-inline CudaException caught across the boundary
+        mixed = _errors_probe(tmp_path, os.path.join(REF, "src", "include"), LIB, "arch=compute_100a,code=sm_100a", "mixed")
+        assert mixed.returncode == 0 and mixed.stdout == mine.stdout, mixed.stdout + mixed.stderr
+        if os.path.exists(REF_GPU_LIB):
+            ref = _errors_probe(tmp_path, os.path.join(REF, "src", "include"), REF_GPU_LIB, "arch=compute_100,code=sm_100", "ref")
+            assert ref.returncode == 0 and ref.stdout == mine.stdout, ref.stdout + ref.stderr
