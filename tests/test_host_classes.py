@@ -53,6 +53,21 @@ def test_host_classes_equal_the_reference_golden(tmp_path):
             assert m.group(1) == m.group(2), ln
 
 
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src", "include")), reason="reference headers not present")
+def test_mixed_build_reference_headers_with_this_library(tmp_path):
+    """An already-compiled GPU-NTT caller relinked: the probe compiled against the REFERENCE's headers and linked against
+    libntt-1.0.a.  Class layouts (NTTParameters, NTTParameters4Step, NTTCPU, NTT_4STEP_CPU, Modulus) and every out-of-line member
+    must agree across the boundary -- the output is the golden file again."""
+    if not os.path.exists(LIB):
+        subprocess.check_call(["bash", os.path.join(ROOT, "gpu_ntt_b200", "build_cxx.sh")])
+    obj, exe = str(tmp_path / "probe_mixed.o"), str(tmp_path / "probe_mixed")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-w", "-I", os.path.join(REF, "src", "include"), "-I", os.path.join(CUDA, "include"),
+                           "-x", "c++", "-c", PROBE, "-o", obj])
+    subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe, obj, LIB, "-cudart", "static"])
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    assert mask(out) == open(GOLDEN).read()
+
+
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src", "lib")), reason="reference sources not present")
 def test_golden_is_what_the_reference_sources_print(tmp_path):
     exe = str(tmp_path / "probe_ref")
