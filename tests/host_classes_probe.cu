@@ -58,7 +58,7 @@ template <typename T> static void merge(const char* name, int logn, ReductionPol
     }
 }
 
-template <typename T> static void fourstep(const char* name, int logn)
+template <typename T> static void fourstep(const char* name, int logn, bool transforms = true)
 {
     NTTParameters4Step<T> P(logn, X_N_minus);
     std::printf("%s 4step logn=%d | n=%llu p=%llu bit=%llu mu=%llu omega=%llu psi=%llu n_inv=%llu n_inv_gpu=%llu root=%llu iroot=%llu size=%llu n1=%d n2=%d\n",
@@ -71,6 +71,7 @@ template <typename T> static void fourstep(const char* name, int logn)
                 P.n2_based_inverse_root_of_unity_table.size(), fold(P.n2_based_inverse_root_of_unity_table),
                 P.W_inverse_root_of_unity_table.size(), fold(P.W_inverse_root_of_unity_table),
                 fold(P.gpu_root_of_unity_table_generator(P.n2_based_root_of_unity_table)));
+    if (!transforms) return; // (the large shapes: parameters and tables only)
     NTT_4STEP_CPU<T> cpu(P);
     std::vector<T> a = input<T>((size_t) 1 << logn, P.modulus.value, 5 + logn), b = input<T>((size_t) 1 << logn, P.modulus.value, 55 + logn);
     a[1] = P.modulus.value - 1;
@@ -147,6 +148,9 @@ int main()
         fourstep<Data64>("u64", logn);
         fourstep<Data32>("u32", logn);
     }
+    // every remaining shape of matrix_dimention() (nttparameters.cu:305-354), up to BASELINE config C4 (2^24 = 256 x 65536)
+    for (int logn : {18, 19, 20, 21, 22, 23, 24}) fourstep<Data64>("u64", logn, false);
+    for (int logn : {18, 20, 22, 24}) fourstep<Data32>("u32", logn, false);
     std::printf("bitreverse %d %d %d\n", bitreverse(1, 4), bitreverse(6, 3), bitreverse(1234, 12));
     return 0;
 }

@@ -1,7 +1,7 @@
 """CPU-only: the host classes a GPU-NTT caller builds its tables with are the reference's, value for value.  tests/host_classes_probe.cu
 prints every public member of NTTParameters<T> / NTTParameters4Step<T> (primes, roots, n^-1, table hashes, the bit-reversed device
 tables) and hashes of what NTTCPU / NTT_4STEP_CPU / schoolbook_poly_multiplication compute, for Data32 and Data64, both ring types,
-logN 1..13 (merge) and 12..17 (4-step).  It is compiled against include/gpuntt + gpu_ntt_b200/lib/libntt-1.0.a and its output compared
+logN 1..13 (merge) and 12..17 (4-step; parameters and tables of every shape up to 2^24).  It is compiled against include/gpuntt + gpu_ntt_b200/lib/libntt-1.0.a and its output compared
 line for line with tests/golden/host_classes.txt -- the output of the SAME source compiled against the reference's headers and the
 reference's own CPU sources (nttparameters.cu, ntt_cpu.cu, ntt_4step_cpu.cu, common.cu), regenerated and re-checked live wherever
 /root/reference exists.  One member is masked: NTTParameters4Step::n_inv_gpu is never assigned by the reference's constructor
@@ -45,7 +45,7 @@ def test_host_classes_equal_the_reference_golden(tmp_path):
     got = mask(out).splitlines()
     for i, (a, b) in enumerate(zip(want.splitlines(), got)):
         assert a == b, f"line {i + 1}:\nreference: {a}\nthis repo: {b}"
-    assert len(got) == len(want.splitlines()) == 181
+    assert len(got) == len(want.splitlines()) == 203
     # the masked member: n^-1 here (the reference leaves it unassigned)
     for ln in out.splitlines():
         m = re.search(r" n_inv=(\d+) n_inv_gpu=(\d+)", ln)
